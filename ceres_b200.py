@@ -1,0 +1,12 @@
+"""Import shim: the product package lives in ``ceres-solver-cuda_b200/`` (a name that
+is not a Python identifier); this module loads it under the name ``ceres_b200``."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ceres-solver-cuda_b200")
+_spec = importlib.util.spec_from_file_location(
+    "ceres_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["ceres_b200"] = _mod
+_spec.loader.exec_module(_mod)
