@@ -4,3 +4,4 @@ The product is C++/CUDA (``csrc/``, ``include/``); Python here only generates
 workloads (``problems``) and binds the test driver / C ABI for pytest and bench.py
 (``binding``)."""
 from . import problems  # noqa: F401
+from . import binding  # noqa: F401

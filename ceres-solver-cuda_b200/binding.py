@@ -1,0 +1,225 @@
+"""ctypes binding of the test/bench driver (tests/driver/libceres_b200_driver.so),
+which replays a ProblemSpec through the product's public C++ API and evaluates it
+through the C ABI (include/ceres_b200.h).  No oracle, no CPU fallback: on a machine
+without a CUDA device only the layout (structure) build works."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(ROOT, "ceres-solver-cuda_b200", "lib", "libceres_b200.so")
+DRIVER_PATH = os.path.join(ROOT, "tests", "driver", "libceres_b200_driver.so")
+_DRV = None
+_ABI = None
+
+# Every symbol include/ceres_b200.h declares.
+ABI_SYMBOLS = [
+    "cb200_engine_create", "cb200_engine_destroy", "cb200_engine_last_error",
+    "cb200_engine_set_parameter_blocks", "cb200_engine_add_residual_blocks",
+    "cb200_engine_set_layout", "cb200_engine_set_shard", "cb200_engine_finalize",
+    "cb200_nccl_unique_id", "cb200_engine_comm_init", "cb200_engine_evaluate",
+    "cb200_engine_evaluate_device", "cb200_engine_device_ptr", "cb200_engine_shard_info",
+    "cb200_engine_last_timing", "cb200_host_alloc", "cb200_host_free", "cb200_version",
+]
+
+
+def build(jobs=8):
+    """Compiles libceres_b200.so and the driver for sm_100a (nvcc cross-compiles on CPU)."""
+    subprocess.check_call(["make", "-C", ROOT, f"-j{jobs}", "all"], stdout=subprocess.DEVNULL)
+
+
+def abi():
+    global _ABI
+    if _ABI is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build() (no fallback)")
+        _ABI = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        _ABI.cb200_version.restype = C.c_char_p
+        _ABI.cb200_nccl_unique_id.argtypes = [C.c_void_p]
+    return _ABI
+
+
+def driver():
+    global _DRV
+    if _DRV is None:
+        abi()
+        if not os.path.exists(DRIVER_PATH):
+            raise RuntimeError(f"{DRIVER_PATH} is missing: run __graft_entry__.build()")
+        L = C.CDLL(DRIVER_PATH)
+        L.drv_create.restype = C.c_void_p
+        L.drv_create.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int]
+        L.drv_destroy.argtypes = [C.c_void_p]
+        L.drv_error.restype = C.c_char_p
+        L.drv_error.argtypes = [C.c_void_p]
+        L.drv_build.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]
+        L.drv_dims.argtypes = [C.c_void_p, C.c_void_p]
+        L.drv_fixed_cost.restype = C.c_double
+        L.drv_fixed_cost.argtypes = [C.c_void_p]
+        L.drv_initial_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.drv_get_ints.restype = C.c_int64
+        L.drv_get_ints.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.drv_pb_table.argtypes = [C.c_void_p, C.c_void_p]
+        L.drv_jacobian_values.restype = C.POINTER(C.c_double)
+        L.drv_jacobian_values.argtypes = [C.c_void_p]
+        L.drv_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int]
+        L.drv_evaluate_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.drv_timing.argtypes = [C.c_void_p, C.c_void_p]
+        L.drv_shard_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.drv_plus.argtypes = [C.c_void_p] * 4
+        L.drv_dense_jacobian.argtypes = [C.c_void_p, C.c_void_p]
+        _DRV = L
+    return _DRV
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = abi().cb200_nccl_unique_id(buf)
+    if rc != 0:
+        raise RuntimeError("cb200_nccl_unique_id failed (libnccl.so.2 not found?)")
+    return buf.raw
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+_INT_ARRAYS = {
+    "residual_layout": 0, "jacobian_per_residual_layout": 1, "jacobian_per_residual_offsets": 2,
+    "program_rbs": 3, "program_pbs": 4, "col_block_size": 5, "col_block_pos": 6,
+    "row_block_size": 7, "row_block_pos": 8, "row_cells_start": 9, "cell_block_id": 10,
+    "cell_position": 11, "crs_rows": 12, "crs_cols": 13, "constant_pbs": 14,
+    "jacobian_layout_storage": 15,
+}
+
+
+class CudaProblem:
+    """ProblemCUDA + Program + Evaluator for a ProblemSpec.
+
+    with_device=False builds only the program and the Jacobian structure (host code,
+    works without a GPU); evaluate() then raises."""
+
+    def __init__(self, spec, jacobian_format=0, reduce=True, schur_reorder=False,
+                 num_eliminate_blocks=None, with_device=True, device=0, rank=0, world_size=1,
+                 nccl_id: bytes | None = None, bulk=None):
+        L = driver()
+        self.spec = spec
+        if bulk is None:
+            bulk = spec.num_rb > 5000
+        self.h = L.drv_create(
+            spec.num_pb, _p(spec.pb_size), _p(spec.pb_values), _p(spec.pb_constant),
+            _p(spec.pb_manifold_kind), _p(spec.pb_manifold_param), spec.num_rb,
+            _p(spec.rb_type), _p(spec.rb_pb), _p(spec.rb_loss_kind), _p(spec.rb_loss_a),
+            _p(spec.rb_loss_b), _p(spec.fdata), int(bulk))
+        err = L.drv_error(self.h)
+        if err:
+            raise RuntimeError(err.decode())
+        ne = spec.num_eliminate_blocks if num_eliminate_blocks is None else num_eliminate_blocks
+        self.jacobian_format = jacobian_format
+        self.with_device = with_device
+        idbuf = C.create_string_buffer(nccl_id, 128) if nccl_id else None
+        ok = L.drv_build(self.h, int(reduce), int(schur_reorder), int(ne), int(jacobian_format),
+                         int(with_device), int(device), int(rank), int(world_size), idbuf)
+        if not ok:
+            raise RuntimeError("drv_build failed: " + L.drv_error(self.h).decode())
+        dims = np.zeros(10, dtype=np.int64)
+        L.drv_dims(self.h, _p(dims))
+        (self.num_parameters, self.num_effective_parameters, self.num_residuals,
+         self.num_residual_blocks, self.num_parameter_blocks, self.num_jacobian_values,
+         self.values_size, self.num_cells, self.offsets_size,
+         self.num_constant_parameters) = (int(x) for x in dims)
+        self.fixed_cost = float(L.drv_fixed_cost(self.h))
+        ptr = L.drv_jacobian_values(self.h)
+        # zero-copy view of the (pinned) values array of CreateJacobian()
+        self.jacobian_values = np.ctypeslib.as_array(ptr, shape=(max(self.values_size, 1),))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.jacobian_values = None
+            driver().drv_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ints(self, name):
+        L = driver()
+        n = L.drv_get_ints(self.h, _INT_ARRAYS[name], None)
+        out = np.zeros(max(n, 0), dtype=np.int32)
+        if n > 0:
+            L.drv_get_ints(self.h, _INT_ARRAYS[name], _p(out))
+        return out
+
+    def pb_table(self):
+        out = np.zeros((self.num_parameter_blocks, 4), dtype=np.int32)
+        driver().drv_pb_table(self.h, _p(out))
+        return out
+
+    def initial_state(self):
+        s = np.zeros(self.num_parameters)
+        driver().drv_initial_state(self.h, _p(s))
+        return s
+
+    def evaluate(self, state=None, residuals=True, gradient=True, jacobian=True,
+                 apply_loss_function=True, out_residuals=None, out_gradient=None):
+        """Evaluator::Evaluate with host buffers.  Returns (ok, cost, r, g, jacobian_values)."""
+        if not self.with_device:
+            raise RuntimeError("built without a device: there is no CPU fallback")
+        if state is None:
+            state = self.initial_state()
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        cost = np.zeros(1)
+        r = g = None
+        if residuals:
+            r = out_residuals if out_residuals is not None else np.full(self.num_residuals, np.nan)
+        if gradient:
+            g = out_gradient if out_gradient is not None else \
+                np.full(self.num_effective_parameters, np.nan)
+        rc = driver().drv_evaluate(self.h, _p(state), int(apply_loss_function), _p(cost), _p(r),
+                                   _p(g), int(jacobian))
+        if rc < 0:
+            raise RuntimeError("no evaluator")
+        j = self.jacobian_values[:self.values_size] if jacobian else None
+        return bool(rc), float(cost[0]), r, g, j
+
+    def evaluate_device(self, residuals=True, gradient=True, jacobian=True,
+                        apply_loss_function=True):
+        """Re-evaluates at the state already resident in HBM; outputs stay on the device."""
+        cost = np.zeros(1)
+        rc = driver().drv_evaluate_device(self.h, int(apply_loss_function), int(residuals),
+                                          int(gradient), int(jacobian), _p(cost))
+        if rc < 0:
+            raise RuntimeError(f"evaluate_device failed ({rc})")
+        return rc == 0, float(cost[0])
+
+    def timing(self):
+        """ms of the last evaluation: kernels, kernels+reductions+allreduce, whole call; launches."""
+        out = np.zeros(4)
+        driver().drv_timing(self.h, _p(out))
+        return {"kernel_ms": out[0], "device_ms": out[1], "e2e_ms": out[2], "launches": int(out[3])}
+
+    def shard_info(self):
+        info = np.zeros(4, dtype=np.int32)
+        seg = np.zeros(3 * 16, dtype=np.int64)
+        n = driver().drv_shard_info(self.h, _p(info), _p(seg), 16)
+        return {"rb_begin": int(info[0]), "rb_end": int(info[1]), "residual_begin": int(info[2]),
+                "residual_end": int(info[3]),
+                "segments": [tuple(int(x) for x in seg[3 * i:3 * i + 3]) for i in range(max(n, 0))]}
+
+    def plus(self, state, delta):
+        out = np.zeros(self.num_parameters)
+        driver().drv_plus(self.h, _p(np.ascontiguousarray(state)), _p(np.ascontiguousarray(delta)),
+                          _p(out))
+        return out
+
+    def dense_jacobian(self):
+        J = np.zeros((self.num_residuals, self.num_effective_parameters))
+        driver().drv_dense_jacobian(self.h, _p(J))
+        return J

@@ -1,0 +1,710 @@
+// libceres_b200.so — the precompiled, type-erased half of the evaluation engine.
+//
+// Implements the C ABI of include/ceres_b200.h: device buffers, the
+// structure-of-arrays tables the kernels read, the per-rank Jacobian slices, the
+// cost reduction, host<->device transfers and the NCCL all-reduce.  The templated
+// kernels live in include/ceres/internal/evaluate_kernel.cuh and reach this file
+// only as launch thunks.
+//
+// Replaces (reference): internal/ceres/registered_cuda_evaluators.cc:46-280,
+// include/ceres/internal/autodiff_residual_block_cuda_evaluator.h:96-271,
+// include/ceres/internal/cuda_buffer.h:52-182, internal/ceres/context_impl.cc:112-174.
+//
+// Differences from the reference that matter for speed:
+//  * no memset of residuals / Jacobian values (every element is written exactly
+//    once by the kernel; only the gradient accumulator is zeroed);
+//  * no per-thread Jacobian scratch (reference: 2 x nRB x kRes x sum(Ns) doubles);
+//  * one host synchronisation per Evaluate instead of two per residual type;
+//  * the program POSITION of each residual block indexes the layouts, never
+//    ResidualBlock::index() (stale after the Schur reordering, SURVEY.md hazard 1).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ceres_b200.h"
+
+namespace {
+
+// ---- NCCL through dlopen: torch (when it hosts the process) already has
+// libnccl.so.2 loaded and dlopen returns that same copy.
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /* ncclUniqueId by value */ struct Uid, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+struct Uid {
+  char internal[128];
+};
+constexpr int kNcclFloat64 = 8;  // ncclDouble
+constexpr int kNcclSum = 0;      // ncclSum
+
+NcclApi* GetNccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (api.handle) {
+      api.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(api.handle, "ncclGetUniqueId"));
+      api.CommInitRank = reinterpret_cast<int (*)(void**, int, Uid, int)>(
+          dlsym(api.handle, "ncclCommInitRank"));
+      api.AllReduce =
+          reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(
+              dlsym(api.handle, "ncclAllReduce"));
+      api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(api.handle, "ncclCommDestroy"));
+      api.GetErrorString =
+          reinterpret_cast<const char* (*)(int)>(dlsym(api.handle, "ncclGetErrorString"));
+    }
+  }
+  return (api.handle && api.GetUniqueId && api.CommInitRank && api.AllReduce) ? &api : nullptr;
+}
+
+template <typename T>
+struct DeviceBuffer {
+  T* ptr = nullptr;
+  size_t count = 0;
+  cudaError_t Resize(size_t n) {
+    if (n == count && ptr) return cudaSuccess;
+    Free();
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ptr), n * sizeof(T));
+    if (e == cudaSuccess) count = n;
+    return e;
+  }
+  cudaError_t Upload(const std::vector<T>& v, cudaStream_t s) {
+    cudaError_t e = Resize(v.size());
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpyAsync(ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+  void Free() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    count = 0;
+  }
+};
+
+struct Segment {
+  int64_t global_begin, length, local_begin;
+};
+
+struct ResidualType {
+  cb200_residual_type desc;
+  // Host copies as handed over (all residual blocks of the type, any rank).
+  std::vector<int32_t> position;   // program position
+  std::vector<int32_t> pb_ids;     // [n][nb]
+  std::vector<char> functors;
+  std::vector<char> loss_table;
+  int32_t num_losses = 1;
+  std::vector<int32_t> loss_index;
+  // This rank's tables.
+  int32_t n_local = 0;
+  int32_t grid = 0;
+  int32_t cost_partial_offset = 0;
+  DeviceBuffer<char> d_functors, d_loss_table;
+  DeviceBuffer<int32_t> d_loss_index, d_pb, d_jpos, d_jstride, d_respos;
+};
+
+// Sums the per-thread-block cost partials in a fixed order (one block, tree in
+// shared memory) and writes the total next to the gradient.
+__global__ void ReduceCostKernel(const double* __restrict__ partials, int n, double* out) {
+  __shared__ double sm[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += partials[i];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sm[0];
+}
+
+}  // namespace
+
+struct cb200_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5] = {};
+  std::string error;
+  bool finalized = false;
+
+  // parameter blocks
+  int32_t num_active = 0, num_constant = 0, num_parameters = 0, num_effective = 0;
+  int32_t num_constant_parameters = 0, plus_pool = 0;
+  std::vector<cb200_parameter_block> blocks;
+  std::vector<double> constant_state;
+
+  // layout
+  int32_t jacobian_format = 0, num_rb = 0, num_residuals = 0;
+  std::vector<int32_t> residual_layout, jprl, jpro;
+  int64_t num_jacobian_values = 0;
+
+  // shard
+  int32_t rank = 0, world = 1;
+  int32_t rb_begin = 0, rb_end = 0, res_begin = 0, res_end = 0;
+  std::vector<Segment> segments;
+  int64_t local_jacobian_values = 0;
+
+  std::vector<ResidualType*> types;
+
+  DeviceBuffer<double> d_state, d_plus, d_residuals, d_jacobian, d_gradcost, d_cost_partials;
+  DeviceBuffer<int32_t> d_pb_table, d_status;
+  int32_t total_cost_partials = 0;
+
+  // pinned scalars: [cost, status]
+  double* h_scalars = nullptr;
+
+  void* comm = nullptr;
+  double timing[4] = {0, 0, 0, 0};
+
+  int Fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    error = buf;
+    return code;
+  }
+};
+
+#define CB200_CUDA(e, call)                                                            \
+  do {                                                                                 \
+    cudaError_t err__ = (call);                                                        \
+    if (err__ != cudaSuccess)                                                          \
+      return (e)->Fail(CB200_ERROR_CUDA, "%s: %s", #call, cudaGetErrorString(err__));  \
+  } while (0)
+
+extern "C" {
+
+const char* cb200_version(void) { return "ceres_b200 0.1 (sm_100a)"; }
+
+int cb200_engine_create(int device, cb200_engine** out) {
+  if (!out) return CB200_ERROR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    return CB200_ERROR_CUDA;  // fail loudly: there is no CPU fallback
+  }
+  auto* e = new cb200_engine;
+  e->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete e;
+    return CB200_ERROR_CUDA;
+  }
+  for (auto& ev : e->ev) cudaEventCreate(&ev);
+  cudaHostAlloc(reinterpret_cast<void**>(&e->h_scalars), 4 * sizeof(double), cudaHostAllocDefault);
+  *out = e;
+  return CB200_OK;
+}
+
+void cb200_engine_destroy(cb200_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->comm) {
+    if (NcclApi* n = GetNccl()) n->CommDestroy(e->comm);
+  }
+  for (auto* t : e->types) {
+    t->d_functors.Free(); t->d_loss_table.Free(); t->d_loss_index.Free(); t->d_pb.Free();
+    t->d_jpos.Free(); t->d_jstride.Free(); t->d_respos.Free();
+    delete t;
+  }
+  e->d_state.Free(); e->d_plus.Free(); e->d_residuals.Free(); e->d_jacobian.Free();
+  e->d_gradcost.Free(); e->d_cost_partials.Free(); e->d_pb_table.Free(); e->d_status.Free();
+  if (e->h_scalars) cudaFreeHost(e->h_scalars);
+  for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+const char* cb200_engine_last_error(const cb200_engine* e) { return e ? e->error.c_str() : ""; }
+
+int cb200_engine_set_parameter_blocks(cb200_engine* e, int32_t num_active, int32_t num_constant,
+                                      const cb200_parameter_block* blocks, int32_t num_parameters,
+                                      int32_t num_effective_parameters,
+                                      const double* constant_state,
+                                      int32_t num_constant_parameters,
+                                      int32_t plus_jacobian_pool_size) {
+  if (!e || e->finalized || num_active < 0 || num_constant < 0 ||
+      (!blocks && num_active + num_constant > 0))
+    return e ? e->Fail(CB200_ERROR_INVALID_ARGUMENT, "set_parameter_blocks: bad arguments")
+             : CB200_ERROR_INVALID_ARGUMENT;
+  e->num_active = num_active;
+  e->num_constant = num_constant;
+  e->num_parameters = num_parameters;
+  e->num_effective = num_effective_parameters;
+  e->num_constant_parameters = num_constant_parameters;
+  e->plus_pool = plus_jacobian_pool_size;
+  e->blocks.assign(blocks, blocks + num_active + num_constant);
+  e->constant_state.assign(constant_state, constant_state + num_constant_parameters);
+  return CB200_OK;
+}
+
+int cb200_engine_add_residual_blocks(cb200_engine* e, const cb200_residual_type* type, int32_t n,
+                                     const int32_t* program_position,
+                                     const int32_t* parameter_block_ids, const void* functors,
+                                     const void* loss_table, int32_t num_losses,
+                                     const int32_t* loss_index) {
+  if (!e || e->finalized || !type || !type->launch || n < 0 || num_losses < 1 ||
+      type->num_parameter_blocks < 1 || type->num_parameter_blocks > CB200_MAX_PARAMETER_BLOCKS)
+    return e ? e->Fail(CB200_ERROR_INVALID_ARGUMENT, "add_residual_blocks: bad arguments")
+             : CB200_ERROR_INVALID_ARGUMENT;
+  if (num_losses > 1 && !loss_index)
+    return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "add_residual_blocks: loss_index required");
+  auto* t = new ResidualType;
+  t->desc = *type;
+  const int nb = type->num_parameter_blocks;
+  t->position.assign(program_position, program_position + n);
+  t->pb_ids.assign(parameter_block_ids, parameter_block_ids + static_cast<size_t>(n) * nb);
+  const char* f = static_cast<const char*>(functors);
+  t->functors.assign(f, f + static_cast<size_t>(n) * type->functor_size);
+  const char* l = static_cast<const char*>(loss_table);
+  t->loss_table.assign(l, l + static_cast<size_t>(num_losses) * type->loss_size);
+  t->num_losses = num_losses;
+  if (num_losses > 1) t->loss_index.assign(loss_index, loss_index + n);
+  e->types.push_back(t);
+  return CB200_OK;
+}
+
+int cb200_engine_set_layout(cb200_engine* e, int32_t jacobian_format, int32_t num_residual_blocks,
+                            int32_t num_residuals, const int32_t* residual_layout,
+                            const int32_t* jacobian_per_residual_layout,
+                            const int32_t* jacobian_per_residual_offsets, int64_t num_offsets,
+                            int64_t num_jacobian_values) {
+  if (!e || e->finalized || num_residual_blocks < 0 ||
+      (jacobian_format != CB200_JACOBIAN_BLOCK_SPARSE &&
+       jacobian_format != CB200_JACOBIAN_COMPRESSED_ROW))
+    return e ? e->Fail(CB200_ERROR_INVALID_ARGUMENT, "set_layout: bad arguments")
+             : CB200_ERROR_INVALID_ARGUMENT;
+  e->jacobian_format = jacobian_format;
+  e->num_rb = num_residual_blocks;
+  e->num_residuals = num_residuals;
+  e->residual_layout.assign(residual_layout, residual_layout + num_residual_blocks);
+  e->jprl.assign(jacobian_per_residual_layout, jacobian_per_residual_layout + num_residual_blocks);
+  e->jpro.assign(jacobian_per_residual_offsets, jacobian_per_residual_offsets + num_offsets);
+  e->num_jacobian_values = num_jacobian_values;
+  return CB200_OK;
+}
+
+int cb200_engine_set_shard(cb200_engine* e, int32_t rank, int32_t world_size) {
+  if (!e || e->finalized || world_size < 1 || rank < 0 || rank >= world_size)
+    return e ? e->Fail(CB200_ERROR_INVALID_ARGUMENT, "set_shard: bad arguments")
+             : CB200_ERROR_INVALID_ARGUMENT;
+  e->rank = rank;
+  e->world = world_size;
+  return CB200_OK;
+}
+
+int cb200_engine_finalize(cb200_engine* e) {
+  if (!e || e->finalized) return CB200_ERROR_INVALID_ARGUMENT;
+  CB200_CUDA(e, cudaSetDevice(e->device));
+  const int64_t nrb = e->num_rb;
+  e->rb_begin = static_cast<int32_t>(nrb * e->rank / e->world);
+  e->rb_end = static_cast<int32_t>(nrb * (e->rank + 1) / e->world);
+  e->res_begin = e->rb_begin < nrb ? e->residual_layout[e->rb_begin] : e->num_residuals;
+  e->res_end = e->rb_end < nrb ? e->residual_layout[e->rb_end] : e->num_residuals;
+
+  // Device parameter-block table (int4 records).
+  const int npb = e->num_active + e->num_constant;
+  std::vector<int32_t> table(static_cast<size_t>(npb) * 4);
+  for (int i = 0; i < npb; ++i) {
+    const cb200_parameter_block& b = e->blocks[i];
+    const bool constant = i >= e->num_active;
+    table[4 * i + 0] = constant ? e->num_parameters + b.state_offset : b.state_offset;
+    table[4 * i + 1] = constant ? -1 : b.delta_offset;
+    table[4 * i + 2] = b.tangent_size;
+    table[4 * i + 3] = constant ? -1 : b.plus_jacobian_offset;
+  }
+
+  // Pass 1: per type, pick this rank's blocks and find what part of the values
+  // array each (type, argument) stream covers.
+  struct Stream { int64_t lo, hi, covered; };
+  std::vector<Stream> streams;
+  std::vector<std::vector<int32_t>> local_index(e->types.size());
+  for (size_t ti = 0; ti < e->types.size(); ++ti) {
+    ResidualType* t = e->types[ti];
+    const int nb = t->desc.num_parameter_blocks, kres = t->desc.num_residuals;
+    auto& idx = local_index[ti];
+    for (int32_t k = 0; k < static_cast<int32_t>(t->position.size()); ++k) {
+      const int32_t p = t->position[k];
+      if (p < 0 || p >= nrb)
+        return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "residual block position %d out of range", p);
+      if (p >= e->rb_begin && p < e->rb_end) idx.push_back(k);
+    }
+    std::vector<Stream> s(nb, Stream{INT64_MAX, -1, 0});
+    for (int32_t k : idx) {
+      const int32_t L = e->jprl[t->position[k]];
+      int a = 0;
+      for (int j = 0; j < nb; ++j) {
+        const int32_t id = t->pb_ids[static_cast<size_t>(k) * nb + j];
+        if (id < 0 || id >= npb)
+          return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "parameter block id %d out of range", id);
+        if (id >= e->num_active) continue;  // constant: no Jacobian block
+        const int tangent = e->blocks[id].tangent_size;
+        for (int r = 0; r < kres; ++r) {
+          const int64_t pos = e->jpro[static_cast<size_t>(L) + a * kres + r];
+          s[j].lo = std::min(s[j].lo, pos);
+          s[j].hi = std::max(s[j].hi, pos + tangent);
+          s[j].covered += tangent;
+        }
+        ++a;
+      }
+    }
+    for (auto& st : s) if (st.hi >= 0) streams.push_back(st);
+  }
+  // Streams that are dense on their own become segments; otherwise fall back to
+  // the union span.  Overlapping / adjacent segments are merged.
+  e->segments.clear();
+  {
+    bool all_dense = true;
+    int64_t lo = INT64_MAX, hi = -1, covered = 0;
+    for (auto& st : streams) {
+      lo = std::min(lo, st.lo); hi = std::max(hi, st.hi); covered += st.covered;
+      if (st.covered != st.hi - st.lo) all_dense = false;
+    }
+    std::vector<std::pair<int64_t, int64_t>> spans;
+    if (!streams.empty()) {
+      if (all_dense) for (auto& st : streams) spans.emplace_back(st.lo, st.hi);
+      else spans.emplace_back(lo, hi);  // interleaved (compressed-row): one span
+      (void)covered;
+    }
+    std::sort(spans.begin(), spans.end());
+    int64_t local = 0;
+    for (auto& sp : spans) {
+      if (!e->segments.empty() &&
+          sp.first <= e->segments.back().global_begin + e->segments.back().length) {
+        Segment& b = e->segments.back();
+        const int64_t new_end = std::max(b.global_begin + b.length, sp.second);
+        local += new_end - (b.global_begin + b.length);
+        b.length = new_end - b.global_begin;
+      } else {
+        e->segments.push_back(Segment{sp.first, sp.second - sp.first, local});
+        local += sp.second - sp.first;
+      }
+    }
+    e->local_jacobian_values = local;
+  }
+  auto to_local = [&](int64_t pos) -> int32_t {
+    for (const Segment& s : e->segments)
+      if (pos >= s.global_begin && pos < s.global_begin + s.length)
+        return static_cast<int32_t>(pos - s.global_begin + s.local_begin);
+    return -1;
+  };
+
+  // Pass 2: build and upload the per-type tables (argument-major SoA).
+  e->total_cost_partials = 0;
+  for (size_t ti = 0; ti < e->types.size(); ++ti) {
+    ResidualType* t = e->types[ti];
+    const int nb = t->desc.num_parameter_blocks, kres = t->desc.num_residuals;
+    const auto& idx = local_index[ti];
+    const int32_t n = static_cast<int32_t>(idx.size());
+    t->n_local = n;
+    const int tpb = t->desc.threads_per_block > 0 ? t->desc.threads_per_block : 128;
+    t->grid = (n + tpb - 1) / tpb;
+    t->cost_partial_offset = e->total_cost_partials;
+    e->total_cost_partials += t->grid;
+    if (n == 0) continue;
+    std::vector<int32_t> pb(static_cast<size_t>(nb) * n), jpos(static_cast<size_t>(nb) * n, -1);
+    std::vector<int32_t> jstride(n, 0), respos(n), lidx;
+    std::vector<char> fun(static_cast<size_t>(n) * t->desc.functor_size);
+    if (t->num_losses > 1) lidx.resize(n);
+    for (int32_t i = 0; i < n; ++i) {
+      const int32_t k = idx[i];
+      const int32_t p = t->position[k];
+      respos[i] = e->residual_layout[p] - e->res_begin;
+      std::memcpy(fun.data() + static_cast<size_t>(i) * t->desc.functor_size,
+                  t->functors.data() + static_cast<size_t>(k) * t->desc.functor_size,
+                  t->desc.functor_size);
+      if (t->num_losses > 1) lidx[i] = t->loss_index[k];
+      const int32_t L = e->jprl[p];
+      int a = 0;
+      for (int j = 0; j < nb; ++j) {
+        const int32_t id = t->pb_ids[static_cast<size_t>(k) * nb + j];
+        pb[static_cast<size_t>(j) * n + i] = id;
+        if (id >= e->num_active) continue;
+        const int64_t pos0 = e->jpro[static_cast<size_t>(L) + a * kres];
+        jpos[static_cast<size_t>(j) * n + i] = to_local(pos0);
+        if (kres > 1 && jstride[i] == 0)
+          jstride[i] = e->jpro[static_cast<size_t>(L) + a * kres + 1] -
+                       e->jpro[static_cast<size_t>(L) + a * kres];
+        ++a;
+      }
+    }
+    CB200_CUDA(e, t->d_pb.Upload(pb, e->stream));
+    CB200_CUDA(e, t->d_jpos.Upload(jpos, e->stream));
+    CB200_CUDA(e, t->d_jstride.Upload(jstride, e->stream));
+    CB200_CUDA(e, t->d_respos.Upload(respos, e->stream));
+    CB200_CUDA(e, t->d_functors.Upload(fun, e->stream));
+    CB200_CUDA(e, t->d_loss_table.Upload(t->loss_table, e->stream));
+    if (t->num_losses > 1) CB200_CUDA(e, t->d_loss_index.Upload(lidx, e->stream));
+    CB200_CUDA(e, cudaStreamSynchronize(e->stream));  // the vectors die at scope end
+    // The full-problem host copies are no longer needed.
+    std::vector<int32_t>().swap(t->pb_ids);
+    std::vector<char>().swap(t->functors);
+    std::vector<int32_t>().swap(t->loss_index);
+  }
+
+  CB200_CUDA(e, e->d_pb_table.Upload(table, e->stream));
+  CB200_CUDA(e, e->d_state.Resize(static_cast<size_t>(e->num_parameters) +
+                                  e->num_constant_parameters + 1));
+  if (e->num_constant_parameters > 0)
+    CB200_CUDA(e, cudaMemcpyAsync(e->d_state.ptr + e->num_parameters, e->constant_state.data(),
+                                  e->constant_state.size() * sizeof(double),
+                                  cudaMemcpyHostToDevice, e->stream));
+  CB200_CUDA(e, e->d_plus.Resize(static_cast<size_t>(e->plus_pool) + 1));
+  CB200_CUDA(e, e->d_residuals.Resize(static_cast<size_t>(e->res_end - e->res_begin) + 1));
+  CB200_CUDA(e, e->d_jacobian.Resize(static_cast<size_t>(e->local_jacobian_values) + 2));
+  CB200_CUDA(e, e->d_gradcost.Resize(static_cast<size_t>(e->num_effective) + 2));
+  CB200_CUDA(e, e->d_cost_partials.Resize(static_cast<size_t>(e->total_cost_partials) + 1));
+  CB200_CUDA(e, e->d_status.Resize(1));
+  CB200_CUDA(e, cudaStreamSynchronize(e->stream));
+  // Layout arrays were consumed.
+  std::vector<int32_t>().swap(e->jpro);
+  e->finalized = true;
+  return CB200_OK;
+}
+
+int cb200_nccl_unique_id(void* out) {
+  NcclApi* n = GetNccl();
+  if (!n || !out) return CB200_ERROR_NCCL;
+  return n->GetUniqueId(out) == 0 ? CB200_OK : CB200_ERROR_NCCL;
+}
+
+int cb200_engine_comm_init(cb200_engine* e, const void* unique_id, int32_t rank,
+                           int32_t world_size) {
+  if (!e || !unique_id) return CB200_ERROR_INVALID_ARGUMENT;
+  NcclApi* n = GetNccl();
+  if (!n) return e->Fail(CB200_ERROR_NCCL, "libnccl.so.2 not found");
+  CB200_CUDA(e, cudaSetDevice(e->device));
+  Uid id;
+  std::memcpy(id.internal, unique_id, sizeof(id.internal));
+  const int r = n->CommInitRank(&e->comm, world_size, id, rank);
+  if (r != 0)
+    return e->Fail(CB200_ERROR_NCCL, "ncclCommInitRank: %s",
+                   n->GetErrorString ? n->GetErrorString(r) : "?");
+  return CB200_OK;
+}
+
+// Shared by the host-pointer and device-pointer entry points.
+static int EvaluateOnDevice(cb200_engine* e, uint32_t flags, bool want_r, bool want_g,
+                            bool want_j) {
+  cudaStream_t s = e->stream;
+  CB200_CUDA(e, cudaMemsetAsync(e->d_status.ptr, 0, sizeof(int32_t), s));
+  // Only the gradient accumulates; residuals and Jacobian cells are each written
+  // exactly once.  Cost slot and padding are zeroed with it.
+  CB200_CUDA(e, cudaMemsetAsync(e->d_gradcost.ptr, 0,
+                                (static_cast<size_t>(e->num_effective) + 2) * sizeof(double), s));
+  CB200_CUDA(e, cudaEventRecord(e->ev[1], s));
+  int launches = 0;
+  for (ResidualType* t : e->types) {
+    if (t->n_local == 0) continue;
+    cb200_launch_args a{};
+    a.n = t->n_local;
+    a.output_residuals = want_r;
+    a.output_jacobian = want_j;
+    a.output_gradient = want_g;
+    a.apply_loss_function = (flags & CB200_APPLY_LOSS_FUNCTION) ? 1u : 0u;
+    a.crs = e->jacobian_format == CB200_JACOBIAN_COMPRESSED_ROW;
+    a.functors = t->d_functors.ptr;
+    a.loss_table = t->d_loss_table.ptr;
+    a.loss_index = t->num_losses > 1 ? t->d_loss_index.ptr : nullptr;
+    a.parameter_block = t->d_pb.ptr;
+    a.jacobian_pos = t->d_jpos.ptr;
+    a.jacobian_row_stride = t->d_jstride.ptr;
+    a.residual_pos = t->d_respos.ptr;
+    a.parameter_block_table = e->d_pb_table.ptr;
+    a.state = e->d_state.ptr;
+    a.plus_jacobians = e->d_plus.ptr;
+    a.residuals = e->d_residuals.ptr;
+    a.jacobian_values = e->d_jacobian.ptr;
+    a.gradient = e->d_gradcost.ptr;
+    a.cost_partials = e->d_cost_partials.ptr + t->cost_partial_offset;
+    a.status = e->d_status.ptr;
+    const int err = t->desc.launch(&a, s);
+    if (err != 0)
+      return e->Fail(CB200_ERROR_CUDA, "kernel launch: %s",
+                     cudaGetErrorString(static_cast<cudaError_t>(err)));
+    ++launches;
+  }
+  CB200_CUDA(e, cudaEventRecord(e->ev[2], s));
+  if (e->total_cost_partials > 0) {
+    ReduceCostKernel<<<1, 256, 0, s>>>(e->d_cost_partials.ptr, e->total_cost_partials,
+                                       e->d_gradcost.ptr + e->num_effective);
+    ++launches;
+  }
+  if (e->comm && e->world > 1) {
+    NcclApi* n = GetNccl();
+    // One all-reduce over [gradient | cost]; cost-only evaluations reduce 1 double.
+    double* buf = want_g ? e->d_gradcost.ptr : e->d_gradcost.ptr + e->num_effective;
+    const size_t count = want_g ? static_cast<size_t>(e->num_effective) + 1 : 1;
+    const int r = n->AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, e->comm, s);
+    if (r != 0) return e->Fail(CB200_ERROR_NCCL, "ncclAllReduce failed (%d)", r);
+  }
+  CB200_CUDA(e, cudaEventRecord(e->ev[3], s));
+  e->timing[3] = launches;
+  return CB200_OK;
+}
+
+static int FinishTiming(cb200_engine* e) {
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]); e->timing[0] = ms;
+  cudaEventElapsedTime(&ms, e->ev[1], e->ev[3]); e->timing[1] = ms;
+  cudaEventElapsedTime(&ms, e->ev[0], e->ev[4]); e->timing[2] = ms;
+  return CB200_OK;
+}
+
+int cb200_engine_evaluate(cb200_engine* e, const double* state, const double* plus_jacobians,
+                          uint32_t flags, double* cost, double* residuals, double* gradient,
+                          double* jacobian_values) {
+  if (!e) return CB200_ERROR_INVALID_ARGUMENT;
+  if (!e->finalized) return e->Fail(CB200_ERROR_NOT_FINALIZED, "evaluate before finalize");
+  if (!state || !cost) return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "state and cost are required");
+  if (e->plus_pool > 0 && !plus_jacobians)
+    return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "plus_jacobians required");
+  CB200_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t s = e->stream;
+  CB200_CUDA(e, cudaEventRecord(e->ev[0], s));
+  CB200_CUDA(e, cudaMemcpyAsync(e->d_state.ptr, state, sizeof(double) * e->num_parameters,
+                                cudaMemcpyHostToDevice, s));
+  if (e->plus_pool > 0)
+    CB200_CUDA(e, cudaMemcpyAsync(e->d_plus.ptr, plus_jacobians, sizeof(double) * e->plus_pool,
+                                  cudaMemcpyHostToDevice, s));
+  const int rc = EvaluateOnDevice(e, flags, residuals != nullptr, gradient != nullptr,
+                                  jacobian_values != nullptr);
+  if (rc != CB200_OK) return rc;
+  CB200_CUDA(e, cudaMemcpyAsync(e->h_scalars, e->d_gradcost.ptr + e->num_effective,
+                                sizeof(double), cudaMemcpyDeviceToHost, s));
+  CB200_CUDA(e, cudaMemcpyAsync(e->h_scalars + 1, e->d_status.ptr, sizeof(int32_t),
+                                cudaMemcpyDeviceToHost, s));
+  if (!(flags & CB200_SKIP_HOST_COPY)) {
+    if (residuals && e->res_end > e->res_begin)
+      CB200_CUDA(e, cudaMemcpyAsync(residuals + e->res_begin, e->d_residuals.ptr,
+                                    sizeof(double) * (e->res_end - e->res_begin),
+                                    cudaMemcpyDeviceToHost, s));
+    if (gradient && e->num_effective > 0)
+      CB200_CUDA(e, cudaMemcpyAsync(gradient, e->d_gradcost.ptr,
+                                    sizeof(double) * e->num_effective, cudaMemcpyDeviceToHost, s));
+    if (jacobian_values)
+      for (const Segment& seg : e->segments)
+        CB200_CUDA(e, cudaMemcpyAsync(jacobian_values + seg.global_begin,
+                                      e->d_jacobian.ptr + seg.local_begin,
+                                      sizeof(double) * seg.length, cudaMemcpyDeviceToHost, s));
+  }
+  CB200_CUDA(e, cudaEventRecord(e->ev[4], s));
+  CB200_CUDA(e, cudaStreamSynchronize(s));  // the only host synchronisation
+  FinishTiming(e);
+  *cost = e->h_scalars[0];
+  int32_t status;
+  std::memcpy(&status, e->h_scalars + 1, sizeof(status));
+  return status ? CB200_EVALUATION_FAILED : CB200_OK;
+}
+
+int cb200_engine_evaluate_device(cb200_engine* e, const double* state_device,
+                                 const double* plus_jacobians_device, uint32_t flags,
+                                 int want_residuals, int want_gradient, int want_jacobian,
+                                 double* cost) {
+  if (!e) return CB200_ERROR_INVALID_ARGUMENT;
+  if (!e->finalized) return e->Fail(CB200_ERROR_NOT_FINALIZED, "evaluate before finalize");
+  if (!cost) return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "cost is required");
+  CB200_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t s = e->stream;
+  CB200_CUDA(e, cudaEventRecord(e->ev[0], s));
+  if (state_device && state_device != e->d_state.ptr)
+    CB200_CUDA(e, cudaMemcpyAsync(e->d_state.ptr, state_device,
+                                  sizeof(double) * e->num_parameters, cudaMemcpyDeviceToDevice, s));
+  if (plus_jacobians_device && e->plus_pool > 0 && plus_jacobians_device != e->d_plus.ptr)
+    CB200_CUDA(e, cudaMemcpyAsync(e->d_plus.ptr, plus_jacobians_device,
+                                  sizeof(double) * e->plus_pool, cudaMemcpyDeviceToDevice, s));
+  const int rc = EvaluateOnDevice(e, flags, want_residuals != 0, want_gradient != 0,
+                                  want_jacobian != 0);
+  if (rc != CB200_OK) return rc;
+  CB200_CUDA(e, cudaMemcpyAsync(e->h_scalars, e->d_gradcost.ptr + e->num_effective,
+                                sizeof(double), cudaMemcpyDeviceToHost, s));
+  CB200_CUDA(e, cudaMemcpyAsync(e->h_scalars + 1, e->d_status.ptr, sizeof(int32_t),
+                                cudaMemcpyDeviceToHost, s));
+  CB200_CUDA(e, cudaEventRecord(e->ev[4], s));
+  CB200_CUDA(e, cudaStreamSynchronize(s));
+  FinishTiming(e);
+  *cost = e->h_scalars[0];
+  int32_t status;
+  std::memcpy(&status, e->h_scalars + 1, sizeof(status));
+  return status ? CB200_EVALUATION_FAILED : CB200_OK;
+}
+
+void* cb200_engine_device_ptr(cb200_engine* e, int which) {
+  if (!e || !e->finalized) return nullptr;
+  switch (which) {
+    case 0: return e->d_residuals.ptr;
+    case 1: return e->d_gradcost.ptr;
+    case 2: return e->d_jacobian.ptr;
+    case 3: return e->d_state.ptr;
+    case 4: return e->d_plus.ptr;
+    default: return nullptr;
+  }
+}
+
+int cb200_engine_shard_info(cb200_engine* e, int32_t* rb_begin, int32_t* rb_end,
+                            int32_t* residual_begin, int32_t* residual_end, int64_t* segments,
+                            int32_t max_segments) {
+  if (!e || !e->finalized) return -1;
+  if (rb_begin) *rb_begin = e->rb_begin;
+  if (rb_end) *rb_end = e->rb_end;
+  if (residual_begin) *residual_begin = e->res_begin;
+  if (residual_end) *residual_end = e->res_end;
+  const int n = static_cast<int>(e->segments.size());
+  for (int i = 0; i < n && i < max_segments; ++i) {
+    segments[3 * i + 0] = e->segments[i].global_begin;
+    segments[3 * i + 1] = e->segments[i].length;
+    segments[3 * i + 2] = e->segments[i].local_begin;
+  }
+  return n;
+}
+
+int cb200_engine_last_timing(cb200_engine* e, double* out4) {
+  if (!e || !out4) return CB200_ERROR_INVALID_ARGUMENT;
+  for (int i = 0; i < 4; ++i) out4[i] = e->timing[i];
+  return CB200_OK;
+}
+
+void* cb200_host_alloc(uint64_t bytes) {
+  // Pinned so device->host copies of the Jacobian run at full PCIe rate.  The
+  // pointer is tagged by a 64-byte header so cb200_host_free knows how to free it.
+  if (bytes == 0) bytes = 8;
+  void* p = nullptr;
+  int count = 0;
+  bool pinned = false;
+  if (cudaGetDeviceCount(&count) == cudaSuccess && count > 0 &&
+      cudaHostAlloc(&p, bytes + 64, cudaHostAllocPortable) == cudaSuccess) {
+    pinned = true;
+  } else {
+    cudaGetLastError();
+    if (posix_memalign(&p, 64, bytes + 64) != 0) return nullptr;
+  }
+  *static_cast<uint64_t*>(p) = pinned ? 0x70696e6e6564ULL : 0x6d616c6c6f63ULL;
+  return static_cast<char*>(p) + 64;
+}
+
+void cb200_host_free(void* q) {
+  if (!q) return;
+  char* p = static_cast<char*>(q) - 64;
+  if (*reinterpret_cast<uint64_t*>(p) == 0x70696e6e6564ULL) cudaFreeHost(p);
+  else free(p);
+}
+
+}  // extern "C"

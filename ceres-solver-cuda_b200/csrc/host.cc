@@ -1,0 +1,812 @@
+// Host side of the evaluation path: problem graph, reduced program, Jacobian
+// layouts and ProgramEvaluatorCUDA.  Thin by design — it prepares arrays and calls
+// the C ABI (include/ceres_b200.h); all arithmetic runs in the CUDA kernels.
+//
+// Reference counterparts: internal/ceres/problem_impl.cc, program.cc,
+// reorder_program.cc:254-335, block_jacobian_writer.cc, compressed_row_jacobian_writer.cc,
+// program_evaluator_cuda.h:65-183, registered_cuda_evaluators.cc:123-280.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <numeric>
+
+#include "ceres/internal/evaluator.h"
+#include "ceres/internal/program.h"
+#include "ceres/internal/sparse_matrix.h"
+
+namespace ceres {
+namespace internal {
+
+// ------------------------------------------------------------------ ProblemImpl
+ProblemImpl::ProblemImpl(const ProblemOptions& options) : options_(options) {}
+
+ProblemImpl::~ProblemImpl() {
+  if (options_.manifold_ownership == TAKE_OWNERSHIP) {
+    std::sort(manifolds_to_delete_.begin(), manifolds_to_delete_.end());
+    manifolds_to_delete_.erase(
+        std::unique(manifolds_to_delete_.begin(), manifolds_to_delete_.end()),
+        manifolds_to_delete_.end());
+    for (Manifold* m : manifolds_to_delete_) delete m;
+  }
+  if (options_.cost_function_ownership == TAKE_OWNERSHIP) {
+    for (auto& t : types_)
+      for (CostFunction* c : t.cost_functions)
+        if (c) cost_functions_to_delete_.push_back(c);
+    std::sort(cost_functions_to_delete_.begin(), cost_functions_to_delete_.end());
+    cost_functions_to_delete_.erase(
+        std::unique(cost_functions_to_delete_.begin(), cost_functions_to_delete_.end()),
+        cost_functions_to_delete_.end());
+    for (CostFunction* c : cost_functions_to_delete_) delete c;
+  }
+}
+
+ParameterBlock* ProblemImpl::FindParameterBlock(const double* values) const {
+  auto it = pb_map_.find(values);
+  return it == pb_map_.end() ? nullptr : it->second;
+}
+
+ParameterBlock* ProblemImpl::AddParameterBlock(double* values, int size, Manifold* manifold) {
+  ParameterBlock* pb = FindParameterBlock(values);
+  if (pb != nullptr) {
+    if (pb->size != size) {
+      std::fprintf(stderr,
+                   "Tried adding a parameter block with the same double pointer, %p, twice, "
+                   "but with different block sizes. Original size was %d but new size is %d\n",
+                   static_cast<void*>(values), pb->size, size);
+      std::abort();  // the reference CHECK-fails here too (problem_impl.cc:139-147)
+    }
+    if (manifold != nullptr) SetManifold(values, manifold);
+    return pb;
+  }
+  pbs_.emplace_back(new ParameterBlock);
+  pb = pbs_.back().get();
+  pb->user_state = values;
+  pb->size = size;
+  pb->id = static_cast<int>(pbs_.size()) - 1;
+  pb_map_[values] = pb;
+  if (manifold != nullptr) SetManifold(values, manifold);
+  return pb;
+}
+
+void ProblemImpl::SetManifold(double* values, Manifold* manifold) {
+  ParameterBlock* pb = FindParameterBlock(values);
+  if (pb == nullptr) {
+    std::fprintf(stderr, "SetManifold: parameter block %p not found\n", static_cast<void*>(values));
+    std::abort();
+  }
+  if (manifold != nullptr && manifold->AmbientSize() != pb->size) {
+    std::fprintf(stderr, "SetManifold: ambient size %d != parameter block size %d\n",
+                 manifold->AmbientSize(), pb->size);
+    std::abort();
+  }
+  pb->manifold = manifold;
+  if (manifold != nullptr) manifolds_to_delete_.push_back(manifold);
+}
+
+void ProblemImpl::SetParameterBlockConstant(const double* values) {
+  FindParameterBlock(values)->is_set_constant = true;
+}
+void ProblemImpl::SetParameterBlockVariable(double* values) {
+  FindParameterBlock(values)->is_set_constant = false;
+}
+
+void ProblemImpl::SetParameterLowerBound(double* values, int index, double bound) {
+  ParameterBlock* pb = FindParameterBlock(values);
+  if (!pb->lower_bounds) {
+    pb->lower_bounds.reset(new double[pb->size]);
+    std::fill_n(pb->lower_bounds.get(), pb->size, -std::numeric_limits<double>::max());
+  }
+  pb->lower_bounds[index] = bound;
+}
+void ProblemImpl::SetParameterUpperBound(double* values, int index, double bound) {
+  ParameterBlock* pb = FindParameterBlock(values);
+  if (!pb->upper_bounds) {
+    pb->upper_bounds.reset(new double[pb->size]);
+    std::fill_n(pb->upper_bounds.get(), pb->size, std::numeric_limits<double>::max());
+  }
+  pb->upper_bounds[index] = bound;
+}
+double ProblemImpl::GetParameterLowerBound(const double* values, int index) const {
+  const ParameterBlock* pb = FindParameterBlock(values);
+  return pb->lower_bounds ? pb->lower_bounds[index] : -std::numeric_limits<double>::max();
+}
+double ProblemImpl::GetParameterUpperBound(const double* values, int index) const {
+  const ParameterBlock* pb = FindParameterBlock(values);
+  return pb->upper_bounds ? pb->upper_bounds[index] : std::numeric_limits<double>::max();
+}
+
+int ProblemImpl::FindOrAddType(std::type_index key, const cb200_residual_type& desc) {
+  auto it = type_map_.find(key);
+  if (it != type_map_.end()) return it->second;
+  types_.emplace_back();
+  types_.back().desc = desc;
+  types_.back().key = key;
+  const int id = static_cast<int>(types_.size()) - 1;
+  type_map_.emplace(key, id);
+  return id;
+}
+
+ResidualBlock* ProblemImpl::AddResidualBlock(int type, CostFunction* cost_function,
+                                             const void* functor, const void* loss,
+                                             double* const* parameter_blocks) {
+  ResidualTypeStore& t = types_[type];
+  const int nb = t.desc.num_parameter_blocks;
+  for (int j = 0; j < nb; ++j) {
+    // Duplicate parameter blocks in one residual block are an error in Ceres
+    // (problem_impl.cc:264-283).
+    for (int k = 0; k < j; ++k) {
+      if (parameter_blocks[j] == parameter_blocks[k]) {
+        std::fprintf(stderr, "Duplicate parameter blocks in a residual block are not allowed.\n");
+        std::abort();
+      }
+    }
+    ParameterBlock* pb = AddParameterBlock(parameter_blocks[j], t.desc.parameter_block_sizes[j]);
+    t.parameter_blocks.push_back(pb->id);
+  }
+  const char* f = static_cast<const char*>(functor);
+  t.functors.insert(t.functors.end(), f, f + t.desc.functor_size);
+  // Deduplicate loss objects by address: the reference copies one loss object per
+  // residual block to the device (autodiff_residual_block_cuda_evaluator.h:96-133).
+  int loss_id = -1;
+  if (!t.loss_objects.empty() && t.loss_objects.back() == loss) {
+    loss_id = static_cast<int>(t.loss_objects.size()) - 1;
+  } else {
+    for (size_t i = 0; i < t.loss_objects.size(); ++i)
+      if (t.loss_objects[i] == loss) { loss_id = static_cast<int>(i); break; }
+  }
+  if (loss_id < 0) {
+    t.loss_objects.push_back(loss);
+    const char* l = static_cast<const char*>(loss);
+    t.loss_table.insert(t.loss_table.end(), l, l + t.desc.loss_size);
+    loss_id = static_cast<int>(t.loss_objects.size()) - 1;
+  }
+  t.loss_index.push_back(loss_id);
+  t.cost_functions.push_back(cost_function);
+  const int32_t id = static_cast<int32_t>(rbs_.size());
+  t.residual_block_id.push_back(id);
+  rbs_.push_back(ResidualBlockRef{type, t.size() - 1});
+  return HandleOf(id);
+}
+
+int ProblemImpl::NumParameters() const {
+  int n = 0;
+  for (const auto& pb : pbs_) n += pb->size;
+  return n;
+}
+int ProblemImpl::NumResiduals() const {
+  int n = 0;
+  for (const auto& t : types_) n += t.size() * t.desc.num_residuals;
+  return n;
+}
+
+// residual_block.cc:68-204 on the host, for residual blocks outside the program.
+bool ProblemImpl::EvaluateResidualBlockOnHost(int32_t id, bool apply_loss_function, double* cost,
+                                              double* residuals, double** jacobians) const {
+  const ResidualBlockRef ref = rbs_[id];
+  const ResidualTypeStore& t = types_[ref.type];
+  const int nb = t.desc.num_parameter_blocks, kres = t.desc.num_residuals;
+  const double* params[CB200_MAX_PARAMETER_BLOCKS];
+  for (int j = 0; j < nb; ++j)
+    params[j] = pbs_[t.parameter_blocks[static_cast<size_t>(ref.local) * nb + j]]->user_state;
+  std::vector<double> scratch(kres);
+  double* r = residuals ? residuals : scratch.data();
+  const void* functor = t.functors.data() + static_cast<size_t>(ref.local) * t.desc.functor_size;
+  if (!t.host_functor(functor, params, r, jacobians)) return false;
+  double s = 0.0;
+  for (int i = 0; i < kres; ++i) {
+    if (!std::isfinite(r[i]) || r[i] == 1e302) return false;
+    s += r[i] * r[i];
+  }
+  if (!apply_loss_function) {
+    *cost = 0.5 * s;
+    return true;
+  }
+  double rho[3];
+  t.host_loss(t.loss_table.data() + static_cast<size_t>(t.loss_index[ref.local]) * t.desc.loss_size,
+              s, rho);
+  *cost = 0.5 * rho[0];
+  return true;
+}
+
+// ---------------------------------------------------------------------- Program
+Program::Program(ProblemImpl* problem) : problem_(problem) {
+  for (const auto& pb : problem->parameter_blocks()) parameter_blocks_.push_back(pb.get());
+  residual_blocks_.resize(problem->residual_blocks().size());
+  std::iota(residual_blocks_.begin(), residual_blocks_.end(), 0);
+}
+
+void Program::SetParameterOffsetsAndIndex() {
+  for (const auto& pb : problem_->parameter_blocks()) pb->index = -1;
+  int state_offset = 0, delta_offset = 0;
+  for (size_t i = 0; i < parameter_blocks_.size(); ++i) {
+    ParameterBlock* pb = parameter_blocks_[i];
+    pb->index = static_cast<int>(i);
+    pb->state_offset = state_offset;
+    pb->delta_offset = delta_offset;
+    state_offset += pb->size;
+    delta_offset += pb->TangentSize();
+  }
+  state_offset = 0;
+  for (size_t i = 0; i < constant_parameter_blocks_.size(); ++i) {
+    ParameterBlock* pb = constant_parameter_blocks_[i];
+    pb->index = static_cast<int>(i);
+    pb->state_offset = state_offset;
+    pb->delta_offset = -1;
+    state_offset += pb->size;
+  }
+}
+
+std::unique_ptr<Program> Program::CreateReducedProgram(
+    std::vector<double*>* removed_parameter_blocks, double* fixed_cost,
+    std::string* error) const {
+  auto reduced = std::make_unique<Program>(*this);
+  *fixed_cost = 0.0;
+  const auto& rbs = problem_->residual_blocks();
+  const auto& types = problem_->types();
+  std::vector<char> used(problem_->parameter_blocks().size(), 0);
+  std::vector<int32_t> kept;
+  kept.reserve(residual_blocks_.size());
+  for (int32_t id : residual_blocks_) {
+    const ResidualBlockRef ref = rbs[id];
+    const ResidualTypeStore& t = types[ref.type];
+    const int nb = t.desc.num_parameter_blocks;
+    bool all_constant = true;
+    for (int j = 0; j < nb; ++j) {
+      const int pid = t.parameter_blocks[static_cast<size_t>(ref.local) * nb + j];
+      if (!problem_->parameter_blocks()[pid]->IsConstant()) {
+        all_constant = false;
+        used[pid] = 1;
+      }
+    }
+    if (!all_constant) {
+      kept.push_back(id);
+      continue;
+    }
+    double cost = 0.0;
+    if (!problem_->EvaluateResidualBlockOnHost(id, true, &cost, nullptr, nullptr)) {
+      *error = "Evaluation of the residual " + std::to_string(id) +
+               " failed during removal of fixed residual blocks.";
+      return nullptr;
+    }
+    *fixed_cost += cost;
+  }
+  reduced->residual_blocks_.swap(kept);
+  removed_parameter_blocks->clear();
+  reduced->constant_parameter_blocks_.clear();
+  std::vector<ParameterBlock*> active;
+  for (ParameterBlock* pb : parameter_blocks_) {
+    if (used[pb->id]) {
+      active.push_back(pb);
+    } else {
+      reduced->constant_parameter_blocks_.push_back(pb);
+      removed_parameter_blocks->push_back(pb->user_state);
+    }
+  }
+  reduced->parameter_blocks_.swap(active);
+  reduced->SetParameterOffsetsAndIndex();
+  return reduced;
+}
+
+void Program::ReorderParameterBlocksByGroup(
+    const std::unordered_map<const double*, int>& group) {
+  auto group_of = [&](const ParameterBlock* pb) {
+    auto it = group.find(pb->user_state);
+    return it == group.end() ? std::numeric_limits<int>::max() : it->second;
+  };
+  std::stable_sort(parameter_blocks_.begin(), parameter_blocks_.end(),
+                   [&](const ParameterBlock* a, const ParameterBlock* b) {
+                     return group_of(a) < group_of(b);
+                   });
+  SetParameterOffsetsAndIndex();
+}
+
+bool Program::LexicographicallyOrderResidualBlocks(int size_of_first_elimination_group) {
+  const int E = size_of_first_elimination_group;
+  if (E < 1) return false;
+  const auto& rbs = problem_->residual_blocks();
+  const auto& types = problem_->types();
+  const int n = NumResidualBlocks();
+  std::vector<int> per_bucket(E + 1, 0), bucket_of(n);
+  for (int i = 0; i < n; ++i) {
+    const ResidualBlockRef ref = rbs[residual_blocks_[i]];
+    const ResidualTypeStore& t = types[ref.type];
+    const int nb = t.desc.num_parameter_blocks;
+    int position = E;
+    for (int j = 0; j < nb; ++j) {
+      const ParameterBlock* pb =
+          problem_->parameter_blocks()[t.parameter_blocks[static_cast<size_t>(ref.local) * nb + j]]
+              .get();
+      if (IsActive(pb) && !pb->IsConstant()) position = std::min(position, pb->index);
+    }
+    bucket_of[i] = position;
+    per_bucket[position]++;
+  }
+  // Buckets are filled back to front, as the reference does, so the order inside
+  // an E block is the reverse of the input order.
+  std::vector<int> cursor(E + 1);
+  std::partial_sum(per_bucket.begin(), per_bucket.end(), cursor.begin());
+  std::vector<int32_t> reordered(n, -1);
+  for (int i = 0; i < n; ++i) reordered[--cursor[bucket_of[i]]] = residual_blocks_[i];
+  residual_blocks_.swap(reordered);
+  return true;
+}
+
+void Program::ParameterBlocksToStateVector(double* state) const {
+  for (const ParameterBlock* pb : parameter_blocks_) {
+    std::memcpy(state, pb->user_state, sizeof(double) * pb->size);
+    state += pb->size;
+  }
+}
+void Program::StateVectorToParameterBlocks(const double* state) const {
+  for (const ParameterBlock* pb : parameter_blocks_) {
+    std::memcpy(pb->user_state, state, sizeof(double) * pb->size);
+    state += pb->size;
+  }
+}
+void Program::ConstantParameterBlocksToStateVector(double* state) const {
+  for (const ParameterBlock* pb : constant_parameter_blocks_) {
+    std::memcpy(state, pb->user_state, sizeof(double) * pb->size);
+    state += pb->size;
+  }
+}
+bool Program::Plus(const double* state, const double* delta, double* state_plus_delta) const {
+  for (const ParameterBlock* pb : parameter_blocks_) {
+    const double* x = state + pb->state_offset;
+    const double* d = delta + pb->delta_offset;
+    double* out = state_plus_delta + pb->state_offset;
+    if (pb->manifold) {
+      if (!pb->manifold->Plus(x, d, out)) return false;
+    } else {
+      for (int i = 0; i < pb->size; ++i) out[i] = x[i] + d[i];
+    }
+    if (pb->lower_bounds || pb->upper_bounds) {  // parameter_block.h:255-276 projection
+      for (int i = 0; i < pb->size; ++i) {
+        if (pb->lower_bounds) out[i] = std::max(out[i], pb->lower_bounds[i]);
+        if (pb->upper_bounds) out[i] = std::min(out[i], pb->upper_bounds[i]);
+      }
+    }
+  }
+  return true;
+}
+int Program::NumParameters() const {
+  int n = 0;
+  for (const ParameterBlock* pb : parameter_blocks_) n += pb->size;
+  return n;
+}
+int Program::NumEffectiveParameters() const {
+  int n = 0;
+  for (const ParameterBlock* pb : parameter_blocks_) n += pb->TangentSize();
+  return n;
+}
+int Program::NumConstantParameters() const {
+  int n = 0;
+  for (const ParameterBlock* pb : constant_parameter_blocks_) n += pb->size;
+  return n;
+}
+int Program::NumResiduals() const {
+  int n = 0;
+  const auto& rbs = problem_->residual_blocks();
+  for (int32_t id : residual_blocks_) n += problem_->types()[rbs[id].type].desc.num_residuals;
+  return n;
+}
+
+// ---------------------------------------------------------------- Jacobian layout
+namespace {
+struct ActiveBlock {
+  int index;     // program index of the parameter block
+  int argument;  // position among the ACTIVE arguments of the residual block
+  int tangent;
+};
+// The active parameter blocks of residual block `id`, in argument order.
+inline int CollectActive(const Program& program, int32_t id, ActiveBlock* out) {
+  const ProblemImpl* problem = program.problem();
+  const ResidualBlockRef ref = problem->residual_blocks()[id];
+  const ResidualTypeStore& t = problem->types()[ref.type];
+  const int nb = t.desc.num_parameter_blocks;
+  int n = 0;
+  for (int j = 0; j < nb; ++j) {
+    const ParameterBlock* pb =
+        problem->parameter_blocks()[t.parameter_blocks[static_cast<size_t>(ref.local) * nb + j]]
+            .get();
+    if (program.IsActive(pb)) {
+      out[n] = ActiveBlock{pb->index, n, pb->TangentSize()};
+      ++n;
+    }
+  }
+  return n;
+}
+inline int NumResidualsOf(const Program& program, int32_t id) {
+  const ProblemImpl* problem = program.problem();
+  return problem->types()[problem->residual_blocks()[id].type].desc.num_residuals;
+}
+}  // namespace
+
+void BuildJacobianLayout(const Program& program, int jacobian_format, int num_eliminate_blocks,
+                         JacobianLayout* layout) {
+  const auto& rbs = program.residual_blocks();
+  const int nrb = static_cast<int>(rbs.size());
+  layout->jacobian_format = jacobian_format;
+  layout->num_eliminate_blocks = num_eliminate_blocks;
+  layout->residual_layout.resize(nrb);
+  layout->jacobian_per_residual_layout.resize(nrb);
+  layout->cell_positions.clear();
+  ActiveBlock blocks[CB200_MAX_PARAMETER_BLOCKS];
+
+  // Pass 1: residual positions, size of the E region, size of the offsets table.
+  int64_t e_size = 0, total = 0, offsets = 0;
+  int residual_pos = 0;
+  for (int i = 0; i < nrb; ++i) {
+    const int kres = NumResidualsOf(program, rbs[i]);
+    layout->residual_layout[i] = residual_pos;
+    residual_pos += kres;
+    const int na = CollectActive(program, rbs[i], blocks);
+    for (int a = 0; a < na; ++a) {
+      const int64_t cell = static_cast<int64_t>(kres) * blocks[a].tangent;
+      total += cell;
+      if (blocks[a].index < num_eliminate_blocks) e_size += cell;
+    }
+    offsets += static_cast<int64_t>(na) * kres;
+  }
+  layout->num_residuals = residual_pos;
+  layout->num_jacobian_values = total;
+  layout->jacobian_per_residual_offsets.assign(offsets, -1);
+  if (total > std::numeric_limits<int32_t>::max()) {
+    std::fprintf(stderr, "Jacobian has %lld values; the layouts are 32-bit (block_structure.h)\n",
+                 static_cast<long long>(total));
+    std::abort();
+  }
+
+  // Pass 2: positions.
+  int32_t* off = layout->jacobian_per_residual_offsets.data();
+  int cursor = 0;
+  if (jacobian_format == CB200_JACOBIAN_BLOCK_SPARSE) {
+    // E cells first in residual-block order, then F cells (block_jacobian_writer.cc:72-150).
+    int32_t e_pos = 0, f_pos = static_cast<int32_t>(e_size);
+    for (int i = 0; i < nrb; ++i) {
+      const int kres = NumResidualsOf(program, rbs[i]);
+      layout->jacobian_per_residual_layout[i] = cursor;
+      const int na = CollectActive(program, rbs[i], blocks);
+      for (int a = 0; a < na; ++a) {
+        int32_t& pos = blocks[a].index < num_eliminate_blocks ? e_pos : f_pos;
+        layout->cell_positions.push_back(pos);
+        for (int k = 0; k < kres; ++k) {
+          off[cursor++] = pos;
+          pos += blocks[a].tangent;
+        }
+      }
+    }
+  } else {
+    // Scalar rows; inside a row, blocks in increasing parameter-block index
+    // (compressed_row_jacobian_writer.cc:240-300).
+    int32_t row_start = 0;
+    for (int i = 0; i < nrb; ++i) {
+      const int kres = NumResidualsOf(program, rbs[i]);
+      layout->jacobian_per_residual_layout[i] = cursor;
+      const int na = CollectActive(program, rbs[i], blocks);
+      ActiveBlock sorted[CB200_MAX_PARAMETER_BLOCKS];
+      std::copy(blocks, blocks + na, sorted);
+      std::sort(sorted, sorted + na,
+                [](const ActiveBlock& x, const ActiveBlock& y) { return x.index < y.index; });
+      int row_width = 0;
+      for (int a = 0; a < na; ++a) row_width += sorted[a].tangent;
+      int col_pos = 0;
+      for (int a = 0; a < na; ++a) {
+        for (int r = 0; r < kres; ++r)
+          off[cursor + r + kres * sorted[a].argument] = row_start + r * row_width + col_pos;
+        col_pos += sorted[a].tangent;
+      }
+      cursor += na * kres;
+      row_start += kres * row_width;
+    }
+  }
+}
+
+std::unique_ptr<SparseMatrix> CreateJacobianFromLayout(const Program& program,
+                                                       const JacobianLayout& layout) {
+  const auto& rbs = program.residual_blocks();
+  const int nrb = static_cast<int>(rbs.size());
+  ActiveBlock blocks[CB200_MAX_PARAMETER_BLOCKS];
+  if (layout.jacobian_format == CB200_JACOBIAN_BLOCK_SPARSE) {
+    // block_jacobian_writer.cc:192-250
+    auto* bs = new CompressedRowBlockStructure;
+    bs->cols.resize(program.NumParameterBlocks());
+    int cursor = 0;
+    for (int i = 0; i < program.NumParameterBlocks(); ++i) {
+      bs->cols[i].size = program.parameter_blocks()[i]->TangentSize();
+      bs->cols[i].position = cursor;
+      cursor += bs->cols[i].size;
+    }
+    bs->rows.resize(nrb);
+    bs->row_cell_begin.resize(nrb + 1);
+    bs->cells.reserve(layout.cell_positions.size());
+    size_t cell_cursor = 0;
+    for (int i = 0; i < nrb; ++i) {
+      bs->rows[i].size = NumResidualsOf(program, rbs[i]);
+      bs->rows[i].position = layout.residual_layout[i];
+      bs->row_cell_begin[i] = static_cast<int32_t>(bs->cells.size());
+      const int na = CollectActive(program, rbs[i], blocks);
+      const size_t first = bs->cells.size();
+      for (int a = 0; a < na; ++a) {
+        Cell c;
+        c.block_id = blocks[a].index;
+        c.position = layout.cell_positions[cell_cursor++];
+        bs->cells.push_back(c);
+      }
+      std::sort(bs->cells.begin() + first, bs->cells.end(), [](const Cell& x, const Cell& y) {
+        return x.block_id != y.block_id ? x.block_id < y.block_id : x.position < y.position;
+      });
+    }
+    bs->row_cell_begin[nrb] = static_cast<int32_t>(bs->cells.size());
+    return std::make_unique<BlockSparseMatrix>(bs, layout.num_jacobian_values);
+  }
+  // compressed_row_jacobian_writer.cc:93-193
+  const int num_cols = program.NumEffectiveParameters();
+  auto m = std::make_unique<CompressedRowSparseMatrix>(
+      layout.num_residuals, num_cols, layout.num_jacobian_values + num_cols);
+  int* rows = m->mutable_rows();
+  int* cols = m->mutable_cols();
+  rows[0] = 0;
+  int row_pos = 0;
+  for (int i = 0; i < nrb; ++i) {
+    const int kres = NumResidualsOf(program, rbs[i]);
+    const int na = CollectActive(program, rbs[i], blocks);
+    std::sort(blocks, blocks + na,
+              [](const ActiveBlock& x, const ActiveBlock& y) { return x.index < y.index; });
+    int width = 0;
+    for (int a = 0; a < na; ++a) width += blocks[a].tangent;
+    for (int r = 0; r < kres; ++r) rows[row_pos + r + 1] = rows[row_pos + r] + width;
+    int col_pos = 0;
+    for (int a = 0; a < na; ++a) {
+      const int delta = program.parameter_blocks()[blocks[a].index]->delta_offset;
+      for (int r = 0; r < kres; ++r)
+        for (int c = 0; c < blocks[a].tangent; ++c)
+          cols[rows[row_pos + r] + col_pos + c] = delta + c;
+      col_pos += blocks[a].tangent;
+    }
+    row_pos += kres;
+  }
+  m->set_num_nonzeros(layout.num_jacobian_values);
+  // PopulateJacobianRowAndColumnBlockVectors (compressed_row_jacobian_writer.cc:46-70)
+  auto& col_blocks = *m->mutable_col_blocks();
+  int cursor = 0;
+  for (const ParameterBlock* pb : program.parameter_blocks()) {
+    Block b; b.size = pb->TangentSize(); b.position = cursor; cursor += b.size;
+    col_blocks.push_back(b);
+  }
+  auto& row_blocks = *m->mutable_row_blocks();
+  for (int i = 0; i < nrb; ++i) {
+    Block b; b.size = NumResidualsOf(program, rbs[i]); b.position = layout.residual_layout[i];
+    row_blocks.push_back(b);
+  }
+  return m;
+}
+
+// ------------------------------------------------------------ ProgramEvaluatorCUDA
+namespace {
+
+class ProgramEvaluatorCUDA final : public Evaluator {
+ public:
+  ProgramEvaluatorCUDA(const Evaluator::Options& options, Program* program, int jacobian_format)
+      : options_(options), program_(program) {
+    BuildJacobianLayout(*program, jacobian_format, std::max(0, options.num_eliminate_blocks),
+                        &layout_);
+  }
+  ~ProgramEvaluatorCUDA() override {
+    if (engine_) cb200_engine_destroy(engine_);
+    if (plus_jacobians_) cb200_host_free(plus_jacobians_);
+  }
+
+  // RegisteredCUDAEvaluators::Init (registered_cuda_evaluators.cc:226-280).
+  bool Init(std::string* error) {
+    int rc = cb200_engine_create(options_.device, &engine_);
+    if (rc != CB200_OK) {
+      *error = "cb200_engine_create failed: no usable CUDA device " +
+               std::to_string(options_.device) + " (there is no CPU fallback)";
+      engine_ = nullptr;
+      return false;
+    }
+    ProblemImpl* problem = program_->problem();
+    const auto& active = program_->parameter_blocks();
+    const auto& constant = program_->constant_parameter_blocks();
+    std::vector<cb200_parameter_block> blocks;
+    blocks.reserve(active.size() + constant.size());
+    // engine block id of every problem parameter block
+    std::vector<int32_t> engine_id(problem->parameter_blocks().size(), -1);
+    int plus_pool = 0;
+    for (const ParameterBlock* pb : active) {
+      cb200_parameter_block b;
+      b.size = pb->size;
+      b.tangent_size = pb->TangentSize();
+      b.state_offset = pb->state_offset;
+      b.delta_offset = pb->delta_offset;
+      b.plus_jacobian_offset = -1;
+      if (pb->manifold) {
+        b.plus_jacobian_offset = plus_pool;
+        plus_pool += pb->size * b.tangent_size;
+        manifold_blocks_.push_back(pb);
+      }
+      engine_id[pb->id] = static_cast<int32_t>(blocks.size());
+      blocks.push_back(b);
+    }
+    for (const ParameterBlock* pb : constant) {
+      cb200_parameter_block b;
+      b.size = pb->size;
+      b.tangent_size = pb->TangentSize();
+      b.state_offset = pb->state_offset;
+      b.delta_offset = -1;
+      b.plus_jacobian_offset = -1;
+      engine_id[pb->id] = static_cast<int32_t>(blocks.size());
+      blocks.push_back(b);
+    }
+    plus_pool_ = plus_pool;
+    if (plus_pool > 0)
+      plus_jacobians_ = static_cast<double*>(cb200_host_alloc(sizeof(double) * plus_pool));
+    std::vector<double> constant_state(program_->NumConstantParameters() + 1);
+    program_->ConstantParameterBlocksToStateVector(constant_state.data());
+    rc = cb200_engine_set_parameter_blocks(
+        engine_, static_cast<int32_t>(active.size()), static_cast<int32_t>(constant.size()),
+        blocks.data(), program_->NumParameters(), program_->NumEffectiveParameters(),
+        constant_state.data(), program_->NumConstantParameters(), plus_pool);
+    if (rc != CB200_OK) return Fail(error);
+
+    // Bucket the program's residual blocks by type, keeping their program POSITION.
+    const auto& rbs = program_->residual_blocks();
+    const auto& refs = problem->residual_blocks();
+    auto& types = problem->types();
+    std::vector<std::vector<int32_t>> position(types.size()), local(types.size());
+    for (int i = 0; i < static_cast<int>(rbs.size()); ++i) {
+      const ResidualBlockRef ref = refs[rbs[i]];
+      position[ref.type].push_back(i);
+      local[ref.type].push_back(ref.local);
+    }
+    for (size_t ti = 0; ti < types.size(); ++ti) {
+      const ResidualTypeStore& t = types[ti];
+      const int32_t n = static_cast<int32_t>(position[ti].size());
+      if (n == 0) continue;
+      const int nb = t.desc.num_parameter_blocks;
+      std::vector<int32_t> ids(static_cast<size_t>(n) * nb);
+      std::vector<char> functors(static_cast<size_t>(n) * t.desc.functor_size);
+      std::vector<int32_t> loss_index(n);
+      for (int32_t k = 0; k < n; ++k) {
+        const int32_t l = local[ti][k];
+        for (int j = 0; j < nb; ++j)
+          ids[static_cast<size_t>(k) * nb + j] =
+              engine_id[t.parameter_blocks[static_cast<size_t>(l) * nb + j]];
+        std::memcpy(functors.data() + static_cast<size_t>(k) * t.desc.functor_size,
+                    t.functors.data() + static_cast<size_t>(l) * t.desc.functor_size,
+                    t.desc.functor_size);
+        loss_index[k] = t.loss_index[l];
+      }
+      const int32_t num_losses = static_cast<int32_t>(t.loss_objects.size());
+      rc = cb200_engine_add_residual_blocks(engine_, &t.desc, n, position[ti].data(), ids.data(),
+                                            functors.data(), t.loss_table.data(), num_losses,
+                                            num_losses > 1 ? loss_index.data() : nullptr);
+      if (rc != CB200_OK) return Fail(error);
+    }
+    rc = cb200_engine_set_layout(
+        engine_, layout_.jacobian_format, static_cast<int32_t>(rbs.size()), layout_.num_residuals,
+        layout_.residual_layout.data(), layout_.jacobian_per_residual_layout.data(),
+        layout_.jacobian_per_residual_offsets.data(),
+        static_cast<int64_t>(layout_.jacobian_per_residual_offsets.size()),
+        layout_.num_jacobian_values);
+    if (rc != CB200_OK) return Fail(error);
+    rc = cb200_engine_set_shard(engine_, options_.shard_rank, options_.shard_world_size);
+    if (rc != CB200_OK) return Fail(error);
+    rc = cb200_engine_finalize(engine_);
+    if (rc != CB200_OK) return Fail(error);
+    if (options_.nccl_unique_id && options_.shard_world_size > 1) {
+      rc = cb200_engine_comm_init(engine_, options_.nccl_unique_id, options_.shard_rank,
+                                  options_.shard_world_size);
+      if (rc != CB200_OK) return Fail(error);
+    }
+    return true;
+  }
+
+  std::unique_ptr<SparseMatrix> CreateJacobian() const override {
+    return CreateJacobianFromLayout(*program_, layout_);
+  }
+
+  bool Evaluate(const EvaluateOptions& evaluate_options, const double* state, double* cost,
+                double* residuals, double* gradient, SparseMatrix* jacobian) override {
+    const auto start = std::chrono::steady_clock::now();
+    // ParameterBlock::SetState -> UpdatePlusJacobian (parameter_block.h:91-99,312-338):
+    // the plus-Jacobians of the blocks with a manifold, at the new state.
+    if (jacobian != nullptr || gradient != nullptr) {
+      double* cursor = plus_jacobians_;
+      for (const ParameterBlock* pb : manifold_blocks_) {
+        const int n = pb->size * pb->TangentSize();
+        if (!pb->manifold->PlusJacobian(state + pb->state_offset, cursor)) return false;
+        for (int i = 0; i < n; ++i)
+          if (!std::isfinite(cursor[i])) return false;
+        cursor += n;
+      }
+    }
+    const uint32_t flags = evaluate_options.apply_loss_function ? CB200_APPLY_LOSS_FUNCTION : 0u;
+    const int rc = cb200_engine_evaluate(engine_, state, plus_jacobians_, flags, cost, residuals,
+                                         gradient, jacobian ? jacobian->mutable_values() : nullptr);
+    const double seconds =
+        std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    CallStatistics& total = statistics_["Evaluator::Total"];
+    total.time += seconds;
+    total.calls++;
+    CallStatistics& kind = statistics_[(gradient == nullptr && jacobian == nullptr)
+                                           ? "Evaluator::Residual"
+                                           : "Evaluator::Jacobian"];
+    kind.time += seconds;
+    kind.calls++;
+    if (rc < 0) {
+      std::fprintf(stderr, "cb200_engine_evaluate: %s\n", cb200_engine_last_error(engine_));
+      std::abort();  // CUDA API failure: the reference CHECK-aborts (cuda_buffer.h:61-79)
+    }
+    return rc == CB200_OK;
+  }
+
+  bool Plus(const double* state, const double* delta, double* state_plus_delta) const override {
+    return program_->Plus(state, delta, state_plus_delta);
+  }
+  int NumParameters() const override { return program_->NumParameters(); }
+  int NumEffectiveParameters() const override { return program_->NumEffectiveParameters(); }
+  int NumResiduals() const override { return layout_.num_residuals; }
+  std::map<std::string, CallStatistics> Statistics() const override { return statistics_; }
+  cb200_engine* engine() const override { return engine_; }
+  const JacobianLayout* layout() const override { return &layout_; }
+
+ private:
+  bool Fail(std::string* error) {
+    *error = std::string("evaluation engine: ") + cb200_engine_last_error(engine_);
+    return false;
+  }
+  Evaluator::Options options_;
+  Program* program_;
+  JacobianLayout layout_;
+  cb200_engine* engine_ = nullptr;
+  std::vector<const ParameterBlock*> manifold_blocks_;
+  double* plus_jacobians_ = nullptr;
+  int plus_pool_ = 0;
+  std::map<std::string, CallStatistics> statistics_;
+};
+
+}  // namespace
+
+std::unique_ptr<Evaluator> Evaluator::Create(const Evaluator::Options& options, Program* program,
+                                             std::string* error) {
+  int format;
+  switch (options.linear_solver_type) {
+    case DENSE_SCHUR:
+    case SPARSE_SCHUR:
+    case ITERATIVE_SCHUR:
+    case CGNR:
+      format = options.sparse_linear_algebra_library_type == CUDA_SPARSE
+                   ? CB200_JACOBIAN_COMPRESSED_ROW
+                   : CB200_JACOBIAN_BLOCK_SPARSE;
+      break;
+    case SPARSE_NORMAL_CHOLESKY:
+      if (options.dynamic_sparsity) {
+        *error = "The CUDA evaluator stores the Jacobian as BlockSparseMatrix or "
+                 "CompressedRowSparseMatrix only (dynamic_sparsity is not supported).";
+        return nullptr;
+      }
+      format = CB200_JACOBIAN_BLOCK_SPARSE;
+      break;
+    case DENSE_QR:
+    case DENSE_NORMAL_CHOLESKY:
+      *error = "The CUDA evaluator stores the Jacobian as BlockSparseMatrix or "
+               "CompressedRowSparseMatrix only (dense linear solvers are not supported).";
+      return nullptr;
+    default:
+      *error = "Invalid Linear Solver Type. Unable to create evaluator.";
+      return nullptr;
+  }
+  if (!options.use_cuda) {
+    *error = "This library only provides the CUDA evaluator (use_cuda must be true).";
+    return nullptr;
+  }
+  auto evaluator = std::make_unique<ProgramEvaluatorCUDA>(options, program, format);
+  if (!evaluator->Init(error)) return nullptr;
+  return evaluator;
+}
+
+}  // namespace internal
+}  // namespace ceres

@@ -1,0 +1,109 @@
+// Loss functions evaluated on the device.
+//
+// Same classes and Evaluate(s, rho[3]) contract as the reference's
+// include/ceres/loss_function_cuda.h:52-149 (which mirror the CPU losses of
+// internal/ceres/loss_function.cc:44-82): rho[0] = rho(s), rho[1] = rho'(s),
+// rho[2] = rho''(s) for s = ||r||^2.  No virtual Evaluate: the kernel is
+// instantiated per loss type.  LossFunctionCUDABase exists only so ProblemCUDA can
+// own heterogeneous loss objects (problem_cuda.h:455-460).
+#ifndef CERES_B200_LOSS_FUNCTION_CUDA_H_
+#define CERES_B200_LOSS_FUNCTION_CUDA_H_
+
+#include <cmath>
+#include <limits>
+
+#include "ceres/internal/cuda_defs.h"
+
+namespace ceres {
+
+class LossFunctionCUDABase {
+ public:
+  virtual ~LossFunctionCUDABase() {}
+};
+
+// rho(s) = s
+class TrivialLossCUDA : public LossFunctionCUDABase {
+ public:
+  HOST_DEVICE void Evaluate(double s, double rho[3]) const {
+    rho[0] = s;
+    rho[1] = 1.0;
+    rho[2] = 0.0;
+  }
+};
+
+// rho(s) = s for s <= a^2, 2 a sqrt(s) - a^2 beyond.
+class HuberLossCUDA : public LossFunctionCUDABase {
+ public:
+  HOST_DEVICE explicit HuberLossCUDA(double a) : a_(a), b_(a * a) {}
+  HOST_DEVICE void Evaluate(double s, double rho[3]) const {
+    if (s > b_) {
+      const double r = sqrt(s);
+      rho[0] = 2.0 * a_ * r - b_;
+      const double d = a_ / r;
+      const double tiny = 2.2250738585072014e-308;  // numeric_limits<double>::min()
+      rho[1] = d > tiny ? d : tiny;
+      rho[2] = -rho[1] / (2.0 * s);
+    } else {
+      rho[0] = s;
+      rho[1] = 1.0;
+      rho[2] = 0.0;
+    }
+  }
+
+ private:
+  double a_;
+  double b_;
+};
+
+// rho(s) = a^2 log(1 + s / a^2)
+class CauchyLossCUDA : public LossFunctionCUDABase {
+ public:
+  HOST_DEVICE explicit CauchyLossCUDA(double a) : b_(a * a), c_(1 / b_) {}
+  HOST_DEVICE void Evaluate(double s, double rho[3]) const {
+    const double sum = 1.0 + s * c_;
+    const double inv = 1.0 / sum;
+    rho[0] = b_ * log(sum);
+    const double tiny = 2.2250738585072014e-308;
+    rho[1] = inv > tiny ? inv : tiny;
+    rho[2] = -c_ * (inv * inv);
+  }
+
+ private:
+  double b_;
+  double c_;
+};
+
+// a * rho(s)
+template <typename LossFunctionCUDA>
+class ScaledLossCUDA : public LossFunctionCUDABase {
+ public:
+  HOST_DEVICE ScaledLossCUDA(const LossFunctionCUDA& rho, double a) : rho_(rho), a_(a) {}
+  HOST_DEVICE void Evaluate(double s, double rho[3]) const {
+    rho_.Evaluate(s, rho);
+    rho[0] *= a_;
+    rho[1] *= a_;
+    rho[2] *= a_;
+  }
+
+ private:
+  LossFunctionCUDA rho_;
+  double a_;
+};
+
+template <>
+class ScaledLossCUDA<TrivialLossCUDA> : public LossFunctionCUDABase {
+ public:
+  HOST_DEVICE ScaledLossCUDA(const TrivialLossCUDA&, double a) : a_(a) {}
+  HOST_DEVICE void Evaluate(double s, double rho[3]) const {
+    rho[0] = a_ * s;
+    rho[1] = a_;
+    rho[2] = 0.0;
+  }
+
+ private:
+  double a_;
+};
+
+}  // namespace ceres
+
+#endif  // CERES_B200_LOSS_FUNCTION_CUDA_H_

@@ -1,0 +1,1 @@
+#include "ceres/cost_function.h"

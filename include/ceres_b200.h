@@ -1,0 +1,216 @@
+/* ceres_b200.h — C ABI of the B200-native residual/Jacobian evaluation engine.
+ *
+ * This is the drop-in boundary for the one hot path of jwmak/ceres-solver-cuda:
+ * ProgramEvaluatorCUDA::Evaluate -> RegisteredCUDAEvaluators::{Init,Evaluate}
+ * -> per-type AutoDiffResidualBlockCUDAEvaluator::{Init,Evaluate} -> EvaluateKernel.
+ * Plain pointers and sizes only; every function returns an int status, no C++
+ * exceptions cross the boundary.  Each entry point cites the reference interface
+ * it replaces (paths relative to the reference tree).
+ *
+ * The only templated, user-TU-compiled piece is the launch thunk
+ * (cb200_launch_fn): user functors are templates on the scalar type, so the
+ * kernel that calls them has to be instantiated by nvcc in the user's translation
+ * unit (include/ceres/internal/evaluate_kernel.cuh emits it); everything else
+ * — device buffers, layouts, reductions, transfers, NCCL — is in libceres_b200.so.
+ */
+#ifndef CERES_B200_H_
+#define CERES_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB200_MAX_PARAMETER_BLOCKS 10 /* include/ceres/internal/parameter_dims.h users: <= 10 */
+
+/* status codes */
+#define CB200_OK 0
+#define CB200_EVALUATION_FAILED 1 /* a functor returned false or produced a non-finite value:
+                                     Evaluator::Evaluate returns false (internal/ceres/evaluator.h:119-124) */
+#define CB200_ERROR_CUDA (-1)
+#define CB200_ERROR_INVALID_ARGUMENT (-2)
+#define CB200_ERROR_NOT_FINALIZED (-3)
+#define CB200_ERROR_NCCL (-4)
+
+/* cb200_engine_evaluate flags */
+#define CB200_APPLY_LOSS_FUNCTION 1u /* Evaluator::EvaluateOptions::apply_loss_function */
+#define CB200_SKIP_HOST_COPY 2u      /* leave outputs on the device (see cb200_engine_device_ptr) */
+
+#define CB200_JACOBIAN_BLOCK_SPARSE 0   /* BlockJacobianWriter  (internal/ceres/block_jacobian_writer.cc) */
+#define CB200_JACOBIAN_COMPRESSED_ROW 1 /* CompressedRowJacobianWriter (compressed_row_jacobian_writer.cc) */
+
+typedef struct cb200_engine cb200_engine;
+
+/* One parameter block of the (reduced) program; replaces the device AoS record
+ * ParameterBlockCUDA (include/ceres/internal/parameter_block_cuda.h:44-117).
+ * Blocks [0, num_active) are Program::parameter_blocks() in order, blocks
+ * [num_active, num_active + num_constant) are Program::constant_parameter_blocks(). */
+typedef struct cb200_parameter_block {
+  int32_t size;                 /* ambient size */
+  int32_t tangent_size;         /* == size without a manifold */
+  int32_t state_offset;         /* active: into the state vector; constant: into constant_state */
+  int32_t delta_offset;         /* active: into the gradient / Jacobian columns; constant: -1 */
+  int32_t plus_jacobian_offset; /* offset (doubles) of the row-major size x tangent_size plus-Jacobian
+                                   in the pool passed to cb200_engine_evaluate; -1 = no manifold */
+} cb200_parameter_block;
+
+/* Arguments of one kernel launch for one residual-block type.  All pointers are
+ * device pointers owned by the engine.  Structure-of-arrays, argument-major:
+ * entry (arg j, residual block t) of a per-argument table is at [j * n + t]. */
+typedef struct cb200_launch_args {
+  int32_t n;                      /* residual blocks of this type on this rank */
+  uint32_t output_residuals;
+  uint32_t output_jacobian;
+  uint32_t output_gradient;
+  uint32_t apply_loss_function;
+  uint32_t crs;                   /* 1: Jacobian rows use the per-block row stride below */
+  const void* functors;           /* n cost functors, sizeof(CostFunctor) each */
+  const void* loss_table;         /* distinct loss objects of this type */
+  const int32_t* loss_index;      /* per block index into loss_table, or NULL when there is one entry */
+  const int32_t* parameter_block; /* [num_blocks][n] index into parameter_block_table */
+  const int32_t* jacobian_pos;    /* [num_blocks][n] offset of element (0,0) of the block in
+                                     jacobian_values (rank-local), -1 for a constant block */
+  const int32_t* jacobian_row_stride; /* [n] compressed-row: values between consecutive rows */
+  const int32_t* residual_pos;    /* [n] offset of the block's residuals (rank-local) */
+  const int32_t* parameter_block_table; /* int4 per block: state_offset, delta_offset,
+                                      tangent_size, plus_jacobian_offset; constant blocks have
+                                      delta_offset -1 and state_offset already shifted past the
+                                      active state */
+  const double* state;            /* [num_parameters | constant state] */
+  const double* plus_jacobians;
+  double* residuals;
+  double* jacobian_values;
+  double* gradient;
+  double* cost_partials;          /* one per thread block of this launch */
+  int32_t* status;                /* set non-zero when a functor fails / yields a non-finite value */
+} cb200_launch_args;
+
+/* Launch thunk: the single symbol compiled in the user's translation unit per
+ * <CostFunctor, LossFunctionCUDA, kNumResiduals, Ns...>.  Replaces
+ * AutoDiffResidualBlockCUDAEvaluator::Evaluate's kernel launch
+ * (include/ceres/internal/autodiff_residual_block_cuda_evaluator.h:248-250).
+ * `stream` is a cudaStream_t.  Returns a cudaError_t value. */
+typedef int (*cb200_launch_fn)(const cb200_launch_args* args, void* stream);
+
+/* Static description of a residual-block type; replaces the template arguments of
+ * AutoDiffResidualBlockCUDAEvaluator<CostFunctor, LossFunctionCUDA, kNumResiduals, Ns...>
+ * (include/ceres/internal/autodiff_residual_block_cuda_evaluator.h:60-94). */
+typedef struct cb200_residual_type {
+  int32_t num_residuals;
+  int32_t num_parameter_blocks;
+  int32_t parameter_block_sizes[CB200_MAX_PARAMETER_BLOCKS];
+  int32_t functor_size;      /* bytes */
+  int32_t loss_size;         /* bytes */
+  int32_t threads_per_block; /* of the launch thunk; fixes the number of cost partials */
+  cb200_launch_fn launch;
+} cb200_residual_type;
+
+/* ---- lifetime.  Replaces ContextImpl::InitCuda + RegisteredCUDAEvaluators ctor
+ * (internal/ceres/context_impl.cc:112-174, include/ceres/internal/registered_cuda_evaluators.h:64-70). */
+int cb200_engine_create(int device, cb200_engine** engine);
+void cb200_engine_destroy(cb200_engine* engine);
+const char* cb200_engine_last_error(const cb200_engine* engine);
+
+/* ---- structure upload.  Together these replace RegisteredCUDAEvaluators::Init
+ * (internal/ceres/registered_cuda_evaluators.cc:226-280). */
+
+/* SetupParameterBlocks (registered_cuda_evaluators.cc:123-198). */
+int cb200_engine_set_parameter_blocks(cb200_engine* engine, int32_t num_active,
+                                      int32_t num_constant,
+                                      const cb200_parameter_block* blocks,
+                                      int32_t num_parameters,
+                                      int32_t num_effective_parameters,
+                                      const double* constant_state,
+                                      int32_t num_constant_parameters,
+                                      int32_t plus_jacobian_pool_size);
+
+/* SetupResidualBlocks + per-type Init/SetupResidualBlocksOnDevice
+ * (registered_cuda_evaluators.cc:200-224,
+ *  autodiff_residual_block_cuda_evaluator.h:96-133,153-180).
+ * program_position[t] is the block's POSITION in program->residual_blocks()
+ * (the loop index the CPU evaluator uses, program_evaluator.h:186-236), not
+ * ResidualBlock::index().  parameter_block_ids is [n][num_parameter_blocks].
+ * loss_index may be NULL when num_losses == 1. */
+int cb200_engine_add_residual_blocks(cb200_engine* engine, const cb200_residual_type* type,
+                                     int32_t n, const int32_t* program_position,
+                                     const int32_t* parameter_block_ids, const void* functors,
+                                     const void* loss_table, int32_t num_losses,
+                                     const int32_t* loss_index);
+
+/* The layouts ProgramEvaluatorCUDA's constructor builds
+ * (internal/ceres/program_evaluator_cuda.h:69-91,159-170) exactly as the reference's
+ * writers emit them: residual_layout[num_residual_blocks],
+ * jacobian_per_residual_layout[num_residual_blocks] and
+ * jacobian_per_residual_offsets[sum over blocks of active_args * num_residuals]
+ * (BlockJacobianWriter / CompressedRowJacobianWriter::CreateJacobianPerResidualLayout,
+ *  block_jacobian_writer.cc:154-160, compressed_row_jacobian_writer.cc:240-300). */
+int cb200_engine_set_layout(cb200_engine* engine, int32_t jacobian_format,
+                            int32_t num_residual_blocks, int32_t num_residuals,
+                            const int32_t* residual_layout,
+                            const int32_t* jacobian_per_residual_layout,
+                            const int32_t* jacobian_per_residual_offsets,
+                            int64_t num_offsets, int64_t num_jacobian_values);
+
+/* Multi-GPU: this rank evaluates the contiguous range of residual blocks
+ * [floor(rank * n / world), floor((rank + 1) * n / world)) in program order
+ * (no reference equivalent; the reference is single-GPU).  Call before finalize. */
+int cb200_engine_set_shard(cb200_engine* engine, int32_t rank, int32_t world_size);
+
+/* Builds the device tables.  After this the structure is immutable. */
+int cb200_engine_finalize(cb200_engine* engine);
+
+/* NCCL communicator for the cost/gradient all-reduce.  unique_id is the 128-byte
+ * ncclUniqueId created by cb200_nccl_unique_id on rank 0 and broadcast by the caller. */
+int cb200_nccl_unique_id(void* unique_id_128_bytes);
+int cb200_engine_comm_init(cb200_engine* engine, const void* unique_id_128_bytes,
+                           int32_t rank, int32_t world_size);
+
+/* ---- the hot call.  Replaces RegisteredCUDAEvaluators::Evaluate
+ * (internal/ceres/registered_cuda_evaluators.cc:46-103).  All pointers are HOST
+ * pointers.  state has num_parameters doubles; plus_jacobians is the pool described
+ * by cb200_parameter_block::plus_jacobian_offset (may be NULL when the pool is
+ * empty).  cost must not be NULL; residuals / gradient / jacobian_values may each be
+ * NULL, exactly as in Evaluator::Evaluate (internal/ceres/evaluator.h:119-124).
+ * jacobian_values is the values array of the matrix returned by CreateJacobian();
+ * with sharding only this rank's slices are written.
+ * Returns CB200_OK, CB200_EVALUATION_FAILED, or an error. */
+int cb200_engine_evaluate(cb200_engine* engine, const double* state,
+                          const double* plus_jacobians, uint32_t flags, double* cost,
+                          double* residuals, double* gradient, double* jacobian_values);
+
+/* Device-resident variant: same work, inputs already on the device (state_device
+ * has num_parameters doubles, plus_jacobians_device may be NULL), outputs stay on
+ * the device; want_* select what is computed.  *cost is read back (8 bytes). */
+int cb200_engine_evaluate_device(cb200_engine* engine, const double* state_device,
+                                 const double* plus_jacobians_device, uint32_t flags,
+                                 int want_residuals, int want_gradient, int want_jacobian,
+                                 double* cost);
+
+/* Device buffers of the last evaluation, for a device-side consumer (a GPU linear
+ * solver).  which: 0 residuals, 1 gradient, 2 jacobian_values, 3 state. */
+void* cb200_engine_device_ptr(cb200_engine* engine, int which);
+
+/* This rank's slices: residual range and up to max_segments Jacobian value ranges
+ * as (global_offset, length, local_offset) triples.  Returns the segment count. */
+int cb200_engine_shard_info(cb200_engine* engine, int32_t* rb_begin, int32_t* rb_end,
+                            int32_t* residual_begin, int32_t* residual_end,
+                            int64_t* segments, int32_t max_segments);
+
+/* Timing of the last evaluation in milliseconds (CUDA events on the engine's
+ * stream): out[0] kernels only, out[1] kernels + reductions + all-reduce,
+ * out[2] whole call including host<->device copies.  out[3] = kernel launches. */
+int cb200_engine_last_timing(cb200_engine* engine, double* out4);
+
+/* Pinned host memory for the caller's output arrays (CreateJacobian's values):
+ * falls back to malloc when no CUDA device is present. */
+void* cb200_host_alloc(uint64_t bytes);
+void cb200_host_free(void* p);
+
+const char* cb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CERES_B200_H_ */

@@ -1,0 +1,271 @@
+// C interface of the test/bench driver (see driver.h).  Python binds it with
+// ctypes (ceres-solver-cuda_b200/binding.py).
+#include <cstring>
+
+#include "driver.h"
+
+using driver::DriverProblem;
+using ceres::internal::Evaluator;
+
+namespace {
+ceres::Manifold* MakeManifold(int kind, int param, int size) {
+  switch (kind) {
+    case 1: {  // SubsetManifold, param = bitmask of constant coordinates
+      std::vector<int> constant;
+      for (int i = 0; i < size; ++i)
+        if ((param >> i) & 1) constant.push_back(i);
+      return new ceres::SubsetManifold(size, constant);
+    }
+    case 2: return new ceres::QuaternionManifold;
+    case 3: return new ceres::EigenQuaternionManifold;
+    case 4:
+      switch (size - 4) {
+        case 3: return new ceres::ProductManifold<ceres::QuaternionManifold, ceres::EuclideanManifold<3>>;
+        case 6: return new ceres::ProductManifold<ceres::QuaternionManifold, ceres::EuclideanManifold<6>>;
+      }
+      return nullptr;
+    case 5:
+      switch (size - 4) {
+        case 3: return new ceres::ProductManifold<ceres::EigenQuaternionManifold, ceres::EuclideanManifold<3>>;
+        case 6: return new ceres::ProductManifold<ceres::EigenQuaternionManifold, ceres::EuclideanManifold<6>>;
+      }
+      return nullptr;
+  }
+  return nullptr;
+}
+
+const int kTypeBlocks[16] = {2, 2, 2, 1, 2, 2, 10, 1, 3, 3, 2, 2, 2, 3, 1, 4};
+const int kTypeFdata[16] = {2, 2, 2, 3, 7, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 43};
+}  // namespace
+
+extern "C" {
+
+// Builds the ProblemCUDA.  bulk != 0 uses ProblemCUDA::AddResidualBlocks for runs of
+// residual blocks of one type/loss; otherwise every block goes through
+// AddResidualBlock<...> with its own AutoDiffCostFunction, like user code.
+void* drv_create(int num_pb, const int* pb_size, const double* pb_values,
+                 const uint8_t* pb_constant, const int* pb_manifold_kind,
+                 const int* pb_manifold_param, int num_rb, const int* rb_type, const int* rb_pb,
+                 const int* rb_loss_kind, const double* rb_loss_a, const double* rb_loss_b,
+                 const double* fdata, int bulk) {
+  auto* dp = new DriverProblem;
+  dp->pb_offset.resize(num_pb);
+  dp->pb_size.assign(pb_size, pb_size + num_pb);
+  int64_t off = 0;
+  for (int i = 0; i < num_pb; ++i) {
+    dp->pb_offset[i] = off;
+    off += pb_size[i];
+  }
+  dp->values.assign(pb_values, pb_values + off);
+  for (int i = 0; i < num_pb; ++i) dp->problem.AddParameterBlock(dp->pb(i), pb_size[i]);
+
+  int64_t pb_cursor = 0, fd_cursor = 0;
+  int i = 0;
+  while (i < num_rb) {
+    const int type = rb_type[i];
+    if (type < 0 || type >= 16) { dp->error = "unknown cost type"; return dp; }
+    int j = i + 1;
+    while (j < num_rb && rb_type[j] == type && rb_loss_kind[j] == rb_loss_kind[i] &&
+           rb_loss_a[j] == rb_loss_a[i] && rb_loss_b[j] == rb_loss_b[i])
+      ++j;
+    const int n = j - i;
+    bool handled = false, ok = false;
+    ok = driver::AddRunBal(*dp, type, rb_loss_kind[i], rb_loss_a[i], rb_loss_b[i], n,
+                           rb_pb + pb_cursor, fdata + fd_cursor, bulk != 0, &handled);
+    if (!handled)
+      ok = driver::AddRunPose(*dp, type, rb_loss_kind[i], rb_loss_a[i], rb_loss_b[i], n,
+                              rb_pb + pb_cursor, fdata + fd_cursor, bulk != 0, &handled);
+    if (!handled)
+      ok = driver::AddRunTests(*dp, type, rb_loss_kind[i], rb_loss_a[i], rb_loss_b[i], n,
+                               rb_pb + pb_cursor, fdata + fd_cursor, bulk != 0, &handled);
+    if (!handled || !ok) {
+      dp->error = "cost type / loss combination not instantiated in the test driver";
+      return dp;
+    }
+    pb_cursor += static_cast<int64_t>(n) * kTypeBlocks[type];
+    fd_cursor += static_cast<int64_t>(n) * kTypeFdata[type];
+    i = j;
+  }
+  for (int k = 0; k < num_pb; ++k) {
+    if (pb_manifold_kind && pb_manifold_kind[k] != 0) {
+      ceres::Manifold* m = MakeManifold(pb_manifold_kind[k], pb_manifold_param[k], pb_size[k]);
+      if (!m) { dp->error = "manifold kind not available in the test driver"; return dp; }
+      dp->problem.SetManifold(dp->pb(k), m);
+    }
+    if (pb_constant && pb_constant[k]) dp->problem.SetParameterBlockConstant(dp->pb(k));
+  }
+  return dp;
+}
+
+void drv_destroy(void* h) { delete static_cast<DriverProblem*>(h); }
+
+const char* drv_error(void* h) { return static_cast<DriverProblem*>(h)->error.c_str(); }
+
+// Program + layout (+ evaluator when with_device != 0).  Returns 1 on success.
+int drv_build(void* h, int reduce, int schur_reorder, int num_eliminate_blocks,
+              int jacobian_format, int with_device, int device, int rank, int world_size,
+              const void* nccl_unique_id) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  if (!dp->error.empty()) return 0;
+  ceres::internal::ProblemImpl* impl = dp->problem.mutable_problem()->mutable_impl();
+  dp->evaluator.reset();
+  dp->jacobian.reset();
+  dp->full_program = std::make_unique<ceres::internal::Program>(impl);
+  dp->fixed_cost = 0.0;
+  if (reduce) {
+    std::vector<double*> removed;
+    dp->program = dp->full_program->CreateReducedProgram(&removed, &dp->fixed_cost, &dp->error);
+    if (!dp->program) return 0;
+  } else {
+    dp->program = std::make_unique<ceres::internal::Program>(*dp->full_program);
+    dp->program->SetParameterOffsetsAndIndex();
+  }
+  if (schur_reorder && num_eliminate_blocks > 0)
+    dp->program->LexicographicallyOrderResidualBlocks(num_eliminate_blocks);
+
+  if (!with_device) {
+    ceres::internal::BuildJacobianLayout(*dp->program, jacobian_format, num_eliminate_blocks,
+                                         &dp->layout);
+    dp->jacobian = ceres::internal::CreateJacobianFromLayout(*dp->program, dp->layout);
+    return 1;
+  }
+  Evaluator::Options options;
+  options.num_eliminate_blocks = num_eliminate_blocks;
+  options.linear_solver_type = ceres::ITERATIVE_SCHUR;
+  options.sparse_linear_algebra_library_type =
+      jacobian_format == CB200_JACOBIAN_COMPRESSED_ROW ? ceres::CUDA_SPARSE : ceres::NO_SPARSE;
+  options.use_cuda = true;
+  options.registered_cuda_evaluators = dp->problem.mutable_registered_cuda_evaluators();
+  options.device = device;
+  options.shard_rank = rank;
+  options.shard_world_size = world_size;
+  options.nccl_unique_id = nccl_unique_id;
+  dp->evaluator = Evaluator::Create(options, dp->program.get(), &dp->error);
+  if (!dp->evaluator) return 0;
+  dp->layout = *dp->evaluator->layout();
+  dp->jacobian = dp->evaluator->CreateJacobian();
+  return 1;
+}
+
+// dims: [num_parameters, num_effective_parameters, num_residuals, num_residual_blocks,
+//        num_parameter_blocks, num_jacobian_values, values_size, num_cells,
+//        per_residual_offsets_size, num_constant_parameters]
+void drv_dims(void* h, int64_t* dims) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  const auto& p = *dp->program;
+  dims[0] = p.NumParameters();
+  dims[1] = p.NumEffectiveParameters();
+  dims[2] = dp->layout.num_residuals;
+  dims[3] = p.NumResidualBlocks();
+  dims[4] = p.NumParameterBlocks();
+  dims[5] = dp->layout.num_jacobian_values;
+  dims[6] = dp->jacobian ? dp->jacobian->values_size() : 0;
+  dims[7] = static_cast<int64_t>(dp->layout.cell_positions.size());
+  dims[8] = static_cast<int64_t>(dp->layout.jacobian_per_residual_offsets.size());
+  dims[9] = p.NumConstantParameters();
+}
+
+double drv_fixed_cost(void* h) { return static_cast<DriverProblem*>(h)->fixed_cost; }
+
+void drv_initial_state(void* h, double* state) {
+  static_cast<DriverProblem*>(h)->program->ParameterBlocksToStateVector(state);
+}
+
+// Same `which` numbering as oracle_problem_get_ints.
+int64_t drv_get_ints(void* h, int which, int* out) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  std::vector<int> tmp;
+  const std::vector<int>* v = &tmp;
+  const auto* bsm = dynamic_cast<const ceres::internal::BlockSparseMatrix*>(dp->jacobian.get());
+  const auto* crs =
+      dynamic_cast<const ceres::internal::CompressedRowSparseMatrix*>(dp->jacobian.get());
+  switch (which) {
+    case 0: v = &dp->layout.residual_layout; break;
+    case 1: v = &dp->layout.jacobian_per_residual_layout; break;
+    case 2: v = &dp->layout.jacobian_per_residual_offsets; break;
+    case 3: tmp.assign(dp->program->residual_blocks().begin(), dp->program->residual_blocks().end()); break;
+    case 4: for (auto* pb : dp->program->parameter_blocks()) tmp.push_back(pb->id); break;
+    case 5: if (bsm) for (auto& b : bsm->block_structure()->cols) tmp.push_back(b.size); break;
+    case 6: if (bsm) for (auto& b : bsm->block_structure()->cols) tmp.push_back(b.position); break;
+    case 7: if (bsm) for (auto& b : bsm->block_structure()->rows) tmp.push_back(b.size); break;
+    case 8: if (bsm) for (auto& b : bsm->block_structure()->rows) tmp.push_back(b.position); break;
+    case 9: if (bsm) tmp = bsm->block_structure()->row_cell_begin; break;
+    case 10: if (bsm) for (auto& c : bsm->block_structure()->cells) tmp.push_back(c.block_id); break;
+    case 11: if (bsm) for (auto& c : bsm->block_structure()->cells) tmp.push_back(c.position); break;
+    case 12: if (crs) tmp.assign(crs->rows(), crs->rows() + crs->num_rows() + 1); break;
+    case 13: if (crs) tmp.assign(crs->cols(), crs->cols() + crs->values_size()); break;
+    case 14: for (auto* pb : dp->program->constant_parameter_blocks()) tmp.push_back(pb->id); break;
+    case 15: v = &dp->layout.cell_positions; break;
+    default: return -1;
+  }
+  if (out) std::copy(v->begin(), v->end(), out);
+  return static_cast<int64_t>(v->size());
+}
+
+void drv_pb_table(void* h, int* out) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  int i = 0;
+  for (auto* pb : dp->program->parameter_blocks()) {
+    out[4 * i + 0] = pb->index;
+    out[4 * i + 1] = pb->state_offset;
+    out[4 * i + 2] = pb->delta_offset;
+    out[4 * i + 3] = pb->TangentSize();
+    ++i;
+  }
+}
+
+// The pinned values array of the Jacobian created by Evaluator::CreateJacobian().
+double* drv_jacobian_values(void* h) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  return dp->jacobian ? dp->jacobian->mutable_values() : nullptr;
+}
+
+// Evaluator::Evaluate.  want_jacobian writes into drv_jacobian_values().
+// Returns 1 (true), 0 (false: evaluation failed), -1 (no evaluator).
+int drv_evaluate(void* h, const double* state, int apply_loss_function, double* cost,
+                 double* residuals, double* gradient, int want_jacobian) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  if (!dp->evaluator) return -1;
+  Evaluator::EvaluateOptions eo;
+  eo.apply_loss_function = apply_loss_function != 0;
+  return dp->evaluator->Evaluate(eo, state, cost, residuals, gradient,
+                                 want_jacobian ? dp->jacobian.get() : nullptr)
+             ? 1
+             : 0;
+}
+
+// Device-resident evaluation through the C ABI (inputs already in HBM).
+int drv_evaluate_device(void* h, int apply_loss_function, int want_residuals, int want_gradient,
+                        int want_jacobian, double* cost) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  if (!dp->evaluator) return -1;
+  return cb200_engine_evaluate_device(dp->evaluator->engine(), nullptr, nullptr,
+                                      apply_loss_function ? CB200_APPLY_LOSS_FUNCTION : 0u,
+                                      want_residuals, want_gradient, want_jacobian, cost);
+}
+
+int drv_timing(void* h, double* out4) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  if (!dp->evaluator) return -1;
+  return cb200_engine_last_timing(dp->evaluator->engine(), out4);
+}
+
+int drv_shard_info(void* h, int32_t* info4, int64_t* segments, int max_segments) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  if (!dp->evaluator) return -1;
+  return cb200_engine_shard_info(dp->evaluator->engine(), info4, info4 + 1, info4 + 2, info4 + 3,
+                                 segments, max_segments);
+}
+
+int drv_plus(void* h, const double* state, const double* delta, double* out) {
+  return static_cast<DriverProblem*>(h)->program->Plus(state, delta, out) ? 1 : 0;
+}
+
+void drv_dense_jacobian(void* h, double* dense) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  std::vector<double> d;
+  dp->jacobian->ToDenseMatrix(&d);
+  std::memcpy(dense, d.data(), d.size() * sizeof(double));
+}
+
+}  // extern "C"

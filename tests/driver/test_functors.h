@@ -1,0 +1,127 @@
+// Cost functors used only by the parity tests: device restatements of the
+// functors in the reference's own tests for this path.
+#ifndef TESTS_DRIVER_TEST_FUNCTORS_H_
+#define TESTS_DRIVER_TEST_FUNCTORS_H_
+
+#include "ceres/internal/cuda_defs.h"
+#include "ceres/rotation.h"
+
+namespace test_functors {
+
+// internal/ceres/evaluator_cuda_test.cu.cc:115-164  <2, 7, 3>
+struct SnavelyReprojectionErrorNoRadialDistortion {
+  HOST_DEVICE SnavelyReprojectionErrorNoRadialDistortion(double x, double y)
+      : observed_x(x), observed_y(y) {}
+  template <typename T>
+  HOST_DEVICE bool operator()(const T* const camera, const T* const point, T* residuals) const {
+    T p[3];
+    ceres::AngleAxisRotatePoint(camera, point, p);
+    p[0] += camera[3];
+    p[1] += camera[4];
+    p[2] += camera[5];
+    const T xp = -p[0] / p[2];
+    const T yp = -p[1] / p[2];
+    const T& focal = camera[6];
+    residuals[0] = focal * xp - observed_x;
+    residuals[1] = focal * yp - observed_y;
+    return true;
+  }
+  double observed_x, observed_y;
+};
+
+// evaluator_cuda_test.cu.cc:83-109  <3, 3>
+struct PointDisplacementError {
+  HOST_DEVICE PointDisplacementError(double x, double y, double z) : x_(x), y_(y), z_(z) {}
+  template <typename T>
+  HOST_DEVICE bool operator()(const T* const point, T* residuals) const {
+    using ceres::abs;
+    residuals[0] = abs(x_) - abs(point[0]);
+    residuals[1] = abs(y_) - abs(point[1]);
+    residuals[2] = abs(z_) - abs(point[2]);
+    return true;
+  }
+  double x_, y_, z_;
+};
+
+// autodiff_cost_function_cuda_test.cu.cc:42-54  <1, 2, 2>
+struct BinaryScalarCost {
+  HOST_DEVICE explicit BinaryScalarCost(double a) : a_(a) {}
+  template <typename T>
+  HOST_DEVICE bool operator()(const T* const x, const T* const y, T* cost) const {
+    cost[0] = x[0] * y[0] + x[1] * y[1] - T(a_);
+    return true;
+  }
+  double a_;
+};
+
+// autodiff_cost_function_cuda_test.cu.cc:128-146  <1, 1 x 10>
+struct TenParameterCost {
+  template <typename T>
+  HOST_DEVICE bool operator()(const T* const x0, const T* const x1, const T* const x2,
+                              const T* const x3, const T* const x4, const T* const x5,
+                              const T* const x6, const T* const x7, const T* const x8,
+                              const T* const x9, T* cost) const {
+    cost[0] = *x0 + *x1 + *x2 + *x3 + *x4 + *x5 + *x6 + *x7 + *x8 + *x9;
+    return true;
+  }
+  char unused = 0;
+};
+
+// autodiff_cost_function_cuda_test.cu.cc:230-237  <2, 1>
+struct OnlyFillsOneOutputFunctor {
+  template <typename T>
+  HOST_DEVICE bool operator()(const T* x, T* output) const {
+    output[0] = x[0];
+    return true;
+  }
+  char unused = 0;
+};
+
+// Autodiff form of evaluator_test.cc:59-100 ParameterIgnoringCostFunction:
+// residual i = (i + 1) + sum_k sum_j kFactor (j + 1) x_k[j].
+template <int kFactor, int kNumResiduals, bool kSucceeds, int... Ns>
+struct AffineTestCost {
+  template <typename T>
+  HOST_DEVICE bool operator()(const T* const a, const T* const b, T* residuals) const {
+    const T* params[] = {a, b};
+    return Impl(params, residuals);
+  }
+  template <typename T>
+  HOST_DEVICE bool operator()(const T* const a, const T* const b, const T* const c,
+                              T* residuals) const {
+    const T* params[] = {a, b, c};
+    return Impl(params, residuals);
+  }
+  template <typename T>
+  HOST_DEVICE static bool Impl(const T* const* params, T* residuals) {
+    constexpr int sizes[] = {Ns...};
+#pragma unroll
+    for (int i = 0; i < kNumResiduals; ++i) {
+      T r(static_cast<double>(i + 1));
+#pragma unroll
+      for (int k = 0; k < static_cast<int>(sizeof...(Ns)); ++k) {
+#pragma unroll
+        for (int j = 0; j < sizes[k]; ++j)
+          r += params[k][j] * static_cast<double>(kFactor * (j + 1));
+      }
+      residuals[i] = r;
+    }
+    return kSucceeds;
+  }
+  char unused = 0;
+};
+
+// evaluator_test.cc:573-596  <2, 2>
+struct ParameterSensitiveCost {
+  template <typename T>
+  HOST_DEVICE bool operator()(const T* const x, T* residuals) const {
+    residuals[0] = x[0] * x[0];
+    residuals[1] = x[1] * x[1];
+    return true;
+  }
+  char unused = 0;
+};
+
+}  // namespace test_functors
+
+#endif  // TESTS_DRIVER_TEST_FUNCTORS_H_

@@ -1,0 +1,286 @@
+"""GPU parity tests: the CUDA path (through the public C++ API and the C ABI) against
+the oracle on the same seeded inputs.  Tolerances are north_star's: residual and
+Jacobian values 1e-12 relative, cost and gradient 1e-10 relative; structure bit-exact
+(tests/test_host_structure.py)."""
+import itertools
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+from ceres_b200 import binding as B
+from ceres_b200 import problems as P
+
+pytestmark = pytest.mark.gpu
+
+RTOL_VALUES = 1e-12
+RTOL_SUMS = 1e-10
+
+
+def _close(a, b, rtol, what):
+    """|a - b| <= rtol * max(|b|, scale): relative to the magnitude of the vector so
+    that exact zeros next to O(1e3) pixels are not held to an absolute 0."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    scale = max(float(np.max(np.abs(b))) if b.size else 0.0, 1e-300)
+    err = np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-3 * scale)) if b.size else 0.0
+    assert err <= rtol, f"{what}: max relative error {err:.3e} > {rtol:.0e}"
+
+
+def _check(spec, fmt=0, state=None, **kw):
+    op = O.OracleProblem(spec, jacobian_format=fmt, **kw)
+    cp = B.CudaProblem(spec, jacobian_format=fmt, **kw)
+    if state is None:
+        state = op.initial_state()
+    ok_o, c_o, r_o, g_o, j_o = op.evaluate(state)
+    cp.jacobian_values[:] = -1.0  # every value must be overwritten (no memset in the engine)
+    ok_c, c_c, r_c, g_c, j_c = cp.evaluate(state)
+    assert ok_o and ok_c
+    _close(c_c, c_o, RTOL_SUMS, "cost")
+    _close(r_c, r_o, RTOL_VALUES, "residuals")
+    _close(j_c[:op.num_jacobian_values], j_o[:op.num_jacobian_values], RTOL_VALUES, "jacobian")
+    _close(g_c, g_o, RTOL_SUMS, "gradient")
+    return op, cp
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_fork_fixture(fmt):
+    """internal/ceres/evaluator_cuda_test.cu.cc:280-459 (the fork's own GPU-vs-CPU test,
+    tolerance 1e-13 there)."""
+    op, cp = _check(P.evaluator_cuda_test_problem(), fmt)
+    ok, c_c, r_c, g_c, j_c = cp.evaluate()
+    ok, c_o, r_o, g_o, j_o = op.evaluate()
+    assert abs(c_c - c_o) <= 1e-13 * max(1.0, abs(c_o))
+    n = op.num_jacobian_values
+    assert np.linalg.norm(r_c - r_o) <= 1e-13 * np.linalg.norm(r_o)
+    assert np.linalg.norm(g_c - g_o) <= 1e-13 * np.linalg.norm(g_o)
+    assert np.linalg.norm(j_c[:n] - j_o[:n]) <= 1e-13 * np.linalg.norm(j_o[:n])
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+@pytest.mark.parametrize("loss", ["none", "huber", "cauchy"])
+def test_bal_small(fmt, loss):
+    _check(P.bal_problem(16, 300, 1200, seed=1, loss=loss), fmt)
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_bal_subset_manifold_and_constant_cameras(fmt):
+    _check(P.bal_problem(12, 200, 800, seed=2, subset_manifold=True, constant_cameras=3), fmt)
+
+
+def test_bal_s_shape_all_output_combinations():
+    """BAL "S" shape (16 x 22106, 83718 blocks): every combination of requested
+    outputs, as evaluator_test.cc:127-220 CheckAllEvaluationCombinations does."""
+    spec = P.bal_shape("S")
+    op = O.OracleProblem(spec)
+    cp = B.CudaProblem(spec)
+    x = op.initial_state()
+    ok, c_o, r_o, g_o, j_o = op.evaluate(x, num_threads=8)
+    for wr, wg, wj in itertools.product([False, True], repeat=3):
+        cp.jacobian_values[:] = -1.0
+        ok, c, r, g, j = cp.evaluate(x, residuals=wr, gradient=wg, jacobian=wj)
+        assert ok
+        _close(c, c_o, RTOL_SUMS, "cost")
+        if wr:
+            _close(r, r_o, RTOL_VALUES, "residuals")
+        if wg:
+            _close(g, g_o, RTOL_SUMS, "gradient")
+        if wj:
+            _close(j[:op.num_jacobian_values], j_o, RTOL_VALUES, "jacobian")
+
+
+def test_apply_loss_function_false():
+    spec = P.bal_problem(8, 100, 400, seed=3)
+    op = O.OracleProblem(spec)
+    cp = B.CudaProblem(spec)
+    x = op.initial_state()
+    _, c_o, r_o, g_o, j_o = op.evaluate(x, apply_loss_function=False)
+    _, c_c, r_c, g_c, j_c = cp.evaluate(x, apply_loss_function=False)
+    _close(c_c, c_o, RTOL_SUMS, "cost")
+    _close(r_c, r_o, RTOL_VALUES, "residuals")
+    _close(j_c[:op.num_jacobian_values], j_o, RTOL_VALUES, "jacobian")
+    _close(g_c, g_o, RTOL_SUMS, "gradient")
+
+
+@pytest.mark.parametrize("kind,a,b", [(P.LOSS_TRIVIAL, 0, 0), (P.LOSS_SCALED_HUBER, 1.0, 0.7),
+                                      (P.LOSS_SCALED_CAUCHY, 2.0, 1.3),
+                                      (P.LOSS_SCALED_TRIVIAL, 0, 0.4)])
+def test_other_losses(kind, a, b):
+    spec = P.bal_problem(6, 80, 300, seed=4)
+    spec.rb_loss_kind[:] = kind
+    spec.rb_loss_a[:] = a
+    spec.rb_loss_b[:] = b
+    _check(spec)
+
+
+def test_mixed_losses_in_one_type():
+    """Several loss objects of one type: exercises the loss table + per-block index."""
+    spec = P.bal_problem(6, 80, 300, seed=5)
+    spec.rb_loss_a[::3] = 0.5
+    spec.rb_loss_a[1::3] = 2.0
+    _check(spec)
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+@pytest.mark.parametrize("loss", ["none", "cauchy"])
+def test_pose_graph(fmt, loss):
+    _check(P.pose_graph_problem(300, 900, seed=5, loss=loss), fmt)
+
+
+def test_schur_reordered_program_uses_positions():
+    """SURVEY.md hazard 1: after LexicographicallyOrderResidualBlocks the program
+    position differs from the insertion index; values must land in position order."""
+    spec = P.bal_problem(9, 120, 500, seed=6)
+    perm = np.random.default_rng(1).permutation(spec.num_rb)
+    spec = P.ProblemSpec(pb_size=spec.pb_size, pb_values=spec.pb_values, rb_type=spec.rb_type[perm],
+                         rb_pb=spec.rb_pb.reshape(-1, 2)[perm].ravel(),
+                         fdata=spec.fdata.reshape(-1, 2)[perm].ravel(),
+                         rb_loss_kind=spec.rb_loss_kind[perm], rb_loss_a=spec.rb_loss_a[perm],
+                         rb_loss_b=spec.rb_loss_b[perm],
+                         num_eliminate_blocks=spec.num_eliminate_blocks)
+    for fmt in (0, 1):
+        _check(spec, fmt, schur_reorder=True)
+
+
+# ---- the reference's CPU evaluator tables through the CUDA path (evaluator_test.cc:227-560)
+def _xyz(b):
+    return {n: b.add_parameter_block(np.zeros(s)) for n, s in (("x", 2), ("y", 3), ("z", 4))}
+
+
+@pytest.mark.parametrize("fmt,nelim", [(0, 0), (0, 1), (0, 2), (0, 3), (1, 0)])
+def test_evaluator_test_tables(fmt, nelim):
+    b = P.ProblemBuilder()
+    v = _xyz(b)
+    b.set_manifold(v["y"], P.MANIFOLD_SUBSET, 0b001)
+    b.set_manifold(v["z"], P.MANIFOLD_SUBSET, 0b0010)
+    b.add_residual_block(P.AFFINE_1_2_23, [v["x"], v["y"]])
+    b.add_residual_block(P.AFFINE_2_3_24, [v["x"], v["z"]])
+    b.add_residual_block(P.AFFINE_3_4_34, [v["y"], v["z"]])
+    cp = B.CudaProblem(b.build(), jacobian_format=fmt, reduce=False, num_eliminate_blocks=nelim)
+    jac = np.array([1, 2, 2, 3, 0, 0, 0] * 2 + [2, 4, 0, 0, 2, 6, 8] * 3 +
+                   [0, 0, 6, 9, 3, 9, 12] * 4, float).reshape(9, 7)
+    for wr, wg, wj in itertools.product([False, True], repeat=3):
+        ok, c, r, g, j = cp.evaluate(np.zeros(9), residuals=wr, gradient=wg, jacobian=wj)
+        assert ok and c == (1 + 4 + 1 + 4 + 9 + 1 + 4 + 9 + 16) / 2.0
+        if wr:
+            assert r.tolist() == [1.0, 2.0, 1.0, 2.0, 3.0, 1.0, 2.0, 3.0, 4.0]
+        if wg:
+            assert g.tolist() == [15.0, 30.0, 66.0, 99.0, 42.0, 126.0, 168.0]
+        if wj:
+            assert np.array_equal(cp.dense_jacobian(), jac)
+
+
+def test_constant_parameter_table():
+    b = P.ProblemBuilder()
+    v = _xyz(b)
+    b.add_residual_block(P.AFFINE_1_2_23, [v["x"], v["y"]])
+    b.add_residual_block(P.AFFINE_2_3_24, [v["x"], v["z"]])
+    b.add_residual_block(P.AFFINE_3_4_34, [v["y"], v["z"]])
+    b.set_constant(v["z"])
+    cp = B.CudaProblem(b.build(), reduce=True)
+    ok, c, r, g, j = cp.evaluate(np.zeros(5))
+    assert ok and c == 20.5 and g.tolist() == [15.0, 30.0, 33.0, 66.0, 99.0]
+    jac = np.array([1, 2, 1, 2, 3] * 2 + [2, 4, 0, 0, 0] * 3 + [0, 0, 3, 6, 9] * 4, float)
+    assert np.array_equal(cp.dense_jacobian(), jac.reshape(9, 5))
+
+
+def test_failing_functor_returns_false():
+    b = P.ProblemBuilder()
+    v = _xyz(b)
+    b.add_residual_block(P.AFFINE_FAIL, [v["x"], v["y"], v["z"]])
+    cp = B.CudaProblem(b.build(), reduce=False)
+    ok, *_ = cp.evaluate(np.zeros(9), residuals=False, gradient=False, jacobian=False)
+    assert not ok
+
+
+def test_unwritten_residual_is_rejected():
+    """autodiff_cost_function_cuda_test.cu.cc:230-293 + residual_block.cc:110-129: a
+    functor that leaves an output unwritten yields kImpossibleValue, which the CPU
+    evaluator (and this engine, unlike the fork) rejects."""
+    b = P.ProblemBuilder()
+    x = b.add_parameter_block([1.0])
+    b.add_residual_block(P.ONLY_FILLS_ONE, [x])
+    spec = b.build()
+    assert not O.OracleProblem(spec, reduce=False).evaluate()[0]
+    assert not B.CudaProblem(spec, reduce=False).evaluate()[0]
+
+
+def test_non_finite_residual_is_rejected():
+    spec = P.bal_problem(4, 30, 100, seed=7)
+    op = O.OracleProblem(spec)
+    cp = B.CudaProblem(spec)
+    x = op.initial_state()
+    x[5] = np.inf
+    assert not op.evaluate(x)[0]
+    assert not cp.evaluate(x)[0]
+
+
+def test_autodiff_known_answers():
+    """autodiff_cost_function_cuda_test.cu.cc:102-116,205-222 through the engine."""
+    b = P.ProblemBuilder()
+    x = b.add_parameter_block([1.0, 2.0])
+    y = b.add_parameter_block([3.0, 4.0])
+    b.add_residual_block(P.BINARY_SCALAR, [x, y], [1.0])
+    cp = B.CudaProblem(b.build(), reduce=False)
+    ok, c, r, g, j = cp.evaluate()
+    assert ok and r.tolist() == [10.0] and cp.dense_jacobian().tolist() == [[3.0, 4.0, 1.0, 2.0]]
+    b = P.ProblemBuilder()
+    xs = [b.add_parameter_block([float(i)]) for i in range(10)]
+    b.add_residual_block(P.TEN_PARAMETER, xs)
+    cp = B.CudaProblem(b.build(), reduce=False)
+    ok, c, r, g, j = cp.evaluate()
+    assert ok and r.tolist() == [45.0] and cp.dense_jacobian().tolist() == [[1.0] * 10]
+
+
+def test_state_changes_are_respected():
+    """evaluator_test.cc:598-650."""
+    b = P.ProblemBuilder()
+    x = b.add_parameter_block([1.0, 1.0])
+    b.add_residual_block(P.PARAMETER_SENSITIVE, [x])
+    cp = B.CudaProblem(b.build(), reduce=False)
+    ok, c, r, g, j = cp.evaluate(np.array([1.0, 1.0]))
+    assert c == 1.0 and r.tolist() == [1.0, 1.0] and cp.dense_jacobian().tolist() == [[2, 0], [0, 2]]
+    ok, c, r, g, j = cp.evaluate(np.array([2.0, 3.0]))
+    assert c == 48.5 and r.tolist() == [4.0, 9.0] and cp.dense_jacobian().tolist() == [[4, 0], [0, 6]]
+
+
+def test_single_gpu_shards_reassemble():
+    """Multi-GPU sharding emulated on one device: world_size ranks evaluated one after
+    the other, each writing its own slices; the union must equal the unsharded
+    result and cost/gradient must add up (no NCCL involved)."""
+    spec = P.bal_problem(10, 400, 1500, seed=8)
+    for fmt in (0, 1):
+        op = O.OracleProblem(spec, jacobian_format=fmt)
+        x = op.initial_state()
+        _, c_o, r_o, g_o, j_o = op.evaluate(x)
+        W = 3
+        r = np.full(op.num_residuals, np.nan)
+        jv = np.full(op.values_size, np.nan)
+        g = np.zeros(op.num_effective_parameters)
+        c = 0.0
+        covered = 0
+        for k in range(W):
+            cp = B.CudaProblem(spec, jacobian_format=fmt, rank=k, world_size=W)
+            ok, ck, rk, gk, jk = cp.evaluate(x, out_residuals=r)
+            assert ok
+            info = cp.shard_info()
+            for (gb, ln, lb) in info["segments"]:
+                jv[gb:gb + ln] = jk[gb:gb + ln]
+                covered += ln
+            c += ck
+            g += gk
+            cp.close()
+        assert covered == op.num_jacobian_values
+        _close(c, c_o, RTOL_SUMS, "cost")
+        _close(r, r_o, RTOL_VALUES, "residuals")
+        _close(jv[:op.num_jacobian_values], j_o[:op.num_jacobian_values], RTOL_VALUES, "jacobian")
+        _close(g, g_o, RTOL_SUMS, "gradient")
+
+
+def test_device_resident_evaluation_matches():
+    spec = P.bal_problem(8, 200, 700, seed=9)
+    cp = B.CudaProblem(spec)
+    ok, c, r, g, j = cp.evaluate()
+    ok2, c2 = cp.evaluate_device()
+    assert ok and ok2 and c2 == c
+    t = cp.timing()
+    assert t["launches"] >= 2 and t["kernel_ms"] > 0

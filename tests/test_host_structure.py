@@ -1,0 +1,129 @@
+"""CPU tests of the product's host layer: the C-ABI library loads and exports every
+symbol include/ceres_b200.h declares; the reduced program, the BlockSparseMatrix /
+CompressedRowSparseMatrix structure and the per-residual layouts are bit-exact
+against the oracle (north_star: "Jacobian row/column structure and value offsets
+bit-exact")."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+from ceres_b200 import binding as B
+from ceres_b200 import problems as P
+
+STRUCT = ["residual_layout", "jacobian_per_residual_layout", "jacobian_per_residual_offsets",
+          "program_rbs", "program_pbs", "constant_pbs"]
+BSM = ["col_block_size", "col_block_pos", "row_block_size", "row_block_pos", "row_cells_start",
+       "cell_block_id", "cell_position", "jacobian_layout_storage"]
+CRS = ["crs_rows", "crs_cols"]
+
+
+def test_abi_library_exports_every_declared_symbol():
+    header = open(os.path.join(B.ROOT, "include", "ceres_b200.h")).read()
+    declared = set(re.findall(r"\b(cb200_[a-z0-9_]+)\s*\(", header))
+    declared -= {"cb200_launch_fn"}
+    assert declared == set(B.ABI_SYMBOLS), declared ^ set(B.ABI_SYMBOLS)
+    lib = B.abi()
+    for name in B.ABI_SYMBOLS:
+        assert getattr(lib, name) is not None
+    assert b"sm_100a" in lib.cb200_version()
+
+
+def test_engine_create_fails_loudly_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    lib = B.abi()
+    eng = ctypes.c_void_p()
+    rc = lib.cb200_engine_create(0, ctypes.byref(eng))
+    assert rc != 0 and not eng.value
+    spec = P.bal_problem(3, 10, 30, seed=1)
+    with pytest.raises(RuntimeError, match="no usable CUDA device|no CPU fallback"):
+        B.CudaProblem(spec, with_device=True)
+    cp = B.CudaProblem(spec, with_device=False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cp.evaluate()
+
+
+def _compare_structure(spec, fmt, **kw):
+    op = O.OracleProblem(spec, jacobian_format=fmt, **kw)
+    cp = B.CudaProblem(spec, jacobian_format=fmt, with_device=False, **kw)
+    for a in ("num_parameters", "num_effective_parameters", "num_residuals",
+              "num_residual_blocks", "num_parameter_blocks", "num_jacobian_values",
+              "values_size", "num_constant_parameters"):
+        assert getattr(op, a) == getattr(cp, a), a
+    for name in STRUCT + (BSM if fmt == 0 else CRS):
+        assert np.array_equal(op.ints(name), cp.ints(name)), name
+    assert np.array_equal(op.pb_table(), cp.pb_table())
+    assert np.array_equal(op.initial_state(), cp.initial_state())
+    return op, cp
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+@pytest.mark.parametrize("bulk", [False, True])
+def test_bal_structure(fmt, bulk):
+    spec = P.bal_problem(7, 60, 200, seed=4)
+    op = O.OracleProblem(spec, jacobian_format=fmt)
+    cp = B.CudaProblem(spec, jacobian_format=fmt, with_device=False, bulk=bulk)
+    for name in STRUCT + (BSM if fmt == 0 else CRS):
+        assert np.array_equal(op.ints(name), cp.ints(name)), name
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+@pytest.mark.parametrize("nelim", [0, 13, 60])
+def test_bal_structure_eliminate_blocks_and_reorder(fmt, nelim):
+    spec = P.bal_problem(7, 60, 200, seed=5, constant_cameras=2, subset_manifold=True)
+    # shuffle residual blocks so the Schur reordering has work to do
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(spec.num_rb)
+    spec = P.ProblemSpec(pb_size=spec.pb_size, pb_values=spec.pb_values, rb_type=spec.rb_type[perm],
+                         rb_pb=spec.rb_pb.reshape(-1, 2)[perm].ravel(),
+                         fdata=spec.fdata.reshape(-1, 2)[perm].ravel(),
+                         pb_constant=spec.pb_constant, pb_manifold_kind=spec.pb_manifold_kind,
+                         pb_manifold_param=spec.pb_manifold_param,
+                         rb_loss_kind=spec.rb_loss_kind[perm], rb_loss_a=spec.rb_loss_a[perm],
+                         rb_loss_b=spec.rb_loss_b[perm], num_eliminate_blocks=nelim)
+    _compare_structure(spec, fmt, schur_reorder=True)
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_fork_fixture_structure(fmt):
+    op, cp = _compare_structure(P.evaluator_cuda_test_problem(), fmt)
+    assert cp.num_residual_blocks == 5 and cp.num_residuals == 11
+    assert abs(cp.fixed_cost - op.fixed_cost) <= 1e-15
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_pose_graph_structure(fmt):
+    _compare_structure(P.pose_graph_problem(40, 100, seed=3), fmt)
+
+
+def test_all_constant_residual_block_goes_to_fixed_cost():
+    b = P.ProblemBuilder()
+    c = b.add_parameter_block(np.r_[0.01, 0.02, -0.01, 0.1, 0.2, -8.0, 500.0, 1e-7, 1e-13])
+    p = b.add_parameter_block([0.3, -0.2, 0.5], constant=True)
+    q = b.add_parameter_block([0.1, 0.4, -0.3], constant=True)
+    b.add_residual_block(P.SNAVELY, [c, p], [3.0, -2.0], (P.LOSS_HUBER, 1.0))
+    b.add_residual_block(P.POINT_DISPLACEMENT, [q], [0.5, 0.5, 0.5])
+    spec = b.build()
+    op, cp = _compare_structure(spec, 0)
+    assert cp.num_residual_blocks == 1
+    assert op.fixed_cost > 0 and abs(cp.fixed_cost - op.fixed_cost) <= 1e-15 * op.fixed_cost
+
+
+def test_plus_matches_oracle():
+    spec = P.pose_graph_problem(20, 40, seed=8)
+    op = O.OracleProblem(spec)
+    cp = B.CudaProblem(spec, with_device=False)
+    x = op.initial_state()
+    d = np.random.default_rng(1).normal(0, 0.1, op.num_effective_parameters)
+    assert np.allclose(op.plus(x, d), cp.plus(x, d), rtol=0, atol=1e-15)
+    spec = P.bal_problem(5, 30, 90, seed=2, subset_manifold=True)
+    op = O.OracleProblem(spec)
+    cp = B.CudaProblem(spec, with_device=False)
+    x = op.initial_state()
+    d = np.random.default_rng(2).normal(0, 0.1, op.num_effective_parameters)
+    assert np.array_equal(op.plus(x, d), cp.plus(x, d))
