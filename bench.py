@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Headline benchmark: residual blocks evaluated per second (residuals + Jacobian +
+loss + gradient + cost) on a synthetic BAL problem of problem-13682-4456117 shape,
+residual blocks sharded over --gpus B200s (BASELINE.json).
+
+  python bench.py --gpus 1 --steps 20 --warmup 3
+  python -m torch.distributed.run --nproc-per-node 8 ... bench.py --gpus 8 ...
+  python bench.py --impl reference          # the reference algorithm on the host cores
+
+A step is one Evaluator::Evaluate(state, &cost, residuals, gradient, jacobian) over
+the whole problem.  `value` is measured with the state resident in HBM
+(cb200_engine_evaluate_device); `e2e` goes through Evaluator::Evaluate with host
+buffers, host<->device copies inside the timed region.  One JSON line on stdout.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT]
+
+import numpy as np  # noqa: E402
+
+# ALGORITHMIC bytes per residual block for SnavelyReprojectionError<2,9,3>, BlockSparse,
+# all outputs (DESIGN.md "Roofline"): functor 16 + parameter
+# block ids 8 + cell positions 8 + Jacobian 192 + residuals 16 + parameters and gradient
+# amortised 2 x 3.7.
+ALG_BYTES_PER_RB = 248.0
+# Dense-Jet FLOP count of the reference arithmetic for the same functor.
+ALG_FLOPS_PER_RB = 2966.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="L", help="BAL shape S | M | L (SURVEY.md 8d)")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug)")
+    ap.add_argument("--cpu-sample-blocks", type=int, default=6_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while running."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_spec(args):
+    import ceres_b200  # noqa: F401
+    from ceres_b200 import problems as P
+    return P.bal_shape(args.workload, scale=args.scale)
+
+
+def workload_config(args, spec, parallelism):
+    m = spec.meta
+    return {"workload": f"synthetic BAL {m['num_cameras']}x{m['num_points']} "
+                        f"({m['num_observations']} residual blocks), "
+                        "SnavelyReprojectionError<2,9,3> + HuberLossCUDA(1.0), "
+                        "BlockSparseMatrix Jacobian (E=points, F=cameras), "
+                        "outputs: cost+residuals+gradient+Jacobian",
+            "shape": args.workload, "scale": args.scale, "seed": m["seed"],
+            "parallelism": parallelism,
+            "l2": "working set per step (Jacobian values alone %.2f GB) exceeds the 126 MB L2"
+                  % (m["num_observations"] * 192 / 1e9)}
+
+
+# ---------------------------------------------------------------- CPU reference arm
+def cpu_sample(spec, max_blocks):
+    """A bounded sample of the workload: the first max_blocks residual blocks (whole
+    points) with every parameter block they touch kept in place."""
+    from ceres_b200 import problems as P
+    n = min(spec.num_rb, max_blocks)
+    return P.ProblemSpec(
+        pb_size=spec.pb_size, pb_values=spec.pb_values, rb_type=spec.rb_type[:n],
+        rb_pb=spec.rb_pb[:2 * n], fdata=spec.fdata[:2 * n], pb_constant=spec.pb_constant,
+        pb_manifold_kind=spec.pb_manifold_kind, pb_manifold_param=spec.pb_manifold_param,
+        rb_loss_kind=spec.rb_loss_kind[:n], rb_loss_a=spec.rb_loss_a[:n],
+        rb_loss_b=spec.rb_loss_b[:n], num_eliminate_blocks=spec.num_eliminate_blocks), n
+
+
+def time_cpu(spec, max_blocks, steps, warmup):
+    """Times the reference algorithm's CPU port (oracle/, ProgramEvaluator semantics,
+    contiguous static partition over all host threads)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    sample, n = cpu_sample(spec, max_blocks)
+    cores = os.cpu_count() or 1
+    op = O.OracleProblem(sample, fast=True)  # -O3 -march=native build, timing only
+    x = op.initial_state()
+    for _ in range(max(1, warmup)):
+        op.evaluate(x, num_threads=cores)
+    times = []
+    for _ in range(max(1, steps)):
+        t0 = time.perf_counter()
+        ok, *_ = op.evaluate(x, num_threads=cores)
+        times.append(time.perf_counter() - t0)
+        assert ok
+    per_step = float(np.mean(times))
+    return {"value": op.num_residual_blocks / per_step, "unit": "residual blocks/s",
+            "cores": cores, "kind": "port",
+            "build": "oracle/oracle_eval.cc, g++ -O3 -march=native, std::thread static partition",
+            "sample": f"first {op.num_residual_blocks} of {spec.num_rb} residual blocks "
+                      f"(whole problem's parameter blocks), full Evaluate, mean of "
+                      f"{len(times)} calls after {max(1, warmup)} warm-up",
+            "ms_per_step": per_step * 1e3, "best_ms": float(min(times)) * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec = make_spec(args)
+    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
+    cpu = time_cpu(spec, args.cpu_sample_blocks, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "residual blocks/s (residual+Jacobian+loss+gradient)",
+        "value": cpu["value"], "unit": "residual blocks/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": cpu["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args, spec, "cpu-threads"),
+        "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "build")},
+        "e2e": {"value": cpu["value"], "unit": "residual blocks/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ceres_b200  # noqa: F401
+    from ceres_b200 import binding as B
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(B.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        nccl_id = bytes(buf.cpu().numpy().tobytes())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    spec = make_spec(args)
+    t_setup = time.perf_counter()
+    cp = B.CudaProblem(spec, device=local_rank, rank=rank, world_size=world, nccl_id=nccl_id)
+    setup_s = time.perf_counter() - t_setup
+    nrb = cp.num_residual_blocks
+
+    # The caller's buffers: pinned host memory, as INTEGRATION.md asks of the binding.
+    state = B.PinnedArray(cp.num_parameters)
+    residuals = B.PinnedArray(cp.num_residuals)
+    gradient = B.PinnedArray(cp.num_effective_parameters)
+    state.array[:] = cp.initial_state()
+
+    def step_e2e():
+        ok, cost, *_ = cp.evaluate(state.array, out_residuals=residuals.array,
+                                   out_gradient=gradient.array)
+        assert ok
+        return cost
+
+    def step_device():
+        ok, cost = cp.evaluate_device()
+        assert ok
+        return cost
+
+    for _ in range(max(3, args.warmup)):
+        step_e2e()
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    launches_per_step = cp.timing()["launches"]
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- timed region 1: state resident in HBM, outputs stay in HBM.
+    kernel_ms, device_ms = [], []
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_device()
+        t = cp.timing()
+        kernel_ms.append(t["kernel_ms"])
+        device_ms.append(t["device_ms"])
+    barrier()
+    wall_device = max_over_ranks(time.perf_counter() - t0)
+    # ---- timed region 2: end to end through Evaluator::Evaluate with host buffers.
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cost = step_e2e()
+    barrier()
+    wall_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_engine_ms = cp.timing()["e2e_ms"]
+    clocks = sampler.stop()
+
+    # Device time of a step = CUDA events on the engine's stream around kernels +
+    # cost reduction + all-reduce, max over ranks; the wall clock around the K calls
+    # (launch + one host synchronisation each) is reported beside it.
+    dev_ms = max_over_ranks(float(np.mean(device_ms)))
+    ker_ms = max_over_ranks(float(np.mean(kernel_ms)))
+    info = cp.shard_info()
+    local_rb = info["rb_end"] - info["rb_begin"]
+    local_j = sum(s[1] for s in info["segments"])
+    h2d = 8 * cp.num_parameters
+    d2h = 8 * ((info["residual_end"] - info["residual_begin"]) + cp.num_effective_parameters +
+               local_j + 1)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    achieved = ALG_BYTES_PER_RB * local_rb / (ker_ms * 1e-3) / 1e9
+    line = {
+        "metric": "residual blocks/s (residual+Jacobian+loss+gradient)",
+        "value": nrb / (wall_device / args.steps), "unit": "residual blocks/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": wall_device / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, spec, f"residual-block-range x{world}, parameters "
+                                  "replicated, NCCL all-reduce of [gradient|cost]"),
+        "device_ms_per_step": dev_ms, "kernel_ms_per_step": ker_ms,
+        "e2e": {"value": nrb / (wall_e2e / args.steps), "unit": "residual blocks/s",
+                "ms_per_step": wall_e2e / args.steps * 1e3, "engine_ms_last_step": e2e_engine_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "per rank; host buffers page-locked with cb200_host_pin"},
+        "gpu_launches": launches_per_step * args.steps * 2,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None,
+                     "kernel": "EvaluateKernel<true, SnavelyReprojectionError, HuberLossCUDA, 2, 9, 3>",
+                     "algorithmic_bytes_per_block": ALG_BYTES_PER_RB,
+                     "blocks_per_launch": local_rb, "launch_ms": ker_ms, "peak_source": peak_src,
+                     "fp64": {"achieved_tflops": ALG_FLOPS_PER_RB * local_rb / (ker_ms * 1e-3) / 1e12,
+                              "algorithmic_flops_per_block": ALG_FLOPS_PER_RB,
+                              "nominal_peak_tflops": 37.2}},
+        "setup_s": setup_s, "cost": cost,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = time_cpu(spec, args.cpu_sample_blocks, 3, 1)
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "build")}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -23,7 +23,8 @@ ABI_SYMBOLS = [
     "cb200_engine_set_layout", "cb200_engine_set_shard", "cb200_engine_finalize",
     "cb200_nccl_unique_id", "cb200_engine_comm_init", "cb200_engine_evaluate",
     "cb200_engine_evaluate_device", "cb200_engine_device_ptr", "cb200_engine_shard_info",
-    "cb200_engine_last_timing", "cb200_host_alloc", "cb200_host_free", "cb200_version",
+    "cb200_engine_last_timing", "cb200_host_alloc", "cb200_host_pin", "cb200_host_free",
+    "cb200_version",
 ]
 
 
@@ -40,7 +41,38 @@ def abi():
         _ABI = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
         _ABI.cb200_version.restype = C.c_char_p
         _ABI.cb200_nccl_unique_id.argtypes = [C.c_void_p]
+        _ABI.cb200_host_alloc.restype = C.c_void_p
+        _ABI.cb200_host_alloc.argtypes = [C.c_uint64]
+        _ABI.cb200_host_pin.argtypes = [C.c_void_p, C.c_uint64]
+        _ABI.cb200_host_free.argtypes = [C.c_void_p]
     return _ABI
+
+
+class PinnedArray:
+    """float64 vector in cb200_host_alloc memory, page-locked (what a caller of the C
+    ABI allocates for state / residuals / gradient to get full-rate copies)."""
+
+    def __init__(self, n):
+        L = abi()
+        self.n = int(n)
+        self.ptr = L.cb200_host_alloc(8 * max(self.n, 1))
+        if not self.ptr:
+            raise MemoryError("cb200_host_alloc failed")
+        L.cb200_host_pin(self.ptr, 8 * max(self.n, 1))
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_double)),
+                                           shape=(max(self.n, 1),))[:self.n]
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            abi().cb200_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def driver():

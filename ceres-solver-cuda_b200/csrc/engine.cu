@@ -19,13 +19,16 @@
 //    ResidualBlock::index() (stale after the Schur reordering, SURVEY.md hazard 1).
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "ceres_b200.h"
@@ -34,16 +37,16 @@ namespace {
 
 // ---- NCCL through dlopen: torch (when it hosts the process) already has
 // libnccl.so.2 loaded and dlopen returns that same copy.
+struct Uid {
+  char internal[128];
+};
 struct NcclApi {
   void* handle = nullptr;
   int (*GetUniqueId)(void*) = nullptr;
-  int (*CommInitRank)(void**, int, /* ncclUniqueId by value */ struct Uid, int) = nullptr;
+  int (*CommInitRank)(void**, int, /* ncclUniqueId by value */ Uid, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
-};
-struct Uid {
-  char internal[128];
 };
 constexpr int kNcclFloat64 = 8;  // ncclDouble
 constexpr int kNcclSum = 0;      // ncclSum
@@ -682,29 +685,87 @@ int cb200_engine_last_timing(cb200_engine* e, double* out4) {
   return CB200_OK;
 }
 
-void* cb200_host_alloc(uint64_t bytes) {
-  // Pinned so device->host copies of the Jacobian run at full PCIe rate.  The
-  // pointer is tagged by a 64-byte header so cb200_host_free knows how to free it.
-  if (bytes == 0) bytes = 8;
-  void* p = nullptr;
+// ---- host memory: lazy anonymous mappings + page-locking of sub-ranges.
+namespace {
+constexpr uint64_t kPage = 4096;
+constexpr uint64_t kAllocMagic = 0x6362323030686d31ULL;
+struct AllocHeader {
+  uint64_t magic, total_bytes;
+};
+std::mutex g_pin_mutex;
+std::vector<std::pair<uintptr_t, uintptr_t>> g_pinned;  // disjoint [begin, end), sorted
+
+int PinRange(uintptr_t lo, uintptr_t hi) {
+  std::lock_guard<std::mutex> lock(g_pin_mutex);
   int count = 0;
-  bool pinned = false;
-  if (cudaGetDeviceCount(&count) == cudaSuccess && count > 0 &&
-      cudaHostAlloc(&p, bytes + 64, cudaHostAllocPortable) == cudaSuccess) {
-    pinned = true;
-  } else {
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
     cudaGetLastError();
-    if (posix_memalign(&p, 64, bytes + 64) != 0) return nullptr;
+    return CB200_OK;  // nothing to DMA to on this machine
   }
-  *static_cast<uint64_t*>(p) = pinned ? 0x70696e6e6564ULL : 0x6d616c6c6f63ULL;
-  return static_cast<char*>(p) + 64;
+  // Register only the pages not covered by an earlier pin.
+  std::vector<std::pair<uintptr_t, uintptr_t>> todo;
+  uintptr_t cursor = lo;
+  for (const auto& r : g_pinned) {
+    if (r.second <= cursor) continue;
+    if (r.first >= hi) break;
+    if (r.first > cursor) todo.emplace_back(cursor, r.first);
+    cursor = std::max(cursor, r.second);
+    if (cursor >= hi) break;
+  }
+  if (cursor < hi) todo.emplace_back(cursor, hi);
+  for (const auto& t : todo) {
+    cudaError_t err = cudaHostRegister(reinterpret_cast<void*>(t.first), t.second - t.first,
+                                       cudaHostRegisterPortable);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      return CB200_ERROR_CUDA;
+    }
+    g_pinned.push_back(t);
+  }
+  std::sort(g_pinned.begin(), g_pinned.end());
+  return CB200_OK;
+}
+
+void UnpinWithin(uintptr_t lo, uintptr_t hi) {
+  std::lock_guard<std::mutex> lock(g_pin_mutex);
+  std::vector<std::pair<uintptr_t, uintptr_t>> keep;
+  for (const auto& r : g_pinned) {
+    if (r.first >= lo && r.second <= hi) {
+      cudaHostUnregister(reinterpret_cast<void*>(r.first));
+      cudaGetLastError();
+    } else {
+      keep.push_back(r);
+    }
+  }
+  g_pinned.swap(keep);
+}
+}  // namespace
+
+void* cb200_host_alloc(uint64_t bytes) {
+  const uint64_t total = ((bytes + kPage - 1) / kPage + 1) * kPage;
+  void* p = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (p == MAP_FAILED) return nullptr;
+  auto* h = static_cast<AllocHeader*>(p);
+  h->magic = kAllocMagic;
+  h->total_bytes = total;
+  return static_cast<char*>(p) + kPage;
+}
+
+int cb200_host_pin(void* ptr, uint64_t bytes) {
+  if (!ptr || bytes == 0) return CB200_OK;
+  const uintptr_t lo = reinterpret_cast<uintptr_t>(ptr) / kPage * kPage;
+  const uintptr_t hi = (reinterpret_cast<uintptr_t>(ptr) + bytes + kPage - 1) / kPage * kPage;
+  return PinRange(lo, hi);
 }
 
 void cb200_host_free(void* q) {
   if (!q) return;
-  char* p = static_cast<char*>(q) - 64;
-  if (*reinterpret_cast<uint64_t*>(p) == 0x70696e6e6564ULL) cudaFreeHost(p);
-  else free(p);
+  char* p = static_cast<char*>(q) - kPage;
+  auto* h = reinterpret_cast<AllocHeader*>(p);
+  if (h->magic != kAllocMagic) return;
+  const uint64_t total = h->total_bytes;
+  UnpinWithin(reinterpret_cast<uintptr_t>(p), reinterpret_cast<uintptr_t>(p) + total);
+  munmap(p, total);
 }
 
 }  // extern "C"

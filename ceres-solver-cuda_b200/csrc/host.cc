@@ -705,7 +705,13 @@ class ProgramEvaluatorCUDA final : public Evaluator {
   }
 
   std::unique_ptr<SparseMatrix> CreateJacobian() const override {
-    return CreateJacobianFromLayout(*program_, layout_);
+    std::unique_ptr<SparseMatrix> m = CreateJacobianFromLayout(*program_, layout_);
+    // Page-lock the slices this rank's device writes into.
+    int64_t segments[3 * 32];
+    const int n = cb200_engine_shard_info(engine_, nullptr, nullptr, nullptr, nullptr, segments, 32);
+    for (int i = 0; i < n && i < 32; ++i)
+      cb200_host_pin(m->mutable_values() + segments[3 * i], sizeof(double) * segments[3 * i + 1]);
+    return m;
   }
 
   bool Evaluate(const EvaluateOptions& evaluate_options, const double* state, double* cost,

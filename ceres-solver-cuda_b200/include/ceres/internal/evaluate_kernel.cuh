@@ -84,14 +84,13 @@ __device__ __forceinline__ bool IsValidValue(double x) {
   return ::fabs(x) <= 1.7976931348623157e308 && x != 1e302;
 }
 
-// Sums `v` over runs of consecutive lanes that hold the same key; afterwards the
-// first lane of every run holds the run's total.
+// Sums `v` over runs of consecutive lanes; `run_end` is one past the last lane of
+// the calling lane's run.  Afterwards the first lane of every run holds its total.
 template <int kCount>
-__device__ __forceinline__ void WarpSegmentedSum(int key, double (&v)[kCount], int lane) {
+__device__ __forceinline__ void WarpSegmentedSum(int run_end, double (&v)[kCount], int lane) {
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    const int other_key = __shfl_down_sync(0xffffffffu, key, d);
-    const bool take = (lane + d < 32) && (other_key == key);
+    const bool take = lane + d < run_end;
 #pragma unroll
     for (int c = 0; c < kCount; ++c) {
       const double o = __shfl_down_sync(0xffffffffu, v[c], d);
@@ -320,7 +319,12 @@ __global__ void __launch_bounds__(kEvaluateThreads)
         const int key = (valid && active) ? pb_id[j] : -1 - lane;
         const int prev_key = __shfl_up_sync(0xffffffffu, key, 1);
         const bool head = (lane == 0) || (prev_key != key);
-        if (__any_sync(0xffffffffu, !head)) WarpSegmentedSum<kSize>(key, g, lane);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        if (heads != 0xffffffffu) {
+          const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+          const int run_end = above ? __ffs(above) - 1 : 32;
+          WarpSegmentedSum<kSize>(run_end, g, lane);
+        }
         if (head && valid && ok && active) {
           double* __restrict__ dst = a.gradient + pb[j].y;
 #pragma unroll

@@ -202,10 +202,17 @@ int cb200_engine_shard_info(cb200_engine* engine, int32_t* rb_begin, int32_t* rb
  * out[2] whole call including host<->device copies.  out[3] = kernel launches. */
 int cb200_engine_last_timing(cb200_engine* engine, double* out4);
 
-/* Pinned host memory for the caller's output arrays (CreateJacobian's values):
- * falls back to malloc when no CUDA device is present. */
+/* Host memory for the caller's arrays (the values of CreateJacobian(), the state,
+ * residual and gradient vectors).  cb200_host_alloc returns zero-filled, page-aligned,
+ * lazily committed memory (untouched pages cost nothing, so a rank of a sharded run
+ * can hold a full-size values array and only ever touch its slices); cb200_host_pin
+ * page-locks a sub-range for full-rate DMA (cudaHostRegister; a no-op without a
+ * device).  Ranges may overlap earlier pins.  Replaces the pageable
+ * std::unique_ptr<double[]> of internal/ceres/block_sparse_matrix.h:163-167 that makes
+ * the reference's device->host copy its bottleneck (README.md:198-200). */
 void* cb200_host_alloc(uint64_t bytes);
-void cb200_host_free(void* p);
+int cb200_host_pin(void* ptr, uint64_t bytes);
+void cb200_host_free(void* ptr);
 
 const char* cb200_version(void);
 

@@ -14,6 +14,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_FAST = None
 
 
 def build(force=False):
@@ -25,11 +26,31 @@ def build(force=False):
     return so
 
 
-def lib():
-    global _LIB
+def build_fast():
+    """The same source at -O3 -march=native (vectorised, FMA contraction allowed) for
+    TIMING the CPU baseline only; compiled on the machine it runs on.  Parity checks
+    always use the strict build (liboracle.so, -ffp-contract=off)."""
+    import tempfile
+    so = os.path.join(tempfile.gettempdir(), f"liboracle_fast_{os.getuid()}_{os.getpid()}.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O3", "-march=native", "-fPIC", "-pthread",
+                           "-shared", "-Wno-array-bounds", "-o", so,
+                           os.path.join(_HERE, "oracle_eval.cc")])
+    return so
+
+
+def lib(fast=False):
+    global _LIB, _FAST
+    if fast:
+        if _FAST is None:
+            _FAST = _declare(C.CDLL(build_fast()))
+        return _FAST
     if _LIB is None:
-        _LIB = C.CDLL(build())
-        L = _LIB
+        _LIB = _declare(C.CDLL(build()))
+    return _LIB
+
+
+def _declare(L):
+    if True:
         L.oracle_problem_create.restype = C.c_void_p
         L.oracle_problem_create.argtypes = [
             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -54,7 +75,7 @@ def lib():
         L.oracle_manifold_plus.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_angle_axis_rotate_point.argtypes = [C.c_void_p] * 3
         L.oracle_cost_type_info.argtypes = [C.c_int, C.c_void_p]
-    return _LIB
+    return L
 
 
 def _p(a):
@@ -74,8 +95,8 @@ class OracleProblem:
     """Program + evaluator built from a ProblemSpec (see ceres-solver-cuda_b200/problems.py)."""
 
     def __init__(self, spec, jacobian_format=0, reduce=True, schur_reorder=False,
-                 num_eliminate_blocks=None):
-        L = lib()
+                 num_eliminate_blocks=None, fast=False):
+        L = self.L = lib(fast)
         self.spec = spec
         self.h = L.oracle_problem_create(
             spec.num_pb, _p(spec.pb_size), _p(spec.pb_values), _p(spec.pb_constant),
@@ -97,13 +118,13 @@ class OracleProblem:
     def __del__(self):
         try:
             if getattr(self, "h", None):
-                lib().oracle_problem_destroy(self.h)
+                self.L.oracle_problem_destroy(self.h)
                 self.h = None
         except Exception:
             pass
 
     def ints(self, name):
-        L = lib()
+        L = self.L
         n = L.oracle_problem_get_ints(self.h, _INT_ARRAYS[name], None)
         out = np.zeros(n, dtype=np.int32)
         L.oracle_problem_get_ints(self.h, _INT_ARRAYS[name], _p(out))
@@ -111,12 +132,12 @@ class OracleProblem:
 
     def pb_table(self):
         out = np.zeros((self.num_parameter_blocks, 4), dtype=np.int32)
-        lib().oracle_problem_pb_table(self.h, _p(out))
+        self.L.oracle_problem_pb_table(self.h, _p(out))
         return out
 
     def initial_state(self):
         s = np.zeros(self.num_parameters)
-        lib().oracle_problem_initial_state(self.h, _p(s))
+        self.L.oracle_problem_initial_state(self.h, _p(s))
         return s
 
     def evaluate(self, state=None, residuals=True, gradient=True, jacobian=True,
@@ -129,13 +150,13 @@ class OracleProblem:
         r = np.full(self.num_residuals, np.nan) if residuals else None
         g = np.full(self.num_effective_parameters, np.nan) if gradient else None
         j = np.full(self.values_size, np.nan) if jacobian else None
-        ok = lib().oracle_problem_evaluate(self.h, _p(state), int(apply_loss_function),
+        ok = self.L.oracle_problem_evaluate(self.h, _p(state), int(apply_loss_function),
                                            int(num_threads), _p(cost), _p(r), _p(g), _p(j))
         return bool(ok), float(cost[0]), r, g, j
 
     def plus(self, state, delta):
         out = np.zeros(self.num_parameters)
-        lib().oracle_problem_plus(self.h, _p(np.ascontiguousarray(state)),
+        self.L.oracle_problem_plus(self.h, _p(np.ascontiguousarray(state)),
                                   _p(np.ascontiguousarray(delta)), _p(out))
         return out
 

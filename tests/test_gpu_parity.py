@@ -18,12 +18,18 @@ RTOL_SUMS = 1e-10
 
 
 def _close(a, b, rtol, what):
-    """|a - b| <= rtol * max(|b|, scale): relative to the magnitude of the vector so
-    that exact zeros next to O(1e3) pixels are not held to an absolute 0."""
+    """max|a - b| <= rtol * max|b|: relative error in the infinity norm of the whole
+    vector, the norm-wise notion the fork's own GPU-vs-CPU test uses
+    (evaluator_cuda_test.cu.cc:425-440, isApprox).  An element-wise bound is not
+    meaningful here: a residual is predicted - observed with both ~1e2..1e3 px, so two
+    correct implementations differ by ~1e-16 * 1e3 in absolute terms whatever the size
+    of the residual itself."""
     a, b = np.asarray(a, float), np.asarray(b, float)
-    scale = max(float(np.max(np.abs(b))) if b.size else 0.0, 1e-300)
-    err = np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-3 * scale)) if b.size else 0.0
-    assert err <= rtol, f"{what}: max relative error {err:.3e} > {rtol:.0e}"
+    if b.size == 0:
+        return
+    scale = max(float(np.max(np.abs(b))), 1e-300)
+    err = float(np.max(np.abs(a - b))) / scale
+    assert err <= rtol, f"{what}: max error / max magnitude = {err:.3e} > {rtol:.0e}"
 
 
 def _check(spec, fmt=0, state=None, **kw):
@@ -178,7 +184,7 @@ def test_constant_parameter_table():
     b.set_constant(v["z"])
     cp = B.CudaProblem(b.build(), reduce=True)
     ok, c, r, g, j = cp.evaluate(np.zeros(5))
-    assert ok and c == 20.5 and g.tolist() == [15.0, 30.0, 33.0, 66.0, 99.0]
+    assert ok and c == 24.5 and g.tolist() == [15.0, 30.0, 33.0, 66.0, 99.0]
     jac = np.array([1, 2, 1, 2, 3] * 2 + [2, 4, 0, 0, 0] * 3 + [0, 0, 3, 6, 9] * 4, float)
     assert np.array_equal(cp.dense_jacobian(), jac.reshape(9, 5))
 
