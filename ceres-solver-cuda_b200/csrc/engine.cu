@@ -118,7 +118,8 @@ struct ResidualType {
   int32_t grid = 0;
   int32_t cost_partial_offset = 0;
   DeviceBuffer<char> d_functors, d_loss_table;
-  DeviceBuffer<int32_t> d_loss_index, d_pb, d_jpos, d_jstride, d_respos;
+  DeviceBuffer<int32_t> d_loss_index, d_pb, d_soff, d_doff, d_jpos, d_jstride, d_respos;
+  bool plain = true;
 };
 
 // Sums the per-thread-block cost partials in a fixed order (one block, tree in
@@ -225,7 +226,7 @@ void cb200_engine_destroy(cb200_engine* e) {
   }
   for (auto* t : e->types) {
     t->d_functors.Free(); t->d_loss_table.Free(); t->d_loss_index.Free(); t->d_pb.Free();
-    t->d_jpos.Free(); t->d_jstride.Free(); t->d_respos.Free();
+    t->d_jpos.Free(); t->d_jstride.Free(); t->d_respos.Free(); t->d_soff.Free(); t->d_doff.Free();
     delete t;
   }
   e->d_state.Free(); e->d_plus.Free(); e->d_residuals.Free(); e->d_jacobian.Free();
@@ -424,6 +425,8 @@ int cb200_engine_finalize(cb200_engine* e) {
     e->total_cost_partials += t->grid;
     if (n == 0) continue;
     std::vector<int32_t> pb(static_cast<size_t>(nb) * n), jpos(static_cast<size_t>(nb) * n, -1);
+    std::vector<int32_t> soff(static_cast<size_t>(nb) * n), doff(static_cast<size_t>(nb) * n);
+    t->plain = true;
     std::vector<int32_t> jstride(n, 0), respos(n), lidx;
     std::vector<char> fun(static_cast<size_t>(n) * t->desc.functor_size);
     if (t->num_losses > 1) lidx.resize(n);
@@ -440,6 +443,11 @@ int cb200_engine_finalize(cb200_engine* e) {
       for (int j = 0; j < nb; ++j) {
         const int32_t id = t->pb_ids[static_cast<size_t>(k) * nb + j];
         pb[static_cast<size_t>(j) * n + i] = id;
+        soff[static_cast<size_t>(j) * n + i] = table[4 * id + 0];
+        doff[static_cast<size_t>(j) * n + i] = table[4 * id + 1];
+        if (table[4 * id + 1] < 0 || table[4 * id + 3] >= 0 ||
+            e->blocks[id].tangent_size != e->blocks[id].size)
+          t->plain = false;
         if (id >= e->num_active) continue;
         const int64_t pos0 = e->jpro[static_cast<size_t>(L) + a * kres];
         jpos[static_cast<size_t>(j) * n + i] = to_local(pos0);
@@ -450,6 +458,8 @@ int cb200_engine_finalize(cb200_engine* e) {
       }
     }
     CB200_CUDA(e, t->d_pb.Upload(pb, e->stream));
+    CB200_CUDA(e, t->d_soff.Upload(soff, e->stream));
+    CB200_CUDA(e, t->d_doff.Upload(doff, e->stream));
     CB200_CUDA(e, t->d_jpos.Upload(jpos, e->stream));
     CB200_CUDA(e, t->d_jstride.Upload(jstride, e->stream));
     CB200_CUDA(e, t->d_respos.Upload(respos, e->stream));
@@ -524,6 +534,10 @@ static int EvaluateOnDevice(cb200_engine* e, uint32_t flags, bool want_r, bool w
     a.output_gradient = want_g;
     a.apply_loss_function = (flags & CB200_APPLY_LOSS_FUNCTION) ? 1u : 0u;
     a.crs = e->jacobian_format == CB200_JACOBIAN_COMPRESSED_ROW;
+    a.plain = t->plain ? 1u : 0u;
+    a.cost_partial_count = t->grid;
+    a.state_offset = t->d_soff.ptr;
+    a.delta_offset = t->d_doff.ptr;
     a.functors = t->d_functors.ptr;
     a.loss_table = t->d_loss_table.ptr;
     a.loss_index = t->num_losses > 1 ? t->d_loss_index.ptr : nullptr;

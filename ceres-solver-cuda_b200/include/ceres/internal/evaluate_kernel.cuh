@@ -161,230 +161,421 @@ struct BlockEpilogue {
   }
 };
 
-template <bool kWithJacobians, typename Functor, typename Loss, int kRes, int... Ns>
-__global__ void __launch_bounds__(kEvaluateThreads)
+// ---- asynchronous global -> shared copies (LDGSTS), used to prefetch the next
+// residual block's parameters and functor while the current one is computed.
+__device__ __forceinline__ void CpAsync8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(
+                   static_cast<unsigned>(__cvta_generic_to_shared(smem))),
+               "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void CpAsync4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                   static_cast<unsigned>(__cvta_generic_to_shared(smem))),
+               "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void CpAsync16(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(
+                   static_cast<unsigned>(__cvta_generic_to_shared(smem))),
+               "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void CpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void CpAsyncWait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
+
+// Non-finite detection on the integer pipe: max over values of the high word with
+// the sign shifted out is >= 0xffe00000 iff some value is Inf or NaN.
+__device__ __forceinline__ unsigned FiniteKey(double x) {
+  return static_cast<unsigned>(__double2hiint(x)) << 1;
+}
+constexpr unsigned kNonFiniteKey = 0xffe00000u;
+
+// Kernel variants.
+constexpr int kVariantCost = 0;     // cost / residuals only: plain doubles, no Jets
+constexpr int kVariantPlain = 1;    // Jets; no manifold and no constant block in this type
+constexpr int kVariantGeneric = 2;  // Jets; per-block manifold projection / constant blocks
+
+template <typename Functor, int kNumParameters>
+struct PrefetchLayout {
+  static constexpr int kParamBytes = kNumParameters * 8;
+  static constexpr bool kFunctorInSmem =
+      (sizeof(Functor) % 4 == 0) && (alignof(Functor) <= 16) && (sizeof(Functor) <= 128);
+  static constexpr int kFunctorBytes = kFunctorInSmem ? static_cast<int>(sizeof(Functor)) : 0;
+  // Functor slots are padded to 16 bytes so every slot is 16-byte aligned.
+  static constexpr int kFunctorSlot = (kFunctorBytes + 15) / 16 * 16;
+  static constexpr int kStageBytes = (kParamBytes + kFunctorSlot) * kEvaluateThreads;
+  static constexpr int kSmemBytes = 2 * kStageBytes;
+  static constexpr bool kFits = kSmemBytes <= 46 * 1024;
+};
+
+// One thread evaluates one residual block at a time and walks the type's blocks
+// with a grid stride (persistent CTAs: ResidentCtas() per SM).  Software pipeline per thread:
+//   iteration k:  [state offsets of block k+2 -> registers]
+//                 [cp.async parameters + functor of block k+1 -> shared, stage (k+1)&1]
+//                 [wait for stage k&1] compute block k from shared memory
+// so the two dependent global loads (offset, then the gathered parameters) of a
+// block are in flight during the ~1300 instructions of the previous block instead
+// of stalling the warp (v1 of this kernel: long-scoreboard stalls 7.5 of 15 cycles
+// per issue, FP64 pipe 22% busy; profiles/r1_v1_ncu_summary.txt).
+// CTAs per SM the kernel is compiled for: small functors fit 128 registers (4 CTAs of
+// 128 threads); wide Jets (pose graphs: 14 lanes x 6 residuals) get the full 255.
+__host__ __device__ constexpr int ResidentCtas(int num_residuals, int num_parameters) {
+  return (num_parameters <= 13 && num_residuals <= 3) ? 4 : 2;
+}
+
+template <int kVariant, typename Functor, typename Loss, int kRes, int... Ns>
+__global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ... + 0)))
     EvaluateKernel(const cb200_launch_args a) {
   using Dims = BlockDims<Ns...>;
   constexpr int kNB = Dims::kNumBlocks;
   constexpr int kNP = Dims::kNumParameters;
+  constexpr bool kJets = kVariant != kVariantCost;
+  constexpr bool kGeneric = kVariant == kVariantGeneric;
+  using Layout = PrefetchLayout<Functor, kNP>;
+  constexpr bool kPrefetch = Layout::kFits;
 
-  const int t = blockIdx.x * kEvaluateThreads + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const bool valid = t < a.n;
-  const int tt = valid ? t : a.n - 1;  // idle lanes shadow the last block, write nothing
+  __shared__ __align__(16) unsigned char smem[kPrefetch ? Layout::kSmemBytes : 16];
+  __shared__ double warp_cost[kEvaluateThreads / 32];
 
-  const Functor& functor = static_cast<const Functor*>(a.functors)[tt];
-  const int4* __restrict__ pb_table = reinterpret_cast<const int4*>(a.parameter_block_table);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int n = a.n;
+  const int stride = gridDim.x * kEvaluateThreads;
+  const int first = blockIdx.x * kEvaluateThreads + tid;
+  // Every thread of a CTA runs the same number of iterations (warp collectives).
+  const int cta_first = blockIdx.x * kEvaluateThreads;
+  const int iterations = cta_first < n ? (n - cta_first + stride - 1) / stride : 0;
 
-  int pb_id[kNB];
-  int4 pb[kNB];  // x state_offset, y delta_offset, z tangent_size, w plus_jacobian_offset
+  auto clamp = [&](int rb) { return rb < n ? rb : n - 1; };
+  auto stage_params = [&](int stage) {
+    return reinterpret_cast<double*>(smem + stage * Layout::kStageBytes);
+  };
+  auto stage_functor = [&](int stage) {
+    return smem + stage * Layout::kStageBytes + Layout::kParamBytes * kEvaluateThreads +
+           tid * Layout::kFunctorSlot;
+  };
+  auto load_offsets = [&](int rb, int (&soff)[kNB]) {
+    const int r = clamp(rb);
 #pragma unroll
-  for (int j = 0; j < kNB; ++j) {
-    pb_id[j] = __ldg(a.parameter_block + static_cast<size_t>(j) * a.n + tt);
-    pb[j] = __ldg(pb_table + pb_id[j]);
-  }
-
-  double res[kRes];
-  bool ok;
-  double cost = 0.0;
-
-  if constexpr (!kWithJacobians) {
-    // Cost / residual only: plain doubles, no Jets
-    // (AutoDiffCostFunction::Evaluate with jacobians == nullptr).
-    double x[kNP];
+    for (int j = 0; j < kNB; ++j) soff[j] = __ldg(a.state_offset + static_cast<size_t>(j) * n + r);
+  };
+  auto prefetch = [&](int stage, int rb, const int (&soff)[kNB]) {
+    if constexpr (kPrefetch) {
+      double* dst = stage_params(stage);
 #pragma unroll
-    for (int j = 0; j < kNB; ++j) {
-      const double* __restrict__ src = a.state + pb[j].x;
+      for (int j = 0; j < kNB; ++j) {
+        const double* __restrict__ src = a.state + soff[j];
 #pragma unroll
-      for (int i = 0; i < Dims::Size(j); ++i) x[Dims::Offset(j) + i] = __ldg(src + i);
+        for (int i = 0; i < Dims::Size(j); ++i)
+          CpAsync8(dst + (Dims::Offset(j) + i) * kEvaluateThreads + tid, src + i);
+      }
+      if constexpr (Layout::kFunctorInSmem) {
+        const unsigned char* src =
+            static_cast<const unsigned char*>(a.functors) + static_cast<size_t>(clamp(rb)) * sizeof(Functor);
+        unsigned char* fdst = stage_functor(stage);
+        if constexpr (sizeof(Functor) % 16 == 0) {
+#pragma unroll
+          for (int b = 0; b < static_cast<int>(sizeof(Functor)); b += 16) CpAsync16(fdst + b, src + b);
+        } else if constexpr (sizeof(Functor) % 8 == 0) {
+#pragma unroll
+          for (int b = 0; b < static_cast<int>(sizeof(Functor)); b += 8) CpAsync8(fdst + b, src + b);
+        } else {
+#pragma unroll
+          for (int b = 0; b < static_cast<int>(sizeof(Functor)); b += 4) CpAsync4(fdst + b, src + b);
+        }
+      }
     }
-#pragma unroll
-    for (int r = 0; r < kRes; ++r) res[r] = kImpossibleValue;
-    ok = CallFunctor<Dims>(functor, x, res, std::make_index_sequence<kNB>{});
-#pragma unroll
-    for (int r = 0; r < kRes; ++r) ok = ok && IsValidValue(res[r]);
+    CpAsyncCommit();
+  };
 
-    double s = 0.0;
+  double cost_sum = 0.0;
+  bool all_ok = true;
+
+  int soff_next[kNB];   // state offsets of the block whose prefetch is issued next
+  int soff_cur[kNB];    // state offsets of the block being computed (fallback path)
+  load_offsets(first, soff_cur);
+  prefetch(0, first, soff_cur);
+  load_offsets(first + stride, soff_next);
+
+  for (int k = 0; k < iterations; ++k) {
+    const int rb = first + k * stride;
+    const bool valid = rb < n;
+    const int tt = clamp(rb);
+    const int stage = k & 1;
+
+    // Issue the next block's copies, then fetch the offsets of the one after.
+    int soff_issue[kNB];
 #pragma unroll
-    for (int r = 0; r < kRes; ++r) s += res[r] * res[r];
-    if (a.apply_loss_function) {
-      const Loss* __restrict__ losses = static_cast<const Loss*>(a.loss_table);
-      const Loss& loss = losses[a.loss_index ? __ldg(a.loss_index + tt) : 0];
-      double rho[3];
-      loss.Evaluate(s, rho);
-      cost = 0.5 * rho[0];
-      if (a.output_residuals) {
-        // corrector.h:82-147 then :159-166
-        const double sqrt_rho1 = ::sqrt(rho[1]);
-        double scaling = sqrt_rho1;
+    for (int j = 0; j < kNB; ++j) soff_issue[j] = soff_next[j];
+    prefetch(stage ^ 1, rb + stride, soff_issue);
+    load_offsets(rb + 2 * stride, soff_next);
+
+    // Epilogue-only tables: loaded now, consumed after the functor.
+    int delta_off[kNB], jpos[kNB], tangent_rt[kNB], plus_off[kNB], key[kNB];
+    if constexpr (kJets) {
+#pragma unroll
+      for (int j = 0; j < kNB; ++j) {
+        if constexpr (kGeneric) {
+          const int id = __ldg(a.parameter_block + static_cast<size_t>(j) * n + tt);
+          const int4 rec = __ldg(reinterpret_cast<const int4*>(a.parameter_block_table) + id);
+          delta_off[j] = rec.y;
+          tangent_rt[j] = rec.z;
+          plus_off[j] = rec.w;
+          key[j] = id;
+        } else {
+          delta_off[j] = __ldg(a.delta_offset + static_cast<size_t>(j) * n + tt);
+          tangent_rt[j] = Dims::Size(j);
+          plus_off[j] = -1;
+          key[j] = delta_off[j];
+        }
+        jpos[j] = a.output_jacobian ? __ldg(a.jacobian_pos + static_cast<size_t>(j) * n + tt) : 0;
+      }
+    }
+    const int respos = a.output_residuals ? __ldg(a.residual_pos + tt) : 0;
+    int row_stride_crs = 0;
+    if constexpr (kJets) {
+      if (a.crs && a.output_jacobian) row_stride_crs = __ldg(a.jacobian_row_stride + tt);
+    }
+    const Loss* __restrict__ losses = static_cast<const Loss*>(a.loss_table);
+    const Loss& loss = losses[a.loss_index ? __ldg(a.loss_index + tt) : 0];
+
+    CpAsyncWait<1>();  // this thread's copies for `stage` have landed
+
+    const double* sp = stage_params(stage);
+    auto param = [&](int j, int i) -> double {
+      if constexpr (kPrefetch) {
+        return sp[(Dims::Offset(j) + i) * kEvaluateThreads + tid];
+      } else {
+        return __ldg(a.state + soff_cur[j] + i);
+      }
+    };
+    const Functor* functor_ptr;
+    if constexpr (kPrefetch && Layout::kFunctorInSmem) {
+      functor_ptr = reinterpret_cast<const Functor*>(stage_functor(stage));
+    } else {
+      functor_ptr = static_cast<const Functor*>(a.functors) + tt;
+    }
+    const Functor& functor = *functor_ptr;
+
+    double res[kRes];
+    bool ok;
+    double cost = 0.0;
+    const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
+
+    if constexpr (!kJets) {
+      // AutoDiffCostFunction::Evaluate with jacobians == nullptr.
+      double x[kNP];
+#pragma unroll
+      for (int j = 0; j < kNB; ++j)
+#pragma unroll
+        for (int i = 0; i < Dims::Size(j); ++i) x[Dims::Offset(j) + i] = param(j, i);
+#pragma unroll
+      for (int r = 0; r < kRes; ++r) res[r] = kNaN;  // unwritten outputs stay invalid
+      ok = CallFunctor<Dims>(functor, x, res, std::make_index_sequence<kNB>{});
+      unsigned worst = 0;
+#pragma unroll
+      for (int r = 0; r < kRes; ++r) worst = max(worst, FiniteKey(res[r]));
+      ok = ok && worst < kNonFiniteKey;
+
+      double s = 0.0;
+#pragma unroll
+      for (int r = 0; r < kRes; ++r) s += res[r] * res[r];
+      if (a.apply_loss_function) {
+        double rho[3];
+        loss.Evaluate(s, rho);
+        cost = 0.5 * rho[0];
+        if (a.output_residuals) {
+          // corrector.h:82-147 then :159-166
+          const double sqrt_rho1 = ::sqrt(rho[1]);
+          double scaling = sqrt_rho1;
+          if (!(s == 0.0 || rho[2] <= 0.0)) {
+            const double D = 1.0 + 2.0 * s * rho[2] / rho[1];
+            const double alpha = 1.0 - ::sqrt(D);
+            scaling = sqrt_rho1 / (1 - alpha);
+          }
+#pragma unroll
+          for (int r = 0; r < kRes; ++r) res[r] *= scaling;
+        }
+      } else {
+        cost = 0.5 * s;
+      }
+    } else {
+      using JetT = Jet<double, kNP>;
+      JetT x[kNP];
+#pragma unroll
+      for (int j = 0; j < kNB; ++j)
+#pragma unroll
+        for (int i = 0; i < Dims::Size(j); ++i)
+          x[Dims::Offset(j) + i] = JetT(param(j, i), Dims::Offset(j) + i);
+      JetT out[kRes];
+      // autodiff.h:358-363 invalidates the outputs with kImpossibleValue and the CPU
+      // evaluator rejects evaluations that still contain it
+      // (residual_block_utils.cc:70-95).  Here unwritten outputs are NaN, so the
+      // finite check below covers both conditions.
+#pragma unroll
+      for (int r = 0; r < kRes; ++r) out[r] = JetT::Filled(kNaN, kNaN);
+      ok = CallFunctor<Dims>(functor, x, out, std::make_index_sequence<kNB>{});
+
+      unsigned worst = 0;
+#pragma unroll
+      for (int r = 0; r < kRes; ++r) {
+        res[r] = out[r].a;
+        worst = max(worst, FiniteKey(out[r].a));
+#pragma unroll
+        for (int i = 0; i < kNP; ++i)
+          if (out[r].lane(i)) worst = max(worst, FiniteKey(out[r].v[i]));
+      }
+      ok = ok && worst < kNonFiniteKey;
+
+      double s = 0.0;
+#pragma unroll
+      for (int r = 0; r < kRes; ++r) s += res[r] * res[r];
+
+      double sqrt_rho1 = 1.0, residual_scaling = 1.0, alpha_sq_norm = 0.0;
+      bool correct = false;
+      if (a.apply_loss_function) {
+        double rho[3];
+        loss.Evaluate(s, rho);
+        cost = 0.5 * rho[0];
+        sqrt_rho1 = ::sqrt(rho[1]);
+        residual_scaling = sqrt_rho1;
         if (!(s == 0.0 || rho[2] <= 0.0)) {
           const double D = 1.0 + 2.0 * s * rho[2] / rho[1];
           const double alpha = 1.0 - ::sqrt(D);
-          scaling = sqrt_rho1 / (1 - alpha);
+          residual_scaling = sqrt_rho1 / (1 - alpha);
+          alpha_sq_norm = alpha / s;
         }
-#pragma unroll
-        for (int r = 0; r < kRes; ++r) res[r] *= scaling;
-      }
-    } else {
-      cost = 0.5 * s;
-    }
-  } else {
-    using JetT = Jet<double, kNP>;
-    JetT x[kNP];
-#pragma unroll
-    for (int j = 0; j < kNB; ++j) {
-      const double* __restrict__ src = a.state + pb[j].x;
-#pragma unroll
-      for (int i = 0; i < Dims::Size(j); ++i)
-        x[Dims::Offset(j) + i] = JetT(__ldg(src + i), Dims::Offset(j) + i);
-    }
-    JetT out[kRes];
-#pragma unroll
-    for (int r = 0; r < kRes; ++r) out[r] = JetT::Filled(kImpossibleValue, kImpossibleValue);
-    ok = CallFunctor<Dims>(functor, x, out, std::make_index_sequence<kNB>{});
-
-    // IsEvaluationValid (internal/ceres/residual_block_utils.cc:70-95): the CPU
-    // evaluator rejects non-finite / unwritten values; so does this kernel.
-#pragma unroll
-    for (int r = 0; r < kRes; ++r) {
-      res[r] = out[r].a;
-      ok = ok && IsValidValue(out[r].a);
-#pragma unroll
-      for (int i = 0; i < kNP; ++i)
-        if (out[r].lane(i)) ok = ok && IsValidValue(out[r].v[i]);
-    }
-
-    double s = 0.0;
-#pragma unroll
-    for (int r = 0; r < kRes; ++r) s += res[r] * res[r];
-
-    double sqrt_rho1 = 1.0, residual_scaling = 1.0, alpha_sq_norm = 0.0;
-    bool correct = false;
-    if (a.apply_loss_function) {
-      const Loss* __restrict__ losses = static_cast<const Loss*>(a.loss_table);
-      const Loss& loss = losses[a.loss_index ? __ldg(a.loss_index + tt) : 0];
-      double rho[3];
-      loss.Evaluate(s, rho);
-      cost = 0.5 * rho[0];
-      correct = true;
-      sqrt_rho1 = ::sqrt(rho[1]);
-      residual_scaling = sqrt_rho1;
-      if (!(s == 0.0 || rho[2] <= 0.0)) {
-        const double D = 1.0 + 2.0 * s * rho[2] / rho[1];
-        const double alpha = 1.0 - ::sqrt(D);
-        residual_scaling = sqrt_rho1 / (1 - alpha);
-        alpha_sq_norm = alpha / s;
-      }
-    } else {
-      cost = 0.5 * s;
-    }
-
-    double res_corrected[kRes];
-#pragma unroll
-    for (int r = 0; r < kRes; ++r) res_corrected[r] = res[r] * residual_scaling;
-
-    int row_stride_crs = 0;
-    if (a.crs && a.output_jacobian) row_stride_crs = __ldg(a.jacobian_row_stride + tt);
-
-    // Per parameter block: project, correct, accumulate the gradient, scatter.
-    auto epilogue = [&](auto jc) {
-      constexpr int j = decltype(jc)::value;
-      constexpr int kSize = Dims::Size(j);
-      constexpr int kOff = Dims::Offset(j);
-      const bool active = pb[j].y >= 0;  // constant blocks have no Jacobian
-      int tangent = kSize;
-      double B[kRes][kSize];
-#pragma unroll
-      for (int r = 0; r < kRes; ++r)
-#pragma unroll
-        for (int c = 0; c < kSize; ++c) B[r][c] = out[r].v[kOff + c];
-      if (active && pb[j].w >= 0) {
-        tangent = pb[j].z;
-        BlockEpilogue<kRes, kSize>::MultiplyPlusJacobian(B, a.plus_jacobians + pb[j].w,
-                                                         tangent);
-      }
-      if (correct) BlockEpilogue<kRes, kSize>::Correct(B, tangent, res, sqrt_rho1, alpha_sq_norm);
-
-      if (a.output_gradient) {
-        double g[kSize];
-#pragma unroll
-        for (int c = 0; c < kSize; ++c) {
-          double acc = 0.0;
-#pragma unroll
-          for (int r = 0; r < kRes; ++r) acc += B[r][c] * res_corrected[r];
-          g[c] = (valid && ok && active) ? acc : 0.0;
-        }
-        // Runs of consecutive blocks sharing this parameter block are summed in
-        // the warp first (warp-uniform test, so no divergence around shuffles).
-        const int key = (valid && active) ? pb_id[j] : -1 - lane;
-        const int prev_key = __shfl_up_sync(0xffffffffu, key, 1);
-        const bool head = (lane == 0) || (prev_key != key);
-        const unsigned heads = __ballot_sync(0xffffffffu, head);
-        if (heads != 0xffffffffu) {
-          const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
-          const int run_end = above ? __ffs(above) - 1 : 32;
-          WarpSegmentedSum<kSize>(run_end, g, lane);
-        }
-        if (head && valid && ok && active) {
-          double* __restrict__ dst = a.gradient + pb[j].y;
-#pragma unroll
-          for (int c = 0; c < kSize; ++c)
-            if (c < tangent) RedAdd(dst + c, g[c]);
-        }
+        // Multiplying by exactly 1 changes nothing: skip the correction for blocks in
+        // the quadratic region of the loss (rho' = 1, rho'' = 0).
+        correct = !(sqrt_rho1 == 1.0 && alpha_sq_norm == 0.0);
+      } else {
+        cost = 0.5 * s;
       }
 
-      if (a.output_jacobian && valid && active) {
-        const int pos = __ldg(a.jacobian_pos + static_cast<size_t>(j) * a.n + tt);
-        double* __restrict__ dst = a.jacobian_values + pos;
-        const int stride = a.crs ? row_stride_crs : tangent;
-        if (stride == kSize && tangent == kSize && ((pos & 1) == 0) &&
-            ((kRes * kSize) % 2 == 0)) {
-          // Dense cell, 16-byte aligned: one run of kRes * kSize doubles.
-          double2* __restrict__ d2 = reinterpret_cast<double2*>(dst);
+      double res_corrected[kRes];
 #pragma unroll
-          for (int e = 0; e < kRes * kSize; e += 2) {
-            d2[e / 2] = make_double2(B[e / kSize][e % kSize],
-                                     B[(e + 1) / kSize][(e + 1) % kSize]);
+      for (int r = 0; r < kRes; ++r) res_corrected[r] = res[r] * residual_scaling;
+
+      // Per parameter block: project, correct, accumulate the gradient, scatter.
+      auto epilogue = [&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        constexpr int kSize = Dims::Size(j);
+        constexpr int kOff = Dims::Offset(j);
+        const bool active = kGeneric ? delta_off[j] >= 0 : true;
+        int tangent = kSize;
+        double B[kRes][kSize];
+#pragma unroll
+        for (int r = 0; r < kRes; ++r)
+#pragma unroll
+          for (int c = 0; c < kSize; ++c) B[r][c] = out[r].v[kOff + c];
+        if constexpr (kGeneric) {
+          if (active && plus_off[j] >= 0) {
+            tangent = tangent_rt[j];
+            BlockEpilogue<kRes, kSize>::MultiplyPlusJacobian(B, a.plus_jacobians + plus_off[j],
+                                                             tangent);
           }
-        } else {
+        }
+        if (correct)
+          BlockEpilogue<kRes, kSize>::Correct(B, tangent, res, sqrt_rho1, alpha_sq_norm);
+
+        if (a.output_gradient) {
+          double g[kSize];
 #pragma unroll
-          for (int r = 0; r < kRes; ++r)
+          for (int c = 0; c < kSize; ++c) {
+            double acc = 0.0;
+#pragma unroll
+            for (int r = 0; r < kRes; ++r) acc += B[r][c] * res_corrected[r];
+            g[c] = (valid && ok && active) ? acc : 0.0;
+          }
+          // Runs of consecutive blocks sharing this parameter block are summed in
+          // the warp first (warp-uniform test, so no divergence around shuffles).
+          const int k_ = (valid && active) ? key[j] : -1 - lane;
+          const int prev_key = __shfl_up_sync(0xffffffffu, k_, 1);
+          const bool head = (lane == 0) || (prev_key != k_);
+          const unsigned heads = __ballot_sync(0xffffffffu, head);
+          if (heads != 0xffffffffu) {
+            const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+            const int run_end = above ? __ffs(above) - 1 : 32;
+            WarpSegmentedSum<kSize>(run_end, g, lane);
+          }
+          if (head && valid && ok && active) {
+            double* __restrict__ dst = a.gradient + delta_off[j];
 #pragma unroll
             for (int c = 0; c < kSize; ++c)
-              if (c < tangent) dst[r * stride + c] = B[r][c];
+              if (!kGeneric || c < tangent) RedAdd(dst + c, g[c]);
+          }
         }
+
+        if (a.output_jacobian && valid && active) {
+          double* __restrict__ dst = a.jacobian_values + jpos[j];
+          const int row_stride = a.crs ? row_stride_crs : tangent;
+          if (row_stride == kSize && tangent == kSize && ((jpos[j] & 1) == 0) &&
+              ((kRes * kSize) % 2 == 0)) {
+            // Dense cell, 16-byte aligned: one run of kRes * kSize doubles.
+            double2* __restrict__ d2 = reinterpret_cast<double2*>(dst);
+#pragma unroll
+            for (int e = 0; e < kRes * kSize; e += 2) {
+              d2[e / 2] = make_double2(B[e / kSize][e % kSize],
+                                       B[(e + 1) / kSize][(e + 1) % kSize]);
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < kRes; ++r)
+#pragma unroll
+              for (int c = 0; c < kSize; ++c)
+                if (c < tangent) dst[r * row_stride + c] = B[r][c];
+          }
+        }
+      };
+      if (a.output_jacobian || a.output_gradient) {
+        ForEachBlock(epilogue, std::make_index_sequence<kNB>{});
       }
-    };
-    if (a.output_jacobian || a.output_gradient) {
-      ForEachBlock(epilogue, std::make_index_sequence<kNB>{});
-    }
-    if (correct) {
 #pragma unroll
       for (int r = 0; r < kRes; ++r) res[r] = res_corrected[r];
     }
-  }
 
-  if (valid && !ok) *a.status = 1;
-
-  if (a.output_residuals && valid) {
-    double* __restrict__ dst = a.residuals + __ldg(a.residual_pos + tt);
+    if (valid) {
+      all_ok = all_ok && ok;
+      if (ok) cost_sum += cost;
+      if (a.output_residuals) {
+        double* __restrict__ dst = a.residuals + respos;
+        if ((kRes % 2 == 0) && ((respos & 1) == 0)) {
 #pragma unroll
-    for (int r = 0; r < kRes; ++r) dst[r] = res[r];
+          for (int r = 0; r < kRes; r += 2)
+            reinterpret_cast<double2*>(dst)[r / 2] = make_double2(res[r], res[r + 1 < kRes ? r + 1 : r]);
+        } else {
+#pragma unroll
+          for (int r = 0; r < kRes; ++r) dst[r] = res[r];
+        }
+      }
+    }
+    if constexpr (!kPrefetch) {
+      // Fallback (parameters too large for shared memory): next block's offsets.
+      load_offsets(rb + stride, soff_cur);
+    }
   }
+  CpAsyncWait<0>();
 
-  // Cost: warp shuffle, then one partial per thread block (summed in a fixed order
-  // by the engine, so the cost is reproducible run to run).
-  double c = (valid && ok) ? cost : 0.0;
+  if (!all_ok) *a.status = 1;
+
+  // Cost: warp shuffle, then one partial per CTA (summed in a fixed order by the
+  // engine, so the cost is reproducible run to run for a given grid).
+  double c = cost_sum;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
-  __shared__ double warp_cost[kEvaluateThreads / 32];
-  if (lane == 0) warp_cost[threadIdx.x >> 5] = c;
+  if (lane == 0) warp_cost[tid >> 5] = c;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     double total = 0.0;
 #pragma unroll
     for (int w = 0; w < kEvaluateThreads / 32; ++w) total += warp_cost[w];
     a.cost_partials[blockIdx.x] = total;
+    for (int p = blockIdx.x + gridDim.x; p < a.cost_partial_count; p += gridDim.x)
+      a.cost_partials[p] = 0.0;
   }
 }
 
@@ -392,12 +583,26 @@ __global__ void __launch_bounds__(kEvaluateThreads)
 template <typename Functor, typename Loss, int kRes, int... Ns>
 int LaunchEvaluate(const cb200_launch_args* args, void* stream) {
   if (args->n <= 0) return 0;
-  const int grid = (args->n + kEvaluateThreads - 1) / kEvaluateThreads;
+  static int persistent_ctas = 0;
+  if (persistent_ctas == 0) {
+    int device = 0, sms = 0;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    persistent_ctas = (sms > 0 ? sms : 148) * ResidentCtas(kRes, (Ns + ... + 0));
+  }
+  const int needed = (args->n + kEvaluateThreads - 1) / kEvaluateThreads;
+  int grid = needed < persistent_ctas ? needed : persistent_ctas;
+  if (grid > args->cost_partial_count) grid = args->cost_partial_count;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (args->output_jacobian || args->output_gradient) {
-    EvaluateKernel<true, Functor, Loss, kRes, Ns...><<<grid, kEvaluateThreads, 0, s>>>(*args);
+  if (!(args->output_jacobian || args->output_gradient)) {
+    EvaluateKernel<kVariantCost, Functor, Loss, kRes, Ns...>
+        <<<grid, kEvaluateThreads, 0, s>>>(*args);
+  } else if (args->plain) {
+    EvaluateKernel<kVariantPlain, Functor, Loss, kRes, Ns...>
+        <<<grid, kEvaluateThreads, 0, s>>>(*args);
   } else {
-    EvaluateKernel<false, Functor, Loss, kRes, Ns...><<<grid, kEvaluateThreads, 0, s>>>(*args);
+    EvaluateKernel<kVariantGeneric, Functor, Loss, kRes, Ns...>
+        <<<grid, kEvaluateThreads, 0, s>>>(*args);
   }
   return static_cast<int>(cudaGetLastError());
 }

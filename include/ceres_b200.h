@@ -65,10 +65,15 @@ typedef struct cb200_launch_args {
   uint32_t output_gradient;
   uint32_t apply_loss_function;
   uint32_t crs;                   /* 1: Jacobian rows use the per-block row stride below */
+  uint32_t plain;                 /* 1: no block of this type has a manifold or is constant */
+  int32_t cost_partial_count;     /* entries of cost_partials reserved for this launch; the
+                                     kernel writes all of them (unused ones with zero) */
   const void* functors;           /* n cost functors, sizeof(CostFunctor) each */
   const void* loss_table;         /* distinct loss objects of this type */
   const int32_t* loss_index;      /* per block index into loss_table, or NULL when there is one entry */
   const int32_t* parameter_block; /* [num_blocks][n] index into parameter_block_table */
+  const int32_t* state_offset;    /* [num_blocks][n] offset of the block's parameters in state */
+  const int32_t* delta_offset;    /* [num_blocks][n] offset in the gradient, -1 for a constant block */
   const int32_t* jacobian_pos;    /* [num_blocks][n] offset of element (0,0) of the block in
                                      jacobian_values (rank-local), -1 for a constant block */
   const int32_t* jacobian_row_stride; /* [n] compressed-row: values between consecutive rows */
