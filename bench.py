@@ -30,8 +30,9 @@ import numpy as np  # noqa: E402
 # block ids 8 + cell positions 8 + Jacobian 192 + residuals 16 + parameters and gradient
 # amortised 2 x 3.7.
 ALG_BYTES_PER_RB = 248.0
-# Dense-Jet FLOP count of the reference arithmetic for the same functor.
-ALG_FLOPS_PER_RB = 2966.0
+# Dense-Jet FLOP count of the reference arithmetic for the same functor, loss,
+# Corrector and J^T r included (oracle/count_flops.cc prints 1545 + 218).
+ALG_FLOPS_PER_RB = 1763.0
 
 
 def parse():

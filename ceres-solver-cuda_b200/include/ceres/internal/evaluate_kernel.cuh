@@ -208,9 +208,13 @@ struct PrefetchLayout {
   // Functor slots are padded to 16 bytes so every slot is 16-byte aligned.
   static constexpr int kFunctorSlot = (kFunctorBytes + 15) / 16 * 16;
   static constexpr int kStageBytes = (kParamBytes + kFunctorSlot) * kEvaluateThreads;
-  static constexpr int kSmemBytes = 2 * kStageBytes;
-  static constexpr bool kFits = kSmemBytes <= 46 * 1024;
+  static constexpr int kPrefetchBytes = 2 * kStageBytes;
+  static constexpr bool kFits = kPrefetchBytes <= 96 * 1024;
 };
+
+// Row pitch (doubles) of the per-warp output staging buffer for rows of `n` doubles:
+// odd, so that lanes writing their own row hit different banks.
+__host__ __device__ constexpr int StagePitch(int n) { return n | 1; }
 
 // One thread evaluates one residual block at a time and walks the type's blocks
 // with a grid stride (persistent CTAs: ResidentCtas() per SM).  Software pipeline per thread:
@@ -237,9 +241,14 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
   constexpr bool kGeneric = kVariant == kVariantGeneric;
   using Layout = PrefetchLayout<Functor, kNP>;
   constexpr bool kPrefetch = Layout::kFits;
+  // Dynamic shared memory: [2 prefetch stages][per-warp output staging].
+  constexpr int kPrefetchBytes = kPrefetch ? Layout::kPrefetchBytes : 0;
+  constexpr int kWarpStageDoubles = kJets ? 32 * StagePitch(kRes * Dims::MaxSize()) : 0;
 
-  __shared__ __align__(16) unsigned char smem[kPrefetch ? Layout::kSmemBytes : 16];
+  extern __shared__ __align__(16) unsigned char smem[];
   __shared__ double warp_cost[kEvaluateThreads / 32];
+  double* const wbuf = reinterpret_cast<double*>(smem + kPrefetchBytes) +
+                       (threadIdx.x >> 5) * kWarpStageDoubles;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -502,7 +511,28 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
             const int run_end = above ? __ffs(above) - 1 : 32;
             WarpSegmentedSum<kSize>(run_end, g, lane);
           }
-          if (head && valid && ok && active) {
+          const bool emit = head && valid && ok && active;
+          const unsigned emit_mask = __ballot_sync(0xffffffffu, emit);
+          if (__popc(emit_mask) >= 12) {
+            // Most lanes own a distinct block (the cameras of a BAL warp): stage the
+            // per-lane sums and let consecutive lanes add to consecutive addresses, so
+            // one red instruction touches a few sectors instead of 32.
+            constexpr int kPitch = StagePitch(kSize);
+#pragma unroll
+            for (int c = 0; c < kSize; ++c) wbuf[lane * kPitch + c] = g[c];
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < kSize; ++it) {
+              const int e = it * 32 + lane;
+              const int row = e / kSize;
+              const int c = e - row * kSize;
+              const int d = __shfl_sync(0xffffffffu, delta_off[j], row);
+              const int tg = kGeneric ? __shfl_sync(0xffffffffu, tangent, row) : kSize;
+              if (((emit_mask >> row) & 1u) && c < tg)
+                RedAdd(a.gradient + d + c, wbuf[row * kPitch + c]);
+            }
+            __syncwarp();
+          } else if (emit) {
             double* __restrict__ dst = a.gradient + delta_off[j];
 #pragma unroll
             for (int c = 0; c < kSize; ++c)
@@ -510,24 +540,56 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
           }
         }
 
-        if (a.output_jacobian && valid && active) {
-          double* __restrict__ dst = a.jacobian_values + jpos[j];
+        if (a.output_jacobian) {
+          constexpr int kCell = kRes * kSize;
           const int row_stride = a.crs ? row_stride_crs : tangent;
-          if (row_stride == kSize && tangent == kSize && ((jpos[j] & 1) == 0) &&
-              ((kRes * kSize) % 2 == 0)) {
-            // Dense cell, 16-byte aligned: one run of kRes * kSize doubles.
-            double2* __restrict__ d2 = reinterpret_cast<double2*>(dst);
-#pragma unroll
-            for (int e = 0; e < kRes * kSize; e += 2) {
-              d2[e / 2] = make_double2(B[e / kSize][e % kSize],
-                                       B[(e + 1) / kSize][(e + 1) % kSize]);
-            }
-          } else {
+          const bool dense = valid && active && row_stride == kSize && tangent == kSize;
+          const int base = __shfl_sync(0xffffffffu, jpos[j], 0);
+          // Consecutive residual blocks own consecutive cells (always true inside the
+          // E or the F region of a BlockSparseMatrix): the warp's 32 cells are one run.
+          if (__all_sync(0xffffffffu, dense && jpos[j] == base + lane * kCell)) {
+            constexpr int kPitch = StagePitch(kCell);
 #pragma unroll
             for (int r = 0; r < kRes; ++r)
 #pragma unroll
-              for (int c = 0; c < kSize; ++c)
-                if (c < tangent) dst[r * row_stride + c] = B[r][c];
+              for (int c = 0; c < kSize; ++c) wbuf[lane * kPitch + r * kSize + c] = B[r][c];
+            __syncwarp();
+            double* __restrict__ dst = a.jacobian_values + base;
+            if ((kCell % 2 == 0) && ((base & 1) == 0)) {
+#pragma unroll
+              for (int it = 0; it < kCell / 2; ++it) {
+                const int e = 2 * (it * 32 + lane);
+                const int row = e / kCell;
+                const int col = e - row * kCell;
+                reinterpret_cast<double2*>(dst)[it * 32 + lane] =
+                    make_double2(wbuf[row * kPitch + col], wbuf[row * kPitch + col + 1]);
+              }
+            } else {
+#pragma unroll
+              for (int it = 0; it < kCell; ++it) {
+                const int e = it * 32 + lane;
+                const int row = e / kCell;
+                dst[e] = wbuf[row * kPitch + (e - row * kCell)];
+              }
+            }
+            __syncwarp();
+          } else if (valid && active) {
+            double* __restrict__ dst = a.jacobian_values + jpos[j];
+            if (row_stride == kSize && tangent == kSize && ((jpos[j] & 1) == 0) &&
+                (kCell % 2 == 0)) {
+              double2* __restrict__ d2 = reinterpret_cast<double2*>(dst);
+#pragma unroll
+              for (int e = 0; e < kCell; e += 2) {
+                d2[e / 2] = make_double2(B[e / kSize][e % kSize],
+                                         B[(e + 1) / kSize][(e + 1) % kSize]);
+              }
+            } else {
+#pragma unroll
+              for (int r = 0; r < kRes; ++r)
+#pragma unroll
+                for (int c = 0; c < kSize; ++c)
+                  if (c < tangent) dst[r * row_stride + c] = B[r][c];
+            }
           }
         }
       };
@@ -594,15 +656,31 @@ int LaunchEvaluate(const cb200_launch_args* args, void* stream) {
   int grid = needed < persistent_ctas ? needed : persistent_ctas;
   if (grid > args->cost_partial_count) grid = args->cost_partial_count;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  using Dims = BlockDims<Ns...>;
+  using Layout = PrefetchLayout<Functor, Dims::kNumParameters>;
+  constexpr int kPrefetchBytes = Layout::kFits ? Layout::kPrefetchBytes : 0;
+  constexpr int kJetBytes =
+      kPrefetchBytes + (kEvaluateThreads / 32) * 32 * StagePitch(kRes * Dims::MaxSize()) * 8;
+  constexpr int kCostBytes = kPrefetchBytes > 0 ? kPrefetchBytes : 16;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(EvaluateKernel<kVariantCost, Functor, Loss, kRes, Ns...>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, kCostBytes);
+    cudaFuncSetAttribute(EvaluateKernel<kVariantPlain, Functor, Loss, kRes, Ns...>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, kJetBytes);
+    cudaFuncSetAttribute(EvaluateKernel<kVariantGeneric, Functor, Loss, kRes, Ns...>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, kJetBytes);
+    configured = true;
+  }
   if (!(args->output_jacobian || args->output_gradient)) {
     EvaluateKernel<kVariantCost, Functor, Loss, kRes, Ns...>
-        <<<grid, kEvaluateThreads, 0, s>>>(*args);
+        <<<grid, kEvaluateThreads, kCostBytes, s>>>(*args);
   } else if (args->plain) {
     EvaluateKernel<kVariantPlain, Functor, Loss, kRes, Ns...>
-        <<<grid, kEvaluateThreads, 0, s>>>(*args);
+        <<<grid, kEvaluateThreads, kJetBytes, s>>>(*args);
   } else {
     EvaluateKernel<kVariantGeneric, Functor, Loss, kRes, Ns...>
-        <<<grid, kEvaluateThreads, 0, s>>>(*args);
+        <<<grid, kEvaluateThreads, kJetBytes, s>>>(*args);
   }
   return static_cast<int>(cudaGetLastError());
 }
