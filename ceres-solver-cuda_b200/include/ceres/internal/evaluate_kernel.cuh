@@ -187,27 +187,25 @@ __device__ __forceinline__ void CpAsyncWait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
 }
 
-// Non-finite detection on the integer pipe: max over values of the high word with
-// the sign shifted out is >= 0xffe00000 iff some value is Inf or NaN.
-__device__ __forceinline__ unsigned FiniteKey(double x) {
-  return static_cast<unsigned>(__double2hiint(x)) << 1;
-}
-constexpr unsigned kNonFiniteKey = 0xffe00000u;
-
 // Kernel variants.
 constexpr int kVariantCost = 0;     // cost / residuals only: plain doubles, no Jets
 constexpr int kVariantPlain = 1;    // Jets; no manifold and no constant block in this type
 constexpr int kVariantGeneric = 2;  // Jets; per-block manifold projection / constant blocks
 
-template <typename Functor, int kNumParameters>
+template <typename Functor, int kNumParameters, int kNumBlocks>
 struct PrefetchLayout {
   static constexpr int kParamBytes = kNumParameters * 8;
+  // Per-block int tables that travel with the parameters: [delta offset or block id]
+  // and [Jacobian position] per argument, residual position, CRS row stride, loss index.
+  static constexpr int kIntSlots = 2 * kNumBlocks + 3;
+  static constexpr int kSlotDelta = 0, kSlotJpos = kNumBlocks, kSlotResidual = 2 * kNumBlocks,
+                       kSlotRowStride = 2 * kNumBlocks + 1, kSlotLoss = 2 * kNumBlocks + 2;
   static constexpr bool kFunctorInSmem =
       (sizeof(Functor) % 4 == 0) && (alignof(Functor) <= 16) && (sizeof(Functor) <= 128);
   static constexpr int kFunctorBytes = kFunctorInSmem ? static_cast<int>(sizeof(Functor)) : 0;
   // Functor slots are padded to 16 bytes so every slot is 16-byte aligned.
   static constexpr int kFunctorSlot = (kFunctorBytes + 15) / 16 * 16;
-  static constexpr int kStageBytes = (kParamBytes + kFunctorSlot) * kEvaluateThreads;
+  static constexpr int kStageBytes = (kParamBytes + kIntSlots * 4 + kFunctorSlot) * kEvaluateThreads;
   static constexpr int kPrefetchBytes = 2 * kStageBytes;
   static constexpr bool kFits = kPrefetchBytes <= 96 * 1024;
 };
@@ -227,8 +225,11 @@ __host__ __device__ constexpr int StagePitch(int n) { return n | 1; }
 // per issue, FP64 pipe 22% busy; profiles/r1_v1_ncu_summary.txt).
 // CTAs per SM the kernel is compiled for: small functors fit 128 registers (4 CTAs of
 // 128 threads); wide Jets (pose graphs: 14 lanes x 6 residuals) get the full 255.
+#ifndef CB200_RESIDENT_CTAS_SMALL
+#define CB200_RESIDENT_CTAS_SMALL 4
+#endif
 __host__ __device__ constexpr int ResidentCtas(int num_residuals, int num_parameters) {
-  return (num_parameters <= 13 && num_residuals <= 3) ? 4 : 2;
+  return (num_parameters <= 13 && num_residuals <= 3) ? CB200_RESIDENT_CTAS_SMALL : 2;
 }
 
 template <int kVariant, typename Functor, typename Loss, int kRes, int... Ns>
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
   constexpr int kNP = Dims::kNumParameters;
   constexpr bool kJets = kVariant != kVariantCost;
   constexpr bool kGeneric = kVariant == kVariantGeneric;
-  using Layout = PrefetchLayout<Functor, kNP>;
+  using Layout = PrefetchLayout<Functor, kNP, kNB>;
   constexpr bool kPrefetch = Layout::kFits;
   // Dynamic shared memory: [2 prefetch stages][per-warp output staging].
   constexpr int kPrefetchBytes = kPrefetch ? Layout::kPrefetchBytes : 0;
@@ -263,8 +264,13 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
   auto stage_params = [&](int stage) {
     return reinterpret_cast<double*>(smem + stage * Layout::kStageBytes);
   };
+  auto stage_ints = [&](int stage) {
+    return reinterpret_cast<int*>(smem + stage * Layout::kStageBytes +
+                                  Layout::kParamBytes * kEvaluateThreads);
+  };
   auto stage_functor = [&](int stage) {
-    return smem + stage * Layout::kStageBytes + Layout::kParamBytes * kEvaluateThreads +
+    return smem + stage * Layout::kStageBytes +
+           (Layout::kParamBytes + Layout::kIntSlots * 4) * kEvaluateThreads +
            tid * Layout::kFunctorSlot;
   };
   auto load_offsets = [&](int rb, int (&soff)[kNB]) {
@@ -281,6 +287,29 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
 #pragma unroll
         for (int i = 0; i < Dims::Size(j); ++i)
           CpAsync8(dst + (Dims::Offset(j) + i) * kEvaluateThreads + tid, src + i);
+      }
+      // The int tables of the block (consumed in the epilogue, from shared memory, so
+      // no register is held across the functor).
+      {
+        const int r = clamp(rb);
+        int* idst = stage_ints(stage) + tid;
+        if constexpr (kJets) {
+#pragma unroll
+          for (int j = 0; j < kNB; ++j) {
+            const int32_t* tab = kGeneric ? a.parameter_block : a.delta_offset;
+            CpAsync4(idst + (Layout::kSlotDelta + j) * kEvaluateThreads,
+                     tab + static_cast<size_t>(j) * n + r);
+            if (a.output_jacobian)
+              CpAsync4(idst + (Layout::kSlotJpos + j) * kEvaluateThreads,
+                       a.jacobian_pos + static_cast<size_t>(j) * n + r);
+          }
+          if (a.crs && a.output_jacobian)
+            CpAsync4(idst + Layout::kSlotRowStride * kEvaluateThreads, a.jacobian_row_stride + r);
+        }
+        if (a.output_residuals)
+          CpAsync4(idst + Layout::kSlotResidual * kEvaluateThreads, a.residual_pos + r);
+        if (a.loss_index)
+          CpAsync4(idst + Layout::kSlotLoss * kEvaluateThreads, a.loss_index + r);
       }
       if constexpr (Layout::kFunctorInSmem) {
         const unsigned char* src =
@@ -323,36 +352,47 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
     prefetch(stage ^ 1, rb + stride, soff_issue);
     load_offsets(rb + 2 * stride, soff_next);
 
-    // Epilogue-only tables: loaded now, consumed after the functor.
+    CpAsyncWait<1>();  // this thread's copies for `stage` have landed
+
+    // Per-block int tables: from the prefetched stage (or straight from global memory
+    // when the parameters do not fit in shared memory).
+    const int* sints = stage_ints(stage) + tid;
+    auto table = [&](int slot, const int32_t* global_table, size_t index) -> int {
+      if constexpr (kPrefetch) {
+        return sints[slot * kEvaluateThreads];
+      } else {
+        return __ldg(global_table + index);
+      }
+    };
     int delta_off[kNB], jpos[kNB], tangent_rt[kNB], plus_off[kNB], key[kNB];
     if constexpr (kJets) {
 #pragma unroll
       for (int j = 0; j < kNB; ++j) {
+        const size_t at = static_cast<size_t>(j) * n + tt;
         if constexpr (kGeneric) {
-          const int id = __ldg(a.parameter_block + static_cast<size_t>(j) * n + tt);
+          const int id = table(Layout::kSlotDelta + j, a.parameter_block, at);
           const int4 rec = __ldg(reinterpret_cast<const int4*>(a.parameter_block_table) + id);
           delta_off[j] = rec.y;
           tangent_rt[j] = rec.z;
           plus_off[j] = rec.w;
           key[j] = id;
         } else {
-          delta_off[j] = __ldg(a.delta_offset + static_cast<size_t>(j) * n + tt);
+          delta_off[j] = table(Layout::kSlotDelta + j, a.delta_offset, at);
           tangent_rt[j] = Dims::Size(j);
           plus_off[j] = -1;
           key[j] = delta_off[j];
         }
-        jpos[j] = a.output_jacobian ? __ldg(a.jacobian_pos + static_cast<size_t>(j) * n + tt) : 0;
+        jpos[j] = a.output_jacobian ? table(Layout::kSlotJpos + j, a.jacobian_pos, at) : 0;
       }
     }
-    const int respos = a.output_residuals ? __ldg(a.residual_pos + tt) : 0;
+    const int respos = a.output_residuals ? table(Layout::kSlotResidual, a.residual_pos, tt) : 0;
     int row_stride_crs = 0;
     if constexpr (kJets) {
-      if (a.crs && a.output_jacobian) row_stride_crs = __ldg(a.jacobian_row_stride + tt);
+      if (a.crs && a.output_jacobian)
+        row_stride_crs = table(Layout::kSlotRowStride, a.jacobian_row_stride, tt);
     }
     const Loss* __restrict__ losses = static_cast<const Loss*>(a.loss_table);
-    const Loss& loss = losses[a.loss_index ? __ldg(a.loss_index + tt) : 0];
-
-    CpAsyncWait<1>();  // this thread's copies for `stage` have landed
+    const Loss& loss = losses[a.loss_index ? table(Layout::kSlotLoss, a.loss_index, tt) : 0];
 
     const double* sp = stage_params(stage);
     auto param = [&](int j, int i) -> double {
@@ -385,10 +425,10 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
 #pragma unroll
       for (int r = 0; r < kRes; ++r) res[r] = kNaN;  // unwritten outputs stay invalid
       ok = CallFunctor<Dims>(functor, x, res, std::make_index_sequence<kNB>{});
-      unsigned worst = 0;
+      double check = 0.0;  // stays 0 iff every value is finite (0 * Inf = NaN)
 #pragma unroll
-      for (int r = 0; r < kRes; ++r) worst = max(worst, FiniteKey(res[r]));
-      ok = ok && worst < kNonFiniteKey;
+      for (int r = 0; r < kRes; ++r) check = ::fma(res[r], 0.0, check);
+      ok = ok && check == 0.0;
 
       double s = 0.0;
 #pragma unroll
@@ -429,16 +469,16 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
       for (int r = 0; r < kRes; ++r) out[r] = JetT::Filled(kNaN, kNaN);
       ok = CallFunctor<Dims>(functor, x, out, std::make_index_sequence<kNB>{});
 
-      unsigned worst = 0;
+      double check = 0.0;  // stays 0 iff every value is finite (0 * Inf = NaN)
 #pragma unroll
       for (int r = 0; r < kRes; ++r) {
         res[r] = out[r].a;
-        worst = max(worst, FiniteKey(out[r].a));
+        check = ::fma(out[r].a, 0.0, check);
 #pragma unroll
         for (int i = 0; i < kNP; ++i)
-          if (out[r].lane(i)) worst = max(worst, FiniteKey(out[r].v[i]));
+          if (out[r].lane(i)) check = ::fma(out[r].v[i], 0.0, check);
       }
-      ok = ok && worst < kNonFiniteKey;
+      ok = ok && check == 0.0;
 
       double s = 0.0;
 #pragma unroll
@@ -657,7 +697,7 @@ int LaunchEvaluate(const cb200_launch_args* args, void* stream) {
   if (grid > args->cost_partial_count) grid = args->cost_partial_count;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   using Dims = BlockDims<Ns...>;
-  using Layout = PrefetchLayout<Functor, Dims::kNumParameters>;
+  using Layout = PrefetchLayout<Functor, Dims::kNumParameters, Dims::kNumBlocks>;
   constexpr int kPrefetchBytes = Layout::kFits ? Layout::kPrefetchBytes : 0;
   constexpr int kJetBytes =
       kPrefetchBytes + (kEvaluateThreads / 32) * 32 * StagePitch(kRes * Dims::MaxSize()) * 8;
