@@ -187,6 +187,68 @@ __device__ __forceinline__ void CpAsyncWait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
 }
 
+// Tuning switches (compile-time; scripts/kbench.cu builds the kernel with several
+// settings to measure each on the GPU).
+#ifndef CB200_KERNEL_INTS_IN_SMEM
+#define CB200_KERNEL_INTS_IN_SMEM 1   // per-block int tables ride the cp.async pipeline
+#endif
+#ifndef CB200_KERNEL_FMA_CHECK
+#define CB200_KERNEL_FMA_CHECK 1      // finite check: 1 = FMA chain (FP64 pipe), 0 = integer max
+#endif
+#ifndef CB200_KERNEL_STAGE_GRADIENT
+#define CB200_KERNEL_STAGE_GRADIENT 1 // warp-staged, sector-coalesced gradient reductions
+#endif
+#ifndef CB200_KERNEL_STAGE_JACOBIAN
+#define CB200_KERNEL_STAGE_JACOBIAN 1 // warp-staged, fully coalesced Jacobian stores
+#endif
+#ifndef CB200_KERNEL_BULK_STORE
+#define CB200_KERNEL_BULK_STORE 1     // staged cells leave through TMA bulk copies (UBLKCP)
+#endif
+
+// ---- TMA bulk store shared -> global (cp.async.bulk): one instruction moves a
+// warp's whole run of Jacobian cells; no LDS / STG / address arithmetic per element.
+__device__ __forceinline__ void FenceProxyAsyncShared() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void BulkStore(void* gmem, const void* smem, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem),
+               "r"(static_cast<unsigned>(__cvta_generic_to_shared(smem))), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void BulkCommit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// Waits until the bulk copies issued by this thread have finished READING shared memory.
+__device__ __forceinline__ void BulkWaitRead() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void BulkWaitAll() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+__host__ __device__ constexpr int MaxInt(int a, int b) { return a > b ? a : b; }
+// Doubles of per-warp output staging: either one padded block row per lane (64-bit
+// staging) or every argument's dense cells side by side (bulk-store staging).
+__host__ __device__ constexpr int WarpStageDoubles(int num_residuals, int max_block,
+                                                   int num_parameters) {
+  return 32 * MaxInt((num_residuals * max_block) | 1, num_residuals * num_parameters);
+}
+
+// Accumulates evidence of a non-finite value; Bad() is true iff one was seen.
+struct FiniteCheck {
+#if CB200_KERNEL_FMA_CHECK
+  double acc = 0.0;  // stays 0 iff every value is finite (0 * Inf = NaN)
+  __device__ __forceinline__ void Add(double x) { acc = ::fma(x, 0.0, acc); }
+  __device__ __forceinline__ bool Bad() const { return !(acc == 0.0); }
+#else
+  unsigned worst = 0;  // max of the high words with the sign shifted out
+  __device__ __forceinline__ void Add(double x) {
+    worst = max(worst, static_cast<unsigned>(__double2hiint(x)) << 1);
+  }
+  __device__ __forceinline__ bool Bad() const { return worst >= 0xffe00000u; }
+#endif
+};
+
 // Kernel variants.
 constexpr int kVariantCost = 0;     // cost / residuals only: plain doubles, no Jets
 constexpr int kVariantPlain = 1;    // Jets; no manifold and no constant block in this type
@@ -244,7 +306,7 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
   constexpr bool kPrefetch = Layout::kFits;
   // Dynamic shared memory: [2 prefetch stages][per-warp output staging].
   constexpr int kPrefetchBytes = kPrefetch ? Layout::kPrefetchBytes : 0;
-  constexpr int kWarpStageDoubles = kJets ? 32 * StagePitch(kRes * Dims::MaxSize()) : 0;
+  constexpr int kWarpStageDoubles = kJets ? WarpStageDoubles(kRes, Dims::MaxSize(), kNP) : 0;
 
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ double warp_cost[kEvaluateThreads / 32];
@@ -290,7 +352,7 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
       }
       // The int tables of the block (consumed in the epilogue, from shared memory, so
       // no register is held across the functor).
-      {
+      if constexpr (CB200_KERNEL_INTS_IN_SMEM) {
         const int r = clamp(rb);
         int* idst = stage_ints(stage) + tid;
         if constexpr (kJets) {
@@ -332,6 +394,7 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
 
   double cost_sum = 0.0;
   bool all_ok = true;
+  bool bulk_pending = false;  // warp-uniform: a bulk store may still read the staging buffer
 
   int soff_next[kNB];   // state offsets of the block whose prefetch is issued next
   int soff_cur[kNB];    // state offsets of the block being computed (fallback path)
@@ -358,7 +421,7 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
     // when the parameters do not fit in shared memory).
     const int* sints = stage_ints(stage) + tid;
     auto table = [&](int slot, const int32_t* global_table, size_t index) -> int {
-      if constexpr (kPrefetch) {
+      if constexpr (kPrefetch && CB200_KERNEL_INTS_IN_SMEM) {
         return sints[slot * kEvaluateThreads];
       } else {
         return __ldg(global_table + index);
@@ -425,10 +488,10 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
 #pragma unroll
       for (int r = 0; r < kRes; ++r) res[r] = kNaN;  // unwritten outputs stay invalid
       ok = CallFunctor<Dims>(functor, x, res, std::make_index_sequence<kNB>{});
-      double check = 0.0;  // stays 0 iff every value is finite (0 * Inf = NaN)
+      FiniteCheck check;
 #pragma unroll
-      for (int r = 0; r < kRes; ++r) check = ::fma(res[r], 0.0, check);
-      ok = ok && check == 0.0;
+      for (int r = 0; r < kRes; ++r) check.Add(res[r]);
+      ok = ok && !check.Bad();
 
       double s = 0.0;
 #pragma unroll
@@ -469,16 +532,16 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
       for (int r = 0; r < kRes; ++r) out[r] = JetT::Filled(kNaN, kNaN);
       ok = CallFunctor<Dims>(functor, x, out, std::make_index_sequence<kNB>{});
 
-      double check = 0.0;  // stays 0 iff every value is finite (0 * Inf = NaN)
+      FiniteCheck check;
 #pragma unroll
       for (int r = 0; r < kRes; ++r) {
         res[r] = out[r].a;
-        check = ::fma(out[r].a, 0.0, check);
+        check.Add(out[r].a);
 #pragma unroll
         for (int i = 0; i < kNP; ++i)
-          if (out[r].lane(i)) check = ::fma(out[r].v[i], 0.0, check);
+          if (out[r].lane(i)) check.Add(out[r].v[i]);
       }
-      ok = ok && check == 0.0;
+      ok = ok && !check.Bad();
 
       double s = 0.0;
 #pragma unroll
@@ -508,6 +571,14 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
       double res_corrected[kRes];
 #pragma unroll
       for (int r = 0; r < kRes; ++r) res_corrected[r] = res[r] * residual_scaling;
+
+      // The staging buffer may still be read by last iteration's bulk stores.
+      if (CB200_KERNEL_BULK_STORE && bulk_pending) {
+        if (lane == 0) BulkWaitRead();
+        __syncwarp();
+        bulk_pending = false;
+      }
+      bool bulk_issued = false;
 
       // Per parameter block: project, correct, accumulate the gradient, scatter.
       auto epilogue = [&](auto jc) {
@@ -553,7 +624,7 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
           }
           const bool emit = head && valid && ok && active;
           const unsigned emit_mask = __ballot_sync(0xffffffffu, emit);
-          if (__popc(emit_mask) >= 12) {
+          if (CB200_KERNEL_STAGE_GRADIENT && __popc(emit_mask) >= 12) {
             // Most lanes own a distinct block (the cameras of a BAL warp): stage the
             // per-lane sums and let consecutive lanes add to consecutive addresses, so
             // one red instruction touches a few sectors instead of 32.
@@ -587,7 +658,23 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
           const int base = __shfl_sync(0xffffffffu, jpos[j], 0);
           // Consecutive residual blocks own consecutive cells (always true inside the
           // E or the F region of a BlockSparseMatrix): the warp's 32 cells are one run.
-          if (__all_sync(0xffffffffu, dense && jpos[j] == base + lane * kCell)) {
+          const bool run = CB200_KERNEL_STAGE_JACOBIAN &&
+                           __all_sync(0xffffffffu, dense && jpos[j] == base + lane * kCell);
+          if (run && CB200_KERNEL_BULK_STORE && (kCell % 2 == 0) && ((base & 1) == 0)) {
+            // Cells laid out exactly as in global memory (pitch = cell, 128-bit stores are
+            // bank-conflict free for cells that are a multiple of 16 bytes), then one
+            // TMA bulk copy for the warp's 32 cells.
+            double* region = wbuf + 32 * kRes * kOff;
+            double2* mine = reinterpret_cast<double2*>(region + lane * kCell);
+#pragma unroll
+            for (int e = 0; e < kCell; e += 2)
+              mine[e / 2] = make_double2(B[e / kSize][e % kSize],
+                                         B[(e + 1) / kSize][(e + 1) % kSize]);
+            FenceProxyAsyncShared();
+            __syncwarp();
+            if (lane == 0) BulkStore(a.jacobian_values + base, region, 32 * kCell * 8);
+            bulk_issued = true;
+          } else if (run) {
             constexpr int kPitch = StagePitch(kCell);
 #pragma unroll
             for (int r = 0; r < kRes; ++r)
@@ -636,6 +723,10 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
       if (a.output_jacobian || a.output_gradient) {
         ForEachBlock(epilogue, std::make_index_sequence<kNB>{});
       }
+      if (bulk_issued) {
+        if (lane == 0) BulkCommit();
+        bulk_pending = true;
+      }
 #pragma unroll
       for (int r = 0; r < kRes; ++r) res[r] = res_corrected[r];
     }
@@ -661,6 +752,7 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
     }
   }
   CpAsyncWait<0>();
+  if (bulk_pending && lane == 0) BulkWaitAll();
 
   if (!all_ok) *a.status = 1;
 
@@ -700,7 +792,8 @@ int LaunchEvaluate(const cb200_launch_args* args, void* stream) {
   using Layout = PrefetchLayout<Functor, Dims::kNumParameters, Dims::kNumBlocks>;
   constexpr int kPrefetchBytes = Layout::kFits ? Layout::kPrefetchBytes : 0;
   constexpr int kJetBytes =
-      kPrefetchBytes + (kEvaluateThreads / 32) * 32 * StagePitch(kRes * Dims::MaxSize()) * 8;
+      kPrefetchBytes +
+      (kEvaluateThreads / 32) * WarpStageDoubles(kRes, Dims::MaxSize(), Dims::kNumParameters) * 8;
   constexpr int kCostBytes = kPrefetchBytes > 0 ? kPrefetchBytes : 16;
   static bool configured = false;
   if (!configured) {

@@ -1,0 +1,108 @@
+// Stand-alone micro-benchmark of the BAL evaluation kernel: builds a synthetic
+// BAL-shaped table set directly in C++ (no engine, no Python) and times
+// LaunchEvaluate<SnavelyReprojectionError, HuberLossCUDA, 2, 9, 3>.  Compiled several
+// times with different -DCB200_KERNEL_* settings to A/B kernel variants on the GPU.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Iinclude \
+//        -Iceres-solver-cuda_b200/include -Iceres-solver-cuda_b200/examples scripts/kbench.cu
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+
+#include "ceres/internal/evaluate_kernel.cuh"
+#include "ceres/loss_function_cuda.h"
+#include "snavely_reprojection_error.h"
+
+using Functor = ceres::examples::SnavelyReprojectionError;
+using Loss = ceres::HuberLossCUDA;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { std::printf("%s: %s\n", #x, cudaGetErrorString(e_)); std::exit(1);} } while (0)
+
+template <typename T> T* Upload(const std::vector<T>& v) {
+  T* d; CK(cudaMalloc(&d, v.size() * sizeof(T) + 16));
+  CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice)); return d;
+}
+
+int main(int argc, char** argv) {
+  const int nc = argc > 1 ? std::atoi(argv[1]) : 13682;
+  const int np = argc > 2 ? std::atoi(argv[2]) : 4456117;
+  const int n = argc > 3 ? std::atoi(argv[3]) : 28987644;
+  const int want_g = argc > 4 ? std::atoi(argv[4]) : 1;
+  const int want_j = argc > 5 ? std::atoi(argv[5]) : 1;
+  std::mt19937_64 rng(3);
+  std::normal_distribution<double> N01(0, 1);
+  std::uniform_real_distribution<double> U(0, 1);
+  std::vector<double> state(3 * (size_t)np + 9 * (size_t)nc);
+  for (int i = 0; i < 3 * np; ++i) state[i] = N01(rng);
+  for (int c = 0; c < nc; ++c) {
+    double* cam = &state[3 * (size_t)np + 9 * (size_t)c];
+    for (int k = 0; k < 3; ++k) cam[k] = 0.1 * N01(rng);
+    cam[3] = 0.5 * N01(rng); cam[4] = 0.5 * N01(rng); cam[5] = -8 + 0.5 * N01(rng);
+    cam[6] = 400 + 800 * U(rng); cam[7] = 1e-7 * N01(rng); cam[8] = 1e-13 * N01(rng);
+  }
+  std::vector<int> soff(2 * (size_t)n), doff(2 * (size_t)n), jpos(2 * (size_t)n), respos(n);
+  std::vector<Functor> functors; functors.reserve(n);
+  // observations grouped by point, ~n/np per point, cameras distinct ascending per point
+  size_t k = 0;
+  for (int p = 0; p < np && k < (size_t)n; ++p) {
+    int deg = (int)((size_t)n * (p + 1) / np - (size_t)n * p / np);
+    if (deg < 1) deg = 1;
+    int cam = (int)(nc * U(rng) * U(rng));
+    for (int d = 0; d < deg && k < (size_t)n; ++d, ++k) {
+      cam = (cam + 1 + (int)(U(rng) * (nc / (deg + 1)))) % nc;
+      soff[k] = 3 * np + 9 * cam; soff[n + k] = 3 * p;
+      doff[k] = 3 * np + 9 * cam; doff[n + k] = 3 * p;
+      jpos[k] = 6 * n + 18 * (int)k; jpos[n + k] = 6 * (int)k;  // F then E region (int32 like the layouts)
+      respos[k] = 2 * (int)k;
+      // exact projection + noise so residuals are pixel-sized
+      const double* c9 = &state[soff[k]]; const double* X = &state[3 * (size_t)p];
+      double th = std::sqrt(c9[0]*c9[0]+c9[1]*c9[1]+c9[2]*c9[2]), P[3];
+      double w[3] = {c9[0]/th, c9[1]/th, c9[2]/th}, ct = std::cos(th), st = std::sin(th);
+      double wx[3] = {w[1]*X[2]-w[2]*X[1], w[2]*X[0]-w[0]*X[2], w[0]*X[1]-w[1]*X[0]};
+      double wd = (w[0]*X[0]+w[1]*X[1]+w[2]*X[2])*(1-ct);
+      for (int i = 0; i < 3; ++i) P[i] = X[i]*ct + wx[i]*st + w[i]*wd + c9[3+i];
+      double xp = -P[0]/P[2], yp = -P[1]/P[2], r2 = xp*xp+yp*yp, dd = 1 + r2*(c9[7]+c9[8]*r2);
+      double noise = U(rng) < 0.02 ? 20.0 : 0.5;
+      functors.emplace_back(c9[6]*dd*xp + noise*N01(rng), c9[6]*dd*yp + noise*N01(rng));
+    }
+  }
+  std::printf("blocks %zu (jacobian %.2f GB)\n", k, 192.0 * k / 1e9);
+  Loss loss(1.0);
+  cb200_launch_args a{};
+  a.n = n; a.output_residuals = 1; a.output_jacobian = want_j; a.output_gradient = want_g;
+  a.apply_loss_function = 1; a.crs = 0; a.plain = 1;
+  const int grid_max = (n + 127) / 128;
+  a.cost_partial_count = grid_max;
+  a.functors = Upload(functors);
+  std::vector<char> lb((char*)&loss, (char*)&loss + sizeof(loss));
+  a.loss_table = Upload(lb); a.loss_index = nullptr;
+  a.state_offset = Upload(soff); a.delta_offset = Upload(doff); a.jacobian_pos = Upload(jpos);
+  a.residual_pos = Upload(respos); a.parameter_block = nullptr; a.parameter_block_table = nullptr;
+  a.jacobian_row_stride = nullptr; a.state = Upload(state); a.plus_jacobians = nullptr;
+  double *res, *jac, *grad, *cp; int* status;
+  CK(cudaMalloc(&res, 16 * (size_t)n)); CK(cudaMalloc(&jac, 192 * (size_t)n));
+  CK(cudaMalloc(&grad, 8 * state.size())); CK(cudaMalloc(&cp, 8 * (size_t)grid_max)); CK(cudaMalloc(&status, 4));
+  CK(cudaMemset(status, 0, 4));
+  a.residuals = res; a.jacobian_values = jac; a.gradient = grad; a.cost_partials = cp; a.status = status;
+  cudaStream_t s; CK(cudaStreamCreate(&s));
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e9f, sum = 0; const int reps = 10;
+  for (int it = 0; it < reps + 3; ++it) {
+    CK(cudaMemsetAsync(grad, 0, 8 * state.size(), s));
+    cudaEventRecord(e0, s);
+    int rc = ceres::internal::LaunchEvaluate<Functor, Loss, 2, 9, 3>(&a, s);
+    cudaEventRecord(e1, s);
+    CK(cudaStreamSynchronize(s));
+    if (rc) { std::printf("launch failed %d\n", rc); return 1; }
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (it >= 3) { best = ms < best ? ms : best; sum += ms; }
+  }
+  int st; CK(cudaMemcpy(&st, status, 4, cudaMemcpyDeviceToHost));
+  std::vector<double> part(grid_max); CK(cudaMemcpy(part.data(), cp, 8 * (size_t)grid_max, cudaMemcpyDeviceToHost));
+  double cost = 0; for (double v : part) cost += v;
+  std::printf("KBENCH %s ctas=%d ints_smem=%d fma_check=%d stage_g=%d stage_j=%d g=%d j=%d : mean %.3f ms best %.3f ms  (%.2f G blocks/s)  status=%d cost=%.6e\n",
+              argc > 6 ? argv[6] : "", CB200_RESIDENT_CTAS_SMALL, CB200_KERNEL_INTS_IN_SMEM, CB200_KERNEL_FMA_CHECK,
+              CB200_KERNEL_STAGE_GRADIENT, CB200_KERNEL_STAGE_JACOBIAN, want_g, want_j, sum / reps, best, n / (sum / reps) / 1e6, st, cost);
+  return 0;
+}
