@@ -227,11 +227,12 @@ __device__ __forceinline__ void BulkWaitAll() {
 }
 
 __host__ __device__ constexpr int MaxInt(int a, int b) { return a > b ? a : b; }
-// Doubles of per-warp output staging: either one padded block row per lane (64-bit
-// staging) or every argument's dense cells side by side (bulk-store staging).
+// Doubles of per-warp output staging: every argument's dense cells side by side.
+// Argument j stages into its own region [32 * kRes * Offset(j), +32 * kRes * Size(j));
+// padded (odd-pitch) staging may spill 32 doubles past its region, hence the slack.
 __host__ __device__ constexpr int WarpStageDoubles(int num_residuals, int max_block,
                                                    int num_parameters) {
-  return 32 * MaxInt((num_residuals * max_block) | 1, num_residuals * num_parameters);
+  return 32 * num_residuals * num_parameters + 32 + 0 * max_block;
 }
 
 // Accumulates evidence of a non-finite value; Bad() is true iff one was seen.
@@ -285,10 +286,12 @@ __host__ __device__ constexpr int StagePitch(int n) { return n | 1; }
 // block are in flight during the ~1300 instructions of the previous block instead
 // of stalling the warp (v1 of this kernel: long-scoreboard stalls 7.5 of 15 cycles
 // per issue, FP64 pipe 22% busy; profiles/r1_v1_ncu_summary.txt).
-// CTAs per SM the kernel is compiled for: small functors fit 128 registers (4 CTAs of
-// 128 threads); wide Jets (pose graphs: 14 lanes x 6 residuals) get the full 255.
+// CTAs per SM the kernel is compiled for.  Measured on B200 for the BAL functor
+// (scripts/kbench.cu): 3 CTAs x 128 threads (170 registers, 61 KB shared each) equal or
+// beat 4 (128 registers, spills) and 5; wide Jets (pose graphs: 14 lanes x 6 residuals)
+// get the full 255 registers.
 #ifndef CB200_RESIDENT_CTAS_SMALL
-#define CB200_RESIDENT_CTAS_SMALL 4
+#define CB200_RESIDENT_CTAS_SMALL 3
 #endif
 __host__ __device__ constexpr int ResidentCtas(int num_residuals, int num_parameters) {
   return (num_parameters <= 13 && num_residuals <= 3) ? CB200_RESIDENT_CTAS_SMALL : 2;
@@ -629,8 +632,9 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
             // per-lane sums and let consecutive lanes add to consecutive addresses, so
             // one red instruction touches a few sectors instead of 32.
             constexpr int kPitch = StagePitch(kSize);
+            double* gbuf = wbuf + 32 * kRes * kOff;  // this argument's own region
 #pragma unroll
-            for (int c = 0; c < kSize; ++c) wbuf[lane * kPitch + c] = g[c];
+            for (int c = 0; c < kSize; ++c) gbuf[lane * kPitch + c] = g[c];
             __syncwarp();
 #pragma unroll
             for (int it = 0; it < kSize; ++it) {
@@ -640,7 +644,7 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
               const int d = __shfl_sync(0xffffffffu, delta_off[j], row);
               const int tg = kGeneric ? __shfl_sync(0xffffffffu, tangent, row) : kSize;
               if (((emit_mask >> row) & 1u) && c < tg)
-                RedAdd(a.gradient + d + c, wbuf[row * kPitch + c]);
+                RedAdd(a.gradient + d + c, gbuf[row * kPitch + c]);
             }
             __syncwarp();
           } else if (emit) {
@@ -676,10 +680,11 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
             bulk_issued = true;
           } else if (run) {
             constexpr int kPitch = StagePitch(kCell);
+            double* jbuf = wbuf + 32 * kRes * kOff;
 #pragma unroll
             for (int r = 0; r < kRes; ++r)
 #pragma unroll
-              for (int c = 0; c < kSize; ++c) wbuf[lane * kPitch + r * kSize + c] = B[r][c];
+              for (int c = 0; c < kSize; ++c) jbuf[lane * kPitch + r * kSize + c] = B[r][c];
             __syncwarp();
             double* __restrict__ dst = a.jacobian_values + base;
             if ((kCell % 2 == 0) && ((base & 1) == 0)) {
@@ -689,14 +694,14 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
                 const int row = e / kCell;
                 const int col = e - row * kCell;
                 reinterpret_cast<double2*>(dst)[it * 32 + lane] =
-                    make_double2(wbuf[row * kPitch + col], wbuf[row * kPitch + col + 1]);
+                    make_double2(jbuf[row * kPitch + col], jbuf[row * kPitch + col + 1]);
               }
             } else {
 #pragma unroll
               for (int it = 0; it < kCell; ++it) {
                 const int e = it * 32 + lane;
                 const int row = e / kCell;
-                dst[e] = wbuf[row * kPitch + (e - row * kCell)];
+                dst[e] = jbuf[row * kPitch + (e - row * kCell)];
               }
             }
             __syncwarp();
