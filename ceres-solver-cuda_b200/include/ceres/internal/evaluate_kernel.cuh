@@ -612,18 +612,25 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
             double acc = 0.0;
 #pragma unroll
             for (int r = 0; r < kRes; ++r) acc += B[r][c] * res_corrected[r];
-            g[c] = (valid && ok && active) ? acc : 0.0;
+            g[c] = acc;
           }
-          // Runs of consecutive blocks sharing this parameter block are summed in
-          // the warp first (warp-uniform test, so no divergence around shuffles).
+          // Long runs of consecutive blocks sharing this parameter block (few distinct
+          // blocks in the warp) are summed in the warp first, so one lane per run adds to
+          // memory.  Short runs (the 3-10 observations of a BAL point) go out directly:
+          // lanes of one red instruction that hit the same sector share one L2 request,
+          // which is cheaper than 5 shuffle steps per value.
           const int k_ = (valid && active) ? key[j] : -1 - lane;
           const int prev_key = __shfl_up_sync(0xffffffffu, k_, 1);
-          const bool head = (lane == 0) || (prev_key != k_);
+          bool head = (lane == 0) || (prev_key != k_);
           const unsigned heads = __ballot_sync(0xffffffffu, head);
-          if (heads != 0xffffffffu) {
+          if (__popc(heads) <= 4) {
+#pragma unroll
+            for (int c = 0; c < kSize; ++c) g[c] = (valid && ok && active) ? g[c] : 0.0;
             const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
             const int run_end = above ? __ffs(above) - 1 : 32;
             WarpSegmentedSum<kSize>(run_end, g, lane);
+          } else {
+            head = true;  // every lane adds its own contribution
           }
           const bool emit = head && valid && ok && active;
           const unsigned emit_mask = __ballot_sync(0xffffffffu, emit);

@@ -247,8 +247,11 @@ CERES_B200_JET_FN Jet<T, N> operator/(const Jet<T, N>& f, const Jet<T, N>& g) {
 }
 template <typename T, int N>
 CERES_B200_JET_FN Jet<T, N> operator/(T s, const Jet<T, N>& g) {
-  const T c = -s / (g.a * g.a);
-  return jet_internal::Chain(g, s / g.a, c);
+  // s / g.a and -s / g.a^2 from one reciprocal (the reference divides twice; the
+  // results agree to an ulp or two).
+  const T g_inv = T(1.0) / g.a;
+  const T q = s * g_inv;
+  return jet_internal::Chain(g, q, -q * g_inv);
 }
 template <typename T, int N>
 CERES_B200_JET_FN Jet<T, N> operator/(const Jet<T, N>& f, T s) {
