@@ -35,6 +35,7 @@ AFFINE_3_4_34 = 12
 AFFINE_FAIL = 13        # <20, 3, 2, 3, 4>(succeeds=false)
 PARAMETER_SENSITIVE = 14
 POSE_GRAPH_3D = 15      # <6, 3, 4, 3, 4> examples/slam/pose_graph_3d/pose_graph_3d_error_term.h
+JET_BATTERY = 16        # <40, 2> every Jet operation (jet_cuda_test.cu.cc)
 
 # (num_residuals, block sizes, functor data length)
 COST_TYPES = {
@@ -54,6 +55,7 @@ COST_TYPES = {
     AFFINE_FAIL: (3, (2, 3, 4), 0),
     PARAMETER_SENSITIVE: (2, (2,), 0),
     POSE_GRAPH_3D: (6, (3, 4, 3, 4), 43),
+    JET_BATTERY: (40, (2,), 0),
 }
 
 # ---- loss kinds (include/ceres/loss_function_cuda.h:62-149)

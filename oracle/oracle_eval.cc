@@ -144,6 +144,7 @@ static const std::vector<CostTypeInfo>& CostTypes() {
       /* 13 */ MakeType<AffineTestCost<20, 3, false, 2, 3, 4>, 3, 2, 3, 4>(0),
       /* 14 */ MakeType<ParameterSensitiveCost, 2, 2>(0),
       /* 15 */ MakeType<PoseGraph3dErrorTerm, 6, 3, 4, 3, 4>(43),
+      /* 16 */ MakeType<JetBatteryCost, 40, 2>(0),
   };
   return types;
 }
@@ -1210,6 +1211,37 @@ void oracle_manifold_plus(int kind, int param, int ambient, const double* x,
 
 void oracle_angle_axis_rotate_point(const double* aa, const double* pt, double* out) {
   oracle::AngleAxisRotatePoint(aa, pt, out);
+}
+
+void oracle_quaternion_to_angle_axis_jet(const double* q, double* value, double* jac) {
+  using J = oracle::Jet<4>;
+  J x[4], out[3];
+  for (int i = 0; i < 4; ++i) x[i] = J(q[i], i);
+  oracle::QuaternionToAngleAxis(x, out);
+  for (int r = 0; r < 3; ++r) {
+    value[r] = out[r].a;
+    for (int c = 0; c < 4; ++c) jac[r * 4 + c] = out[r].v[c];
+  }
+}
+
+// Same battery, in the same order, as oracle/ref_arith.cc ref_jet_battery.
+int oracle_jet_battery(const double* in, double* out) {
+  using namespace oracle;
+  using J = oracle::Jet<2>;
+  const J x(in[0], 0), y(in[1], 1);
+  int k = 0;
+  auto put = [&](const J& j) { out[k++] = j.a; out[k++] = j.v[0]; out[k++] = j.v[1]; };
+  put(x + y); put(x - y); put(x * y); put(x / y); put(-x); put(x + 1.5); put(1.5 - x);
+  put(x * 1.5); put(1.5 / x); put(x / 1.5);
+  put(sqrt(x)); put(exp(x)); put(log(x)); put(sin(x));
+  put(cos(x)); put(tan(x)); put(asin(x / 3.0)); put(acos(x / 3.0));
+  put(atan(x)); put(sinh(x)); put(cosh(x)); put(tanh(x));
+  put(abs(-x)); put(atan2(y, x)); put(pow(x, 1.7)); put(pow(x, y));
+  put(hypot(x, y)); put(hypot(x, y, x * y)); put(cbrt(x));
+  put(exp2(x)); put(log2(x)); put(log10(x)); put(log1p(x));
+  put(expm1(x)); put(fmax(x, y)); put(fmin(x, y)); put(erf(x));
+  put(erfc(x)); put(copysign(x, -y)); put(fma(x, y, x));
+  return k / 3;
 }
 
 }  // extern "C"

@@ -349,6 +349,27 @@ struct PoseGraph3dErrorTerm {
   }
 };
 
+// The 40 Jet operations of oracle/ref_arith.cc ref_jet_battery as a cost functor
+// <40, 2>: residual k = op_k(x, y) (inputs of internal/ceres/jet_cuda_test.cu.cc).
+struct JetBatteryCost {
+  template <typename T>
+  bool operator()(const double*, const T* const p, T* r) const {
+    const T& x = p[0];
+    const T& y = p[1];
+    int k = 0;
+    r[k++] = x + y; r[k++] = x - y; r[k++] = x * y; r[k++] = x / y; r[k++] = -x;
+    r[k++] = x + 1.5; r[k++] = 1.5 - x; r[k++] = x * 1.5; r[k++] = 1.5 / x; r[k++] = x / 1.5;
+    r[k++] = sqrt(x); r[k++] = exp(x); r[k++] = log(x); r[k++] = sin(x); r[k++] = cos(x);
+    r[k++] = tan(x); r[k++] = asin(x / 3.0); r[k++] = acos(x / 3.0); r[k++] = atan(x);
+    r[k++] = sinh(x); r[k++] = cosh(x); r[k++] = tanh(x); r[k++] = abs(-x); r[k++] = atan2(y, x);
+    r[k++] = pow(x, 1.7); r[k++] = pow(x, y); r[k++] = hypot(x, y); r[k++] = hypot(x, y, x * y);
+    r[k++] = cbrt(x); r[k++] = exp2(x); r[k++] = log2(x); r[k++] = log10(x); r[k++] = log1p(x);
+    r[k++] = expm1(x); r[k++] = fmax(x, y); r[k++] = fmin(x, y); r[k++] = erf(x); r[k++] = erfc(x);
+    r[k++] = copysign(x, -y); r[k++] = fma(x, y, x);
+    return true;
+  }
+};
+
 }  // namespace oracle
 
 #endif  // ORACLE_FUNCTORS_H_

@@ -233,6 +233,99 @@ template <int N> inline Jet<N> pow(const Jet<N>& f, double g) {
   const double tmp = g * std::pow(f.a, g - 1.0);
   return scaled_(f, std::pow(f.a, g), tmp);
 }
+
+// jet.h:556-576 copysign
+template <int N> inline Jet<N> copysign(const Jet<N>& f, const Jet<N> g) {
+  const double d = std::fpclassify(g.a) == FP_ZERO ? std::numeric_limits<double>::infinity() : 0.0;
+  const double sa = std::copysign(1.0, f.a);
+  const double sb = std::copysign(1.0, g.a);
+  Jet<N> h; h.a = std::copysign(f.a, g.a);
+  for (int i = 0; i < N; ++i) h.v[i] = sa * sb * f.v[i] + std::abs(f.a) * d * g.v[i];
+  return h;
+}
+// jet.h:586-598 log10 / log1p, :608-613 expm1
+template <int N> inline Jet<N> log10(const Jet<N>& f) {
+  const double a_inverse = 1.0 / (f.a * std::log(10.0));
+  Jet<N> h; h.a = std::log10(f.a);
+  for (int i = 0; i < N; ++i) h.v[i] = f.v[i] * a_inverse;
+  return h;
+}
+template <int N> inline Jet<N> log1p(const Jet<N>& f) {
+  const double a_inverse = 1.0 / (1.0 + f.a);
+  Jet<N> h; h.a = std::log1p(f.a);
+  for (int i = 0; i < N; ++i) h.v[i] = f.v[i] * a_inverse;
+  return h;
+}
+template <int N> inline Jet<N> expm1(const Jet<N>& f) {
+  const double tmp = std::expm1(f.a);
+  return scaled_(f, tmp, tmp + 1.0);
+}
+// jet.h:665-682 sinh / cosh / tanh
+template <int N> inline Jet<N> sinh(const Jet<N>& f) { return scaled_(f, std::sinh(f.a), std::cosh(f.a)); }
+template <int N> inline Jet<N> cosh(const Jet<N>& f) { return scaled_(f, std::cosh(f.a), std::sinh(f.a)); }
+template <int N> inline Jet<N> tanh(const Jet<N>& f) {
+  const double t = std::tanh(f.a);
+  return scaled_(f, t, 1.0 - t * t);
+}
+// jet.h:705-724 cbrt / exp2 / log2
+template <int N> inline Jet<N> cbrt(const Jet<N>& f) {
+  const double derivative = 1.0 / (3.0 * std::cbrt(f.a * f.a));
+  Jet<N> h; h.a = std::cbrt(f.a);
+  for (int i = 0; i < N; ++i) h.v[i] = f.v[i] * derivative;
+  return h;
+}
+template <int N> inline Jet<N> exp2(const Jet<N>& f) {
+  const double tmp = std::exp2(f.a);
+  const double derivative = tmp * std::log(2.0);
+  Jet<N> h; h.a = tmp;
+  for (int i = 0; i < N; ++i) h.v[i] = f.v[i] * derivative;
+  return h;
+}
+template <int N> inline Jet<N> log2(const Jet<N>& f) {
+  const double derivative = 1.0 / (f.a * std::log(2.0));
+  Jet<N> h; h.a = std::log2(f.a);
+  for (int i = 0; i < N; ++i) h.v[i] = f.v[i] * derivative;
+  return h;
+}
+// jet.h:763-772 fma
+template <int N> inline Jet<N> fma(const Jet<N>& x, const Jet<N>& y, const Jet<N>& z) {
+  Jet<N> h; h.a = std::fma(x.a, y.a, z.a);
+  for (int i = 0; i < N; ++i) h.v[i] = y.a * x.v[i] + x.a * y.v[i] + z.v[i];
+  return h;
+}
+// jet.h:806-846 fmax / fmin (Jet average on equality)
+template <int N> inline Jet<N> fmax(const Jet<N>& x, const Jet<N>& y) {
+  if (std::isnan(x.a) || std::isnan(y.a) || std::islessgreater(x.a, y.a))
+    return (std::isnan(x.a) || std::isless(x.a, y.a)) ? y : x;
+  return (x + y) * 0.5;
+}
+template <int N> inline Jet<N> fmin(const Jet<N>& x, const Jet<N>& y) {
+  if (std::isnan(x.a) || std::isnan(y.a) || std::islessgreater(x.a, y.a))
+    return (std::isnan(x.a) || std::isgreater(x.a, y.a)) ? y : x;
+  return (x + y) * 0.5;
+}
+// jet.h:863-885 erf / erfc
+template <int N> inline Jet<N> erf(const Jet<N>& x) {
+  const double c = std::exp(-x.a * x.a) * (1.0 / std::sqrt(std::atan(1.0)));
+  Jet<N> h; h.a = std::erf(x.a);
+  for (int i = 0; i < N; ++i) h.v[i] = x.v[i] * std::exp(-x.a * x.a) * (1.0 / std::sqrt(std::atan(1.0)));
+  (void)c;
+  return h;
+}
+template <int N> inline Jet<N> erfc(const Jet<N>& x) {
+  Jet<N> h; h.a = std::erfc(x.a);
+  for (int i = 0; i < N; ++i) h.v[i] = -x.v[i] * std::exp(-x.a * x.a) * (1.0 / std::sqrt(std::atan(1.0)));
+  return h;
+}
+// jet.h:1262-1290 pow(Jet, Jet), generic branch (f > 0)
+template <int N> inline Jet<N> pow(const Jet<N>& f, const Jet<N>& g) {
+  const double tmp1 = std::pow(f.a, g.a);
+  const double tmp2 = g.a * std::pow(f.a, g.a - 1.0);
+  const double tmp3 = tmp1 * std::log(f.a);
+  Jet<N> h; h.a = tmp1;
+  for (int i = 0; i < N; ++i) h.v[i] = tmp2 * f.v[i] + tmp3 * g.v[i];
+  return h;
+}
 // jet.h:1096-1130: classification acts on the scalar part.
 template <int N> inline int fpclassify(const Jet<N>& f) { return std::fpclassify(f.a); }
 inline int fpclassify(double x) { return std::fpclassify(x); }
@@ -240,7 +333,10 @@ inline int fpclassify(double x) { return std::fpclassify(x); }
 // Scalar overloads so functors templated on T compile with T = double.
 using std::abs; using std::sqrt; using std::sin; using std::cos; using std::atan2;
 using std::log; using std::exp; using std::acos; using std::asin; using std::tan;
-using std::atan; using std::pow;
+using std::atan; using std::pow; using std::sinh; using std::cosh; using std::tanh;
+using std::cbrt; using std::exp2; using std::log2; using std::log10; using std::log1p;
+using std::expm1; using std::fmax; using std::fmin; using std::erf; using std::erfc;
+using std::copysign; using std::fma;
 inline double hypot(double x, double y) { return std::hypot(x, y); }
 inline double hypot(double x, double y, double z) { return std::hypot(x, y, z); }
 

@@ -233,6 +233,18 @@ def manifold_plus(kind, param, x, delta):
     return out
 
 
+def quaternion_to_angle_axis_jet(q):
+    v, j = np.zeros(3), np.zeros(12)
+    lib().oracle_quaternion_to_angle_axis_jet(_p(np.ascontiguousarray(q, float)), _p(v), _p(j))
+    return v, j
+
+
+def jet_battery(xy):
+    buf = np.zeros(3 * 64)
+    k = lib().oracle_jet_battery(_p(np.ascontiguousarray(xy, float)), _p(buf))
+    return buf[:3 * k]
+
+
 def angle_axis_rotate_point(aa, pt):
     out = np.zeros(3)
     lib().oracle_angle_axis_rotate_point(_p(np.ascontiguousarray(aa, float)),

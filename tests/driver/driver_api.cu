@@ -34,8 +34,9 @@ ceres::Manifold* MakeManifold(int kind, int param, int size) {
   return nullptr;
 }
 
-const int kTypeBlocks[16] = {2, 2, 2, 1, 2, 2, 10, 1, 3, 3, 2, 2, 2, 3, 1, 4};
-const int kTypeFdata[16] = {2, 2, 2, 3, 7, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 43};
+const int kNumTypes = 17;
+const int kTypeBlocks[kNumTypes] = {2, 2, 2, 1, 2, 2, 10, 1, 3, 3, 2, 2, 2, 3, 1, 4, 1};
+const int kTypeFdata[kNumTypes] = {2, 2, 2, 3, 7, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 43, 0};
 }  // namespace
 
 extern "C" {
@@ -63,7 +64,7 @@ void* drv_create(int num_pb, const int* pb_size, const double* pb_values,
   int i = 0;
   while (i < num_rb) {
     const int type = rb_type[i];
-    if (type < 0 || type >= 16) { dp->error = "unknown cost type"; return dp; }
+    if (type < 0 || type >= kNumTypes) { dp->error = "unknown cost type"; return dp; }
     int j = i + 1;
     while (j < num_rb && rb_type[j] == type && rb_loss_kind[j] == rb_loss_kind[i] &&
            rb_loss_a[j] == rb_loss_a[i] && rb_loss_b[j] == rb_loss_b[i])

@@ -122,6 +122,31 @@ struct ParameterSensitiveCost {
   char unused = 0;
 };
 
+// Every Jet operation, in the order of oracle/ref_arith.cc ref_jet_battery  <40, 2>
+// (the operations internal/ceres/jet_cuda_test.cu.cc:123-1056 exercises on the device).
+struct JetBatteryCost {
+  template <typename T>
+  HOST_DEVICE bool operator()(const T* const p, T* r) const {
+    // Qualified calls: for T = double they pick the HOST_DEVICE overloads of ceres/jet.h
+    // (the global 3-argument hypot is host-only), for T = Jet the Jet overloads.
+    namespace c = ceres;
+    const T& x = p[0];
+    const T& y = p[1];
+    r[0] = x + y; r[1] = x - y; r[2] = x * y; r[3] = x / y; r[4] = -x;
+    r[5] = x + 1.5; r[6] = 1.5 - x; r[7] = x * 1.5; r[8] = 1.5 / x; r[9] = x / 1.5;
+    r[10] = c::sqrt(x); r[11] = c::exp(x); r[12] = c::log(x); r[13] = c::sin(x);
+    r[14] = c::cos(x); r[15] = c::tan(x); r[16] = c::asin(x / 3.0); r[17] = c::acos(x / 3.0);
+    r[18] = c::atan(x); r[19] = c::sinh(x); r[20] = c::cosh(x); r[21] = c::tanh(x);
+    r[22] = c::abs(-x); r[23] = c::atan2(y, x); r[24] = c::pow(x, 1.7); r[25] = c::pow(x, y);
+    r[26] = c::hypot(x, y); r[27] = c::hypot(x, y, x * y); r[28] = c::cbrt(x);
+    r[29] = c::exp2(x); r[30] = c::log2(x); r[31] = c::log10(x); r[32] = c::log1p(x);
+    r[33] = c::expm1(x); r[34] = c::fmax(x, y); r[35] = c::fmin(x, y); r[36] = c::erf(x);
+    r[37] = c::erfc(x); r[38] = c::copysign(x, -y); r[39] = c::fma(x, y, x);
+    return true;
+  }
+  char unused = 0;
+};
+
 }  // namespace test_functors
 
 #endif  // TESTS_DRIVER_TEST_FUNCTORS_H_

@@ -290,3 +290,56 @@ def test_device_resident_evaluation_matches():
     assert ok and ok2 and c2 == c
     t = cp.timing()
     assert t["launches"] >= 2 and t["kernel_ms"] > 0
+
+
+# ---- the CUDA path against the REFERENCE's own arithmetic (tests/golden/reference_arith.npz,
+# produced from /root/reference headers by tests/golden/make_golden.py)
+import os as _os
+_G = np.load(_os.path.join(_os.path.dirname(__file__), "golden", "reference_arith.npz"))
+
+
+def _golden_problem(cost_type, cams, pts, obs):
+    b = P.ProblemBuilder()
+    for cam, pt, ob in zip(cams, pts, obs):
+        c = b.add_parameter_block(cam)
+        p = b.add_parameter_block(pt)
+        b.add_residual_block(cost_type, [c, p], ob)
+    return b.build()
+
+
+@pytest.mark.parametrize("name,cost_type,csize", [("snavely", P.SNAVELY, 9), ("quat", P.SNAVELY_QUAT, 10)])
+def test_golden_reprojection_errors(name, cost_type, csize):
+    cams = _G["snavely_cam"] if name == "snavely" else _G["quat_cam"]
+    res_ref = _G[name + "_res"]
+    jc_ref, jp_ref = _G[name + "_jcam"], _G[name + "_jpt"]
+    spec = _golden_problem(cost_type, cams, _G["snavely_pt"], _G["snavely_obs"])
+    cp = B.CudaProblem(spec, reduce=False)
+    ok, c, r, g, j = cp.evaluate()
+    assert ok
+    n = cams.shape[0]
+    r = r.reshape(n, 2)
+    # BlockSparseMatrix, num_eliminate_blocks = 0: cells in residual-block order,
+    # camera cell then point cell
+    cell = j[:n * 2 * (csize + 3)].reshape(n, 2 * (csize + 3))
+    jc, jp = cell[:, :2 * csize], cell[:, 2 * csize:]
+    for i in range(n):
+        scale_r = np.max(np.abs(_G["snavely_obs"][i])) + np.max(np.abs(res_ref[i]))
+        assert np.max(np.abs(r[i] - res_ref[i])) <= 1e-12 * scale_r
+        assert np.max(np.abs(jc[i] - jc_ref[i])) <= 1e-12 * np.max(np.abs(jc_ref[i]))
+        assert np.max(np.abs(jp[i] - jp_ref[i])) <= 1e-12 * np.max(np.abs(jp_ref[i]))
+
+
+def test_golden_jet_operations_on_device():
+    """Every Jet operation evaluated by the device Jet (ceres/jet.h of this repo) against
+    the reference's jet.h; tolerance 1e-13 as in internal/ceres/jet_cuda_test.cu.cc:72-98."""
+    for xy, want in zip(_G["jet_xy"], _G["jet_battery"]):
+        b = P.ProblemBuilder()
+        x = b.add_parameter_block(xy)
+        b.add_residual_block(P.JET_BATTERY, [x])
+        cp = B.CudaProblem(b.build(), reduce=False)
+        ok, c, r, g, j = cp.evaluate()
+        assert ok
+        want = want.reshape(40, 3)
+        J = cp.dense_jacobian()
+        assert np.allclose(r, want[:, 0], rtol=1e-13, atol=1e-300)
+        assert np.allclose(J, want[:, 1:], rtol=1e-13, atol=1e-15)
