@@ -145,6 +145,7 @@ struct cb200_engine {
   cudaEvent_t ev[5] = {};
   std::string error;
   bool finalized = false;
+  bool planning = false;  // CB200_PLANNING_ONLY: no device, structure only
 
   // parameter blocks
   int32_t num_active = 0, num_constant = 0, num_parameters = 0, num_effective = 0;
@@ -200,6 +201,15 @@ const char* cb200_version(void) { return "ceres_b200 0.1 (sm_100a)"; }
 int cb200_engine_create(int device, cb200_engine** out) {
   if (!out) return CB200_ERROR_INVALID_ARGUMENT;
   *out = nullptr;
+  if (device == CB200_PLANNING_ONLY) {
+    // Structure planning without a device: finalize computes this rank's residual
+    // block range and Jacobian segments (cb200_engine_shard_info); evaluate fails.
+    auto* planner = new cb200_engine;
+    planner->device = device;
+    planner->planning = true;
+    *out = planner;
+    return CB200_OK;
+  }
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
     return CB200_ERROR_CUDA;  // fail loudly: there is no CPU fallback
@@ -219,6 +229,11 @@ int cb200_engine_create(int device, cb200_engine** out) {
 
 void cb200_engine_destroy(cb200_engine* e) {
   if (!e) return;
+  if (e->planning) {
+    for (auto* t : e->types) delete t;
+    delete e;
+    return;
+  }
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->comm) {
@@ -317,7 +332,7 @@ int cb200_engine_set_shard(cb200_engine* e, int32_t rank, int32_t world_size) {
 
 int cb200_engine_finalize(cb200_engine* e) {
   if (!e || e->finalized) return CB200_ERROR_INVALID_ARGUMENT;
-  CB200_CUDA(e, cudaSetDevice(e->device));
+  if (!e->planning) CB200_CUDA(e, cudaSetDevice(e->device));
   const int64_t nrb = e->num_rb;
   e->rb_begin = static_cast<int32_t>(nrb * e->rank / e->world);
   e->rb_end = static_cast<int32_t>(nrb * (e->rank + 1) / e->world);
@@ -457,6 +472,7 @@ int cb200_engine_finalize(cb200_engine* e) {
         ++a;
       }
     }
+    if (e->planning) continue;
     CB200_CUDA(e, t->d_pb.Upload(pb, e->stream));
     CB200_CUDA(e, t->d_soff.Upload(soff, e->stream));
     CB200_CUDA(e, t->d_doff.Upload(doff, e->stream));
@@ -473,6 +489,10 @@ int cb200_engine_finalize(cb200_engine* e) {
     std::vector<int32_t>().swap(t->loss_index);
   }
 
+  if (e->planning) {
+    e->finalized = true;
+    return CB200_OK;
+  }
   CB200_CUDA(e, e->d_pb_table.Upload(table, e->stream));
   CB200_CUDA(e, e->d_state.Resize(static_cast<size_t>(e->num_parameters) +
                                   e->num_constant_parameters + 1));
@@ -502,6 +522,7 @@ int cb200_nccl_unique_id(void* out) {
 int cb200_engine_comm_init(cb200_engine* e, const void* unique_id, int32_t rank,
                            int32_t world_size) {
   if (!e || !unique_id) return CB200_ERROR_INVALID_ARGUMENT;
+  if (e->planning) return e->Fail(CB200_ERROR_CUDA, "planning-only engine");
   NcclApi* n = GetNccl();
   if (!n) return e->Fail(CB200_ERROR_NCCL, "libnccl.so.2 not found");
   CB200_CUDA(e, cudaSetDevice(e->device));
@@ -591,6 +612,7 @@ int cb200_engine_evaluate(cb200_engine* e, const double* state, const double* pl
                           double* jacobian_values) {
   if (!e) return CB200_ERROR_INVALID_ARGUMENT;
   if (!e->finalized) return e->Fail(CB200_ERROR_NOT_FINALIZED, "evaluate before finalize");
+  if (e->planning) return e->Fail(CB200_ERROR_CUDA, "planning-only engine: no device, no CPU fallback");
   if (!state || !cost) return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "state and cost are required");
   if (e->plus_pool > 0 && !plus_jacobians)
     return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "plus_jacobians required");
@@ -638,6 +660,7 @@ int cb200_engine_evaluate_device(cb200_engine* e, const double* state_device,
                                  double* cost) {
   if (!e) return CB200_ERROR_INVALID_ARGUMENT;
   if (!e->finalized) return e->Fail(CB200_ERROR_NOT_FINALIZED, "evaluate before finalize");
+  if (e->planning) return e->Fail(CB200_ERROR_CUDA, "planning-only engine: no device, no CPU fallback");
   if (!cost) return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "cost is required");
   CB200_CUDA(e, cudaSetDevice(e->device));
   cudaStream_t s = e->stream;
@@ -665,7 +688,7 @@ int cb200_engine_evaluate_device(cb200_engine* e, const double* state_device,
 }
 
 void* cb200_engine_device_ptr(cb200_engine* e, int which) {
-  if (!e || !e->finalized) return nullptr;
+  if (!e || !e->finalized || e->planning) return nullptr;
   switch (which) {
     case 0: return e->d_residuals.ptr;
     case 1: return e->d_gradcost.ptr;

@@ -603,7 +603,8 @@ class ProgramEvaluatorCUDA final : public Evaluator {
     int rc = cb200_engine_create(options_.device, &engine_);
     if (rc != CB200_OK) {
       *error = "cb200_engine_create failed: no usable CUDA device " +
-               std::to_string(options_.device) + " (there is no CPU fallback)";
+               std::to_string(options_.device) +
+               " (there is no CPU fallback; device -1 only plans the sharding)";
       engine_ = nullptr;
       return false;
     }
@@ -717,6 +718,10 @@ class ProgramEvaluatorCUDA final : public Evaluator {
   bool Evaluate(const EvaluateOptions& evaluate_options, const double* state, double* cost,
                 double* residuals, double* gradient, SparseMatrix* jacobian) override {
     const auto start = std::chrono::steady_clock::now();
+    if (options_.device < 0) {
+      std::fprintf(stderr, "Evaluate on a planning-only evaluator: no device, no CPU fallback\n");
+      return false;
+    }
     // ParameterBlock::SetState -> UpdatePlusJacobian (parameter_block.h:91-99,312-338):
     // the plus-Jacobians of the blocks with a manifold, at the new state.
     if (jacobian != nullptr || gradient != nullptr) {

@@ -113,6 +113,7 @@ typedef struct cb200_residual_type {
 
 /* ---- lifetime.  Replaces ContextImpl::InitCuda + RegisteredCUDAEvaluators ctor
  * (internal/ceres/context_impl.cc:112-174, include/ceres/internal/registered_cuda_evaluators.h:64-70). */
+#define CB200_PLANNING_ONLY (-1) /* device argument: plan the sharding on a host without a GPU */
 int cb200_engine_create(int device, cb200_engine** engine);
 void cb200_engine_destroy(cb200_engine* engine);
 const char* cb200_engine_last_error(const cb200_engine* engine);
