@@ -323,6 +323,17 @@ def run_ours(args):
 
 
 if __name__ == "__main__":
+    # Libraries (NCCL's version banner) print to fd 1; keep stdout for the one JSON line.
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
+    _real_print = print
+
+    def print(*args, **kw):  # noqa: A001
+        if kw.get("flush") and args and isinstance(args[0], str) and args[0].startswith("{"):
+            os.write(_json_fd, (args[0] + "\n").encode())
+        else:
+            _real_print(*args, **kw)
+
     a = parse()
     if a.impl == "reference":
         run_reference(a)
