@@ -303,7 +303,11 @@ def run_ours(args):
         "gpu_launches": launches_per_step * args.steps * 2,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None,
+                     "frac": achieved / peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the
+                     # ncu --set full capture in profiles/r1_v6_ncu_summary.txt (L, 1 GPU)
+                     "traffic": 7.592e9 if (args.workload == "L" and args.scale == 1.0
+                                            and world == 1) else None,
                      "kernel": "EvaluateKernel<true, SnavelyReprojectionError, HuberLossCUDA, 2, 9, 3>",
                      "algorithmic_bytes_per_block": ALG_BYTES_PER_RB,
                      "blocks_per_launch": local_rb, "launch_ms": ker_ms, "peak_source": peak_src,

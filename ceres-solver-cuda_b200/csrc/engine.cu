@@ -435,7 +435,9 @@ int cb200_engine_finalize(cb200_engine* e) {
     const int32_t n = static_cast<int32_t>(idx.size());
     t->n_local = n;
     const int tpb = t->desc.threads_per_block > 0 ? t->desc.threads_per_block : 128;
-    t->grid = (n + tpb - 1) / tpb;
+    // Cost partials reserved for the launch: the thunk's (persistent) grid is clamped to
+    // this, so the fixed-order reduction reads at most 1024 values per type.
+    t->grid = std::min((n + tpb - 1) / tpb, 1024);
     t->cost_partial_offset = e->total_cost_partials;
     e->total_cost_partials += t->grid;
     if (n == 0) continue;
