@@ -339,16 +339,18 @@ int cb200_engine_finalize(cb200_engine* e) {
   e->res_begin = e->rb_begin < nrb ? e->residual_layout[e->rb_begin] : e->num_residuals;
   e->res_end = e->rb_end < nrb ? e->residual_layout[e->rb_end] : e->num_residuals;
 
-  // Device parameter-block table (int4 records).
+  // Device parameter-block table (8 ints per block, read as two int4).
   const int npb = e->num_active + e->num_constant;
-  std::vector<int32_t> table(static_cast<size_t>(npb) * 4);
+  std::vector<int32_t> table(static_cast<size_t>(npb) * 8, 0);
   for (int i = 0; i < npb; ++i) {
     const cb200_parameter_block& b = e->blocks[i];
     const bool constant = i >= e->num_active;
-    table[4 * i + 0] = constant ? e->num_parameters + b.state_offset : b.state_offset;
-    table[4 * i + 1] = constant ? -1 : b.delta_offset;
-    table[4 * i + 2] = b.tangent_size;
-    table[4 * i + 3] = constant ? -1 : b.plus_jacobian_offset;
+    table[8 * i + 0] = constant ? e->num_parameters + b.state_offset : b.state_offset;
+    table[8 * i + 1] = constant ? -1 : b.delta_offset;
+    table[8 * i + 2] = b.tangent_size;
+    table[8 * i + 3] = constant ? CB200_MANIFOLD_NONE : b.manifold_kind;
+    table[8 * i + 4] = b.manifold_param;
+    table[8 * i + 5] = constant ? -1 : b.plus_jacobian_offset;
   }
 
   // Pass 1: per type, pick this rank's blocks and find what part of the values
@@ -460,9 +462,9 @@ int cb200_engine_finalize(cb200_engine* e) {
       for (int j = 0; j < nb; ++j) {
         const int32_t id = t->pb_ids[static_cast<size_t>(k) * nb + j];
         pb[static_cast<size_t>(j) * n + i] = id;
-        soff[static_cast<size_t>(j) * n + i] = table[4 * id + 0];
-        doff[static_cast<size_t>(j) * n + i] = table[4 * id + 1];
-        if (table[4 * id + 1] < 0 || table[4 * id + 3] >= 0 ||
+        soff[static_cast<size_t>(j) * n + i] = table[8 * id + 0];
+        doff[static_cast<size_t>(j) * n + i] = table[8 * id + 1];
+        if (table[8 * id + 1] < 0 || table[8 * id + 3] != CB200_MANIFOLD_NONE ||
             e->blocks[id].tangent_size != e->blocks[id].size)
           t->plain = false;
         if (id >= e->num_active) continue;

@@ -623,10 +623,20 @@ class ProgramEvaluatorCUDA final : public Evaluator {
       b.state_offset = pb->state_offset;
       b.delta_offset = pb->delta_offset;
       b.plus_jacobian_offset = -1;
+      b.manifold_kind = CB200_MANIFOLD_NONE;
+      b.manifold_param = 0;
       if (pb->manifold) {
-        b.plus_jacobian_offset = plus_pool;
-        plus_pool += pb->size * b.tangent_size;
-        manifold_blocks_.push_back(pb);
+        int kind = 0, param = 0;
+        if (pb->manifold->DeviceDescription(&kind, &param)) {
+          // The kernel applies this manifold itself: nothing to compute or copy per call.
+          b.manifold_kind = kind;
+          b.manifold_param = param;
+        } else {
+          b.manifold_kind = CB200_MANIFOLD_GENERIC;
+          b.plus_jacobian_offset = plus_pool;
+          plus_pool += pb->size * b.tangent_size;
+          manifold_blocks_.push_back(pb);
+        }
       }
       engine_id[pb->id] = static_cast<int32_t>(blocks.size());
       blocks.push_back(b);
@@ -638,6 +648,8 @@ class ProgramEvaluatorCUDA final : public Evaluator {
       b.state_offset = pb->state_offset;
       b.delta_offset = -1;
       b.plus_jacobian_offset = -1;
+      b.manifold_kind = CB200_MANIFOLD_NONE;
+      b.manifold_param = 0;
       engine_id[pb->id] = static_cast<int32_t>(blocks.size());
       blocks.push_back(b);
     }

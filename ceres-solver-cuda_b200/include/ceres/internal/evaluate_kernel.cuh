@@ -104,12 +104,11 @@ __device__ __forceinline__ void RedAdd(double* address, double value) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(address), "d"(value) : "memory");
 }
 
-// Everything that happens to one parameter block's Jacobian after autodiff.
-// B is the kRes x kSize ambient block; on exit its first `tangent` columns hold
-// the final (manifold-projected, loss-corrected) block.
+// Jacobian block helpers.  B is the kRes x kSize ambient block.
 template <int kRes, int kSize>
 struct BlockEpilogue {
-  // B <- B * P, P row-major kSize x tangent (cuda_evaluator_kernel.h:355-371).
+  // B <- B * P, P row-major kSize x tangent (cuda_evaluator_kernel.h:355-371); used for
+  // manifolds the device does not know (CB200_MANIFOLD_GENERIC).
   static __device__ __forceinline__ void MultiplyPlusJacobian(double (&B)[kRes][kSize],
                                                               const double* __restrict__ P,
                                                               int tangent) {
@@ -139,7 +138,7 @@ struct BlockEpilogue {
   }
 
   // corrector.h:174-213 CorrectJacobian, column by column.
-  static __device__ __forceinline__ void Correct(double (&B)[kRes][kSize], int tangent,
+  static __device__ __forceinline__ void Correct(double (&B)[kRes][kSize],
                                                  const double (&res)[kRes], double sqrt_rho1,
                                                  double alpha_sq_norm) {
     if (alpha_sq_norm == 0.0) {
@@ -255,6 +254,48 @@ constexpr int kVariantCost = 0;     // cost / residuals only: plain doubles, no 
 constexpr int kVariantPlain = 1;    // Jets; no manifold and no constant block in this type
 constexpr int kVariantGeneric = 2;  // Jets; per-block manifold projection / constant blocks
 
+// ---- derivative passes.  Wide problems (pose graphs: 14 derivative lanes x 6 residuals
+// = 90 live doubles of output alone) are differentiated in several passes, each seeding
+// only some parameter blocks (Jet width = their total size, all other blocks constants):
+// the scalar part is recomputed per pass but registers per thread drop by the pass count,
+// which removes the local-memory spills that otherwise dominate.  Small problems use one pass.
+template <int kRes, int... Ns>
+struct PassPlan {
+  using Dims = BlockDims<Ns...>;
+  static constexpr int kNB = Dims::kNumBlocks;
+  static constexpr bool kSinglePass = kRes * Dims::kNumParameters <= 40;
+  static constexpr int kMaxWidth = Dims::MaxSize() > 8 ? Dims::MaxSize() : 8;
+  // pass index of block j: greedy grouping of consecutive blocks up to kMaxWidth lanes
+  __host__ __device__ static constexpr int PassOf(int j) {
+    if (kSinglePass) return 0;
+    int pass = 0, width = 0;
+    for (int i = 0; i <= j; ++i) {
+      if (width + Dims::Size(i) > kMaxWidth && width > 0) { ++pass; width = 0; }
+      width += Dims::Size(i);
+    }
+    return pass;
+  }
+  static constexpr int kNumPasses = PassOf(kNB - 1) + 1;
+  __host__ __device__ static constexpr int FirstBlock(int pass) {
+    for (int j = 0; j < kNB; ++j) if (PassOf(j) == pass) return j;
+    return kNB;
+  }
+  __host__ __device__ static constexpr int EndBlock(int pass) {
+    int e = 0;
+    for (int j = 0; j < kNB; ++j) if (PassOf(j) == pass) e = j + 1;
+    return e;
+  }
+  __host__ __device__ static constexpr int Width(int pass) {
+    int w = 0;
+    for (int j = 0; j < kNB; ++j) if (PassOf(j) == pass) w += Dims::Size(j);
+    return w;
+  }
+  // derivative lane of parameter i of block j inside its pass
+  __host__ __device__ static constexpr int Lane(int j, int i) {
+    return Dims::Offset(j) - Dims::Offset(FirstBlock(PassOf(j))) + i;
+  }
+};
+
 template <typename Functor, int kNumParameters, int kNumBlocks>
 struct PrefetchLayout {
   static constexpr int kParamBytes = kNumParameters * 8;
@@ -273,23 +314,30 @@ struct PrefetchLayout {
   static constexpr bool kFits = kPrefetchBytes <= 96 * 1024;
 };
 
-// Row pitch (doubles) of the per-warp output staging buffer for rows of `n` doubles:
-// odd, so that lanes writing their own row hit different banks.
 __host__ __device__ constexpr int StagePitch(int n) { return n | 1; }
 
-// One thread evaluates one residual block at a time and walks the type's blocks
-// with a grid stride (persistent CTAs: ResidentCtas() per SM).  Software pipeline per thread:
-//   iteration k:  [state offsets of block k+2 -> registers]
-//                 [cp.async parameters + functor of block k+1 -> shared, stage (k+1)&1]
-//                 [wait for stage k&1] compute block k from shared memory
-// so the two dependent global loads (offset, then the gathered parameters) of a
-// block are in flight during the ~1300 instructions of the previous block instead
-// of stalling the warp (v1 of this kernel: long-scoreboard stalls 7.5 of 15 cycles
-// per issue, FP64 pipe 22% busy; profiles/r1_v1_ncu_summary.txt).
+// Shared memory plan of a kernel instantiation.
+template <typename Functor, int kRes, int... Ns>
+struct SmemPlan {
+  using Dims = BlockDims<Ns...>;
+  using Layout = PrefetchLayout<Functor, Dims::kNumParameters, Dims::kNumBlocks>;
+  static constexpr int kPrefetchBytes = Layout::kFits ? Layout::kPrefetchBytes : 0;
+  // per warp: every argument's cells side by side (Jacobian staging) ...
+  static constexpr int kJacobianDoubles = 32 * kRes * Dims::kNumParameters;
+  // ... and one padded row per lane for the staged gradient reductions
+  static constexpr int kGradientDoubles = 32 * StagePitch(Dims::MaxSize());
+  static constexpr int kWarps = kEvaluateThreads / 32;
+  static constexpr bool kStageJacobian =
+      CB200_KERNEL_STAGE_JACOBIAN &&
+      (kPrefetchBytes + kWarps * (kJacobianDoubles + kGradientDoubles) * 8 <= 72 * 1024);
+  static constexpr int kWarpDoubles = (kStageJacobian ? kJacobianDoubles : 0) + kGradientDoubles;
+  static constexpr int kJetBytes = kPrefetchBytes + kWarps * kWarpDoubles * 8;
+  static constexpr int kCostBytes = kPrefetchBytes > 0 ? kPrefetchBytes : 16;
+};
+
 // CTAs per SM the kernel is compiled for.  Measured on B200 for the BAL functor
-// (scripts/kbench.cu): 3 CTAs x 128 threads (170 registers, 61 KB shared each) equal or
-// beat 4 (128 registers, spills) and 5; wide Jets (pose graphs: 14 lanes x 6 residuals)
-// get the full 255 registers.
+// (scripts/kbench.cu): 3 CTAs x 128 threads (168 registers, no spills, 71 KB shared each)
+// equal or beat 4 (128 registers, spills) and 5; wide problems get 2 CTAs (255 registers).
 #ifndef CB200_RESIDENT_CTAS_SMALL
 #define CB200_RESIDENT_CTAS_SMALL 3
 #endif
@@ -297,24 +345,35 @@ __host__ __device__ constexpr int ResidentCtas(int num_residuals, int num_parame
   return (num_parameters <= 13 && num_residuals <= 3) ? CB200_RESIDENT_CTAS_SMALL : 2;
 }
 
+// One thread evaluates one residual block at a time and walks the type's blocks with a
+// grid stride (persistent CTAs).  Software pipeline per thread:
+//   iteration k:  [state offsets of block k+2 -> registers]
+//                 [cp.async parameters + functor + int tables of block k+1 -> shared]
+//                 [wait for stage k&1] compute block k from shared memory
+// so the two dependent global loads (offset, then the gathered parameters) of a block are
+// in flight during the ~1500 instructions of the previous block instead of stalling the
+// warp (v1 of this kernel: long-scoreboard stalls 7.5 of 15 cycles per issue, FP64 pipe
+// 22% busy; profiles/r1_v1_ncu_summary.txt).
 template <int kVariant, typename Functor, typename Loss, int kRes, int... Ns>
 __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ... + 0)))
     EvaluateKernel(const cb200_launch_args a) {
   using Dims = BlockDims<Ns...>;
+  using Plan = PassPlan<kRes, Ns...>;
+  using Smem = SmemPlan<Functor, kRes, Ns...>;
   constexpr int kNB = Dims::kNumBlocks;
   constexpr int kNP = Dims::kNumParameters;
   constexpr bool kJets = kVariant != kVariantCost;
   constexpr bool kGeneric = kVariant == kVariantGeneric;
   using Layout = PrefetchLayout<Functor, kNP, kNB>;
   constexpr bool kPrefetch = Layout::kFits;
-  // Dynamic shared memory: [2 prefetch stages][per-warp output staging].
-  constexpr int kPrefetchBytes = kPrefetch ? Layout::kPrefetchBytes : 0;
-  constexpr int kWarpStageDoubles = kJets ? WarpStageDoubles(kRes, Dims::MaxSize(), kNP) : 0;
+  constexpr bool kStage = kJets && Smem::kStageJacobian;
 
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ double warp_cost[kEvaluateThreads / 32];
-  double* const wbuf = reinterpret_cast<double*>(smem + kPrefetchBytes) +
-                       (threadIdx.x >> 5) * kWarpStageDoubles;
+  double* const wbuf = reinterpret_cast<double*>(smem + Smem::kPrefetchBytes) +
+                       (threadIdx.x >> 5) * Smem::kWarpDoubles;
+  double* const jbuf = wbuf;                                              // Jacobian staging
+  double* const gbuf = wbuf + (kStage ? Smem::kJacobianDoubles : 0);      // gradient staging
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -377,8 +436,8 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
           CpAsync4(idst + Layout::kSlotLoss * kEvaluateThreads, a.loss_index + r);
       }
       if constexpr (Layout::kFunctorInSmem) {
-        const unsigned char* src =
-            static_cast<const unsigned char*>(a.functors) + static_cast<size_t>(clamp(rb)) * sizeof(Functor);
+        const unsigned char* src = static_cast<const unsigned char*>(a.functors) +
+                                   static_cast<size_t>(clamp(rb)) * sizeof(Functor);
         unsigned char* fdst = stage_functor(stage);
         if constexpr (sizeof(Functor) % 16 == 0) {
 #pragma unroll
@@ -430,21 +489,28 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
         return __ldg(global_table + index);
       }
     };
-    int delta_off[kNB], jpos[kNB], tangent_rt[kNB], plus_off[kNB], key[kNB];
+    // Per argument: where the gradient goes, where the Jacobian block goes, how the
+    // ambient columns map to tangent columns.
+    int delta_off[kNB], jpos[kNB], tangent[kNB], kind[kNB], mparam[kNB], plus_off[kNB], key[kNB];
     if constexpr (kJets) {
 #pragma unroll
       for (int j = 0; j < kNB; ++j) {
         const size_t at = static_cast<size_t>(j) * n + tt;
         if constexpr (kGeneric) {
           const int id = table(Layout::kSlotDelta + j, a.parameter_block, at);
-          const int4 rec = __ldg(reinterpret_cast<const int4*>(a.parameter_block_table) + id);
-          delta_off[j] = rec.y;
-          tangent_rt[j] = rec.z;
-          plus_off[j] = rec.w;
+          const int4* rec = reinterpret_cast<const int4*>(a.parameter_block_table) + 2 * id;
+          const int4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
+          delta_off[j] = r0.y;
+          tangent[j] = r0.z;
+          kind[j] = r0.w;
+          mparam[j] = r1.x;
+          plus_off[j] = r1.y;
           key[j] = id;
         } else {
           delta_off[j] = table(Layout::kSlotDelta + j, a.delta_offset, at);
-          tangent_rt[j] = Dims::Size(j);
+          tangent[j] = Dims::Size(j);
+          kind[j] = CB200_MANIFOLD_NONE;
+          mparam[j] = 0;
           plus_off[j] = -1;
           key[j] = delta_off[j];
         }
@@ -476,21 +542,22 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
     }
     const Functor& functor = *functor_ptr;
 
+    double xval[kNP];
+#pragma unroll
+    for (int j = 0; j < kNB; ++j)
+#pragma unroll
+      for (int i = 0; i < Dims::Size(j); ++i) xval[Dims::Offset(j) + i] = param(j, i);
+
     double res[kRes];
-    bool ok;
+    bool ok = true;
     double cost = 0.0;
     const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
 
     if constexpr (!kJets) {
       // AutoDiffCostFunction::Evaluate with jacobians == nullptr.
-      double x[kNP];
-#pragma unroll
-      for (int j = 0; j < kNB; ++j)
-#pragma unroll
-        for (int i = 0; i < Dims::Size(j); ++i) x[Dims::Offset(j) + i] = param(j, i);
 #pragma unroll
       for (int r = 0; r < kRes; ++r) res[r] = kNaN;  // unwritten outputs stay invalid
-      ok = CallFunctor<Dims>(functor, x, res, std::make_index_sequence<kNB>{});
+      ok = CallFunctor<Dims>(functor, xval, res, std::make_index_sequence<kNB>{});
       FiniteCheck check;
 #pragma unroll
       for (int r = 0; r < kRes; ++r) check.Add(res[r]);
@@ -519,225 +586,295 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
         cost = 0.5 * s;
       }
     } else {
-      using JetT = Jet<double, kNP>;
-      JetT x[kNP];
+      // ---- where the Jacobian leaves through shared memory + TMA (warp-uniform plan)
+      // BlockSparse: argument j's 32 cells are one run of the values array (always true
+      // inside the E or F region); CompressedRow: the warp's 32 row groups are one run.
+      bool bulk_arg[kNB];
+      bool bulk_all = false;
+      int bulk_base[kNB];
+      int bulk_all_base = 0;
 #pragma unroll
-      for (int j = 0; j < kNB; ++j)
+      for (int j = 0; j < kNB; ++j) { bulk_arg[j] = false; bulk_base[j] = 0; }
+      if constexpr (kStage) {
+        if (a.output_jacobian && CB200_KERNEL_BULK_STORE) {
+          if (!a.crs) {
 #pragma unroll
-        for (int i = 0; i < Dims::Size(j); ++i)
-          x[Dims::Offset(j) + i] = JetT(param(j, i), Dims::Offset(j) + i);
-      JetT out[kRes];
-      // autodiff.h:358-363 invalidates the outputs with kImpossibleValue and the CPU
-      // evaluator rejects evaluations that still contain it
-      // (residual_block_utils.cc:70-95).  Here unwritten outputs are NaN, so the
-      // finite check below covers both conditions.
+            for (int j = 0; j < kNB; ++j) {
+              const int t0 = __shfl_sync(0xffffffffu, tangent[j], 0);
+              const int base = __shfl_sync(0xffffffffu, jpos[j], 0);
+              const bool mine = valid && delta_off[j] >= 0 && tangent[j] == t0 &&
+                                jpos[j] == base + lane * kRes * t0;
+              bulk_arg[j] = __all_sync(0xffffffffu, mine) && ((base & 1) == 0);
+              bulk_base[j] = base;
+            }
+          } else {
+            int lo = 0x7fffffff;
 #pragma unroll
-      for (int r = 0; r < kRes; ++r) out[r] = JetT::Filled(kNaN, kNaN);
-      ok = CallFunctor<Dims>(functor, x, out, std::make_index_sequence<kNB>{});
-
-      FiniteCheck check;
-#pragma unroll
-      for (int r = 0; r < kRes; ++r) {
-        res[r] = out[r].a;
-        check.Add(out[r].a);
-#pragma unroll
-        for (int i = 0; i < kNP; ++i)
-          if (out[r].lane(i)) check.Add(out[r].v[i]);
-      }
-      ok = ok && !check.Bad();
-
-      double s = 0.0;
-#pragma unroll
-      for (int r = 0; r < kRes; ++r) s += res[r] * res[r];
-
-      double sqrt_rho1 = 1.0, residual_scaling = 1.0, alpha_sq_norm = 0.0;
-      bool correct = false;
-      if (a.apply_loss_function) {
-        double rho[3];
-        loss.Evaluate(s, rho);
-        cost = 0.5 * rho[0];
-        sqrt_rho1 = ::sqrt(rho[1]);
-        residual_scaling = sqrt_rho1;
-        if (!(s == 0.0 || rho[2] <= 0.0)) {
-          const double D = 1.0 + 2.0 * s * rho[2] / rho[1];
-          const double alpha = 1.0 - ::sqrt(D);
-          residual_scaling = sqrt_rho1 / (1 - alpha);
-          alpha_sq_norm = alpha / s;
+            for (int j = 0; j < kNB; ++j)
+              if (delta_off[j] >= 0) lo = min(lo, jpos[j]);
+            const int s0 = __shfl_sync(0xffffffffu, row_stride_crs, 0);
+            const int base = __shfl_sync(0xffffffffu, lo, 0);
+            const bool mine = valid && row_stride_crs == s0 && lo == base + lane * kRes * s0;
+            bulk_all = __all_sync(0xffffffffu, mine) && ((base & 1) == 0) && s0 > 0;
+            bulk_all_base = base;
+          }
         }
-        // Multiplying by exactly 1 changes nothing: skip the correction for blocks in
-        // the quadratic region of the loss (rho' = 1, rho'' = 0).
-        correct = !(sqrt_rho1 == 1.0 && alpha_sq_norm == 0.0);
-      } else {
-        cost = 0.5 * s;
       }
-
-      double res_corrected[kRes];
-#pragma unroll
-      for (int r = 0; r < kRes; ++r) res_corrected[r] = res[r] * residual_scaling;
-
       // The staging buffer may still be read by last iteration's bulk stores.
-      if (CB200_KERNEL_BULK_STORE && bulk_pending) {
+      if (kStage && bulk_pending) {
         if (lane == 0) BulkWaitRead();
         __syncwarp();
         bulk_pending = false;
       }
       bool bulk_issued = false;
 
-      // Per parameter block: project, correct, accumulate the gradient, scatter.
-      auto epilogue = [&](auto jc) {
-        constexpr int j = decltype(jc)::value;
-        constexpr int kSize = Dims::Size(j);
-        constexpr int kOff = Dims::Offset(j);
-        const bool active = kGeneric ? delta_off[j] >= 0 : true;
-        int tangent = kSize;
-        double B[kRes][kSize];
-#pragma unroll
-        for (int r = 0; r < kRes; ++r)
-#pragma unroll
-          for (int c = 0; c < kSize; ++c) B[r][c] = out[r].v[kOff + c];
-        if constexpr (kGeneric) {
-          if (active && plus_off[j] >= 0) {
-            tangent = tangent_rt[j];
-            BlockEpilogue<kRes, kSize>::MultiplyPlusJacobian(B, a.plus_jacobians + plus_off[j],
-                                                             tangent);
-          }
-        }
-        if (correct)
-          BlockEpilogue<kRes, kSize>::Correct(B, tangent, res, sqrt_rho1, alpha_sq_norm);
+      double sqrt_rho1 = 1.0, residual_scaling = 1.0, alpha_sq_norm = 0.0;
+      bool correct = false;
+      double res_corrected[kRes];
 
-        if (a.output_gradient) {
-          double g[kSize];
+      // ---- derivative passes
+      auto pass = [&](auto pc) {
+        constexpr int p = decltype(pc)::value;
+        constexpr int kW = Plan::Width(p);
+        constexpr int kFirst = Plan::FirstBlock(p), kEnd = Plan::EndBlock(p);
+        using JetT = Jet<double, kW>;
+        JetT x[kNP];
 #pragma unroll
-          for (int c = 0; c < kSize; ++c) {
-            double acc = 0.0;
+        for (int j = 0; j < kNB; ++j)
 #pragma unroll
-            for (int r = 0; r < kRes; ++r) acc += B[r][c] * res_corrected[r];
-            g[c] = acc;
+          for (int i = 0; i < Dims::Size(j); ++i)
+            x[Dims::Offset(j) + i] = (j >= kFirst && j < kEnd)
+                                         ? JetT(xval[Dims::Offset(j) + i], Plan::Lane(j, i))
+                                         : JetT(xval[Dims::Offset(j) + i]);
+        JetT out[kRes];
+        // autodiff.h:358-363 invalidates the outputs with kImpossibleValue and the CPU
+        // evaluator rejects evaluations that still contain it
+        // (residual_block_utils.cc:70-95).  Here unwritten outputs are NaN, so the
+        // finite check below covers both conditions.
+#pragma unroll
+        for (int r = 0; r < kRes; ++r) out[r] = JetT::Filled(kNaN, kNaN);
+        ok = CallFunctor<Dims>(functor, x, out, std::make_index_sequence<kNB>{}) && ok;
+
+        FiniteCheck check;
+#pragma unroll
+        for (int r = 0; r < kRes; ++r) {
+          if (p == 0) check.Add(out[r].a);
+#pragma unroll
+          for (int i = 0; i < kW; ++i)
+            if (out[r].lane(i)) check.Add(out[r].v[i]);
+        }
+        ok = ok && !check.Bad();
+
+        if constexpr (p == 0) {
+          double s = 0.0;
+#pragma unroll
+          for (int r = 0; r < kRes; ++r) {
+            res[r] = out[r].a;
+            s += res[r] * res[r];
           }
-          // Long runs of consecutive blocks sharing this parameter block (few distinct
-          // blocks in the warp) are summed in the warp first, so one lane per run adds to
-          // memory.  Short runs (the 3-10 observations of a BAL point) go out directly:
-          // lanes of one red instruction that hit the same sector share one L2 request,
-          // which is cheaper than 5 shuffle steps per value.
-          const int k_ = (valid && active) ? key[j] : -1 - lane;
-          const int prev_key = __shfl_up_sync(0xffffffffu, k_, 1);
-          bool head = (lane == 0) || (prev_key != k_);
-          const unsigned heads = __ballot_sync(0xffffffffu, head);
-          if (__popc(heads) <= 4) {
-#pragma unroll
-            for (int c = 0; c < kSize; ++c) g[c] = (valid && ok && active) ? g[c] : 0.0;
-            const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
-            const int run_end = above ? __ffs(above) - 1 : 32;
-            WarpSegmentedSum<kSize>(run_end, g, lane);
-          } else {
-            head = true;  // every lane adds its own contribution
-          }
-          const bool emit = head && valid && ok && active;
-          const unsigned emit_mask = __ballot_sync(0xffffffffu, emit);
-          if (CB200_KERNEL_STAGE_GRADIENT && __popc(emit_mask) >= 12) {
-            // Most lanes own a distinct block (the cameras of a BAL warp): stage the
-            // per-lane sums and let consecutive lanes add to consecutive addresses, so
-            // one red instruction touches a few sectors instead of 32.
-            constexpr int kPitch = StagePitch(kSize);
-            double* gbuf = wbuf + 32 * kRes * kOff;  // this argument's own region
-#pragma unroll
-            for (int c = 0; c < kSize; ++c) gbuf[lane * kPitch + c] = g[c];
-            __syncwarp();
-#pragma unroll
-            for (int it = 0; it < kSize; ++it) {
-              const int e = it * 32 + lane;
-              const int row = e / kSize;
-              const int c = e - row * kSize;
-              const int d = __shfl_sync(0xffffffffu, delta_off[j], row);
-              const int tg = kGeneric ? __shfl_sync(0xffffffffu, tangent, row) : kSize;
-              if (((emit_mask >> row) & 1u) && c < tg)
-                RedAdd(a.gradient + d + c, gbuf[row * kPitch + c]);
+          if (a.apply_loss_function) {
+            double rho[3];
+            loss.Evaluate(s, rho);
+            cost = 0.5 * rho[0];
+            sqrt_rho1 = ::sqrt(rho[1]);
+            residual_scaling = sqrt_rho1;
+            if (!(s == 0.0 || rho[2] <= 0.0)) {
+              const double D = 1.0 + 2.0 * s * rho[2] / rho[1];
+              const double alpha = 1.0 - ::sqrt(D);
+              residual_scaling = sqrt_rho1 / (1 - alpha);
+              alpha_sq_norm = alpha / s;
             }
-            __syncwarp();
-          } else if (emit) {
-            double* __restrict__ dst = a.gradient + delta_off[j];
-#pragma unroll
-            for (int c = 0; c < kSize; ++c)
-              if (!kGeneric || c < tangent) RedAdd(dst + c, g[c]);
+            // Multiplying by exactly 1 changes nothing: skip the correction for blocks
+            // in the quadratic region of the loss (rho' = 1, rho'' = 0).
+            correct = !(sqrt_rho1 == 1.0 && alpha_sq_norm == 0.0);
+          } else {
+            cost = 0.5 * s;
           }
+#pragma unroll
+          for (int r = 0; r < kRes; ++r) res_corrected[r] = res[r] * residual_scaling;
         }
 
-        if (a.output_jacobian) {
-          constexpr int kCell = kRes * kSize;
-          const int row_stride = a.crs ? row_stride_crs : tangent;
-          const bool dense = valid && active && row_stride == kSize && tangent == kSize;
-          const int base = __shfl_sync(0xffffffffu, jpos[j], 0);
-          // Consecutive residual blocks own consecutive cells (always true inside the
-          // E or the F region of a BlockSparseMatrix): the warp's 32 cells are one run.
-          const bool run = CB200_KERNEL_STAGE_JACOBIAN &&
-                           __all_sync(0xffffffffu, dense && jpos[j] == base + lane * kCell);
-          if (run && CB200_KERNEL_BULK_STORE && (kCell % 2 == 0) && ((base & 1) == 0)) {
-            // Cells laid out exactly as in global memory (pitch = cell, 128-bit stores are
-            // bank-conflict free for cells that are a multiple of 16 bytes), then one
-            // TMA bulk copy for the warp's 32 cells.
-            double* region = wbuf + 32 * kRes * kOff;
-            double2* mine = reinterpret_cast<double2*>(region + lane * kCell);
-#pragma unroll
-            for (int e = 0; e < kCell; e += 2)
-              mine[e / 2] = make_double2(B[e / kSize][e % kSize],
-                                         B[(e + 1) / kSize][(e + 1) % kSize]);
-            FenceProxyAsyncShared();
-            __syncwarp();
-            if (lane == 0) BulkStore(a.jacobian_values + base, region, 32 * kCell * 8);
-            bulk_issued = true;
-          } else if (run) {
-            constexpr int kPitch = StagePitch(kCell);
-            double* jbuf = wbuf + 32 * kRes * kOff;
+        // Per parameter block of this pass: project, correct, gradient, scatter.
+        auto epilogue = [&](auto jc) {
+          constexpr int j = decltype(jc)::value;
+          if constexpr (j >= kFirst && j < kEnd) {
+            constexpr int kSize = Dims::Size(j);
+            constexpr int kLane0 = Plan::Lane(j, 0);
+            constexpr unsigned kAll = kSize >= 32 ? 0xffffffffu : ((1u << kSize) - 1u);
+            const bool active = kGeneric ? delta_off[j] >= 0 : true;
+            double B[kRes][kSize];
 #pragma unroll
             for (int r = 0; r < kRes; ++r)
 #pragma unroll
-              for (int c = 0; c < kSize; ++c) jbuf[lane * kPitch + r * kSize + c] = B[r][c];
-            __syncwarp();
-            double* __restrict__ dst = a.jacobian_values + base;
-            if ((kCell % 2 == 0) && ((base & 1) == 0)) {
+              for (int c = 0; c < kSize; ++c) B[r][c] = out[r].v[kLane0 + c];
+
+            // live: ambient columns of B that are tangent columns, in order.
+            unsigned live = kAll;
+            if constexpr (kGeneric) {
+              if (kind[j] == CB200_MANIFOLD_SUBSET) {
+                live = kAll & ~static_cast<unsigned>(mparam[j]);  // column selection
+              } else if (kind[j] == CB200_MANIFOLD_QUATERNION_TAIL ||
+                         kind[j] == CB200_MANIFOLD_EIGEN_QUATERNION_TAIL) {
+                if constexpr (kSize >= 4) {
+                  // d(q (+) delta)/d delta at delta = 0, 4 x 3, from the state itself
+                  // (manifold.cc:62-79); Euclidean tail columns shift left by one.
+                  const bool eigen_order = kind[j] == CB200_MANIFOLD_EIGEN_QUATERNION_TAIL;
+                  const double* q = xval + Dims::Offset(j);
+                  const double qw = eigen_order ? q[3] : q[0];
+                  const double qx = eigen_order ? q[0] : q[1];
+                  const double qy = eigen_order ? q[1] : q[2];
+                  const double qz = eigen_order ? q[2] : q[3];
 #pragma unroll
-              for (int it = 0; it < kCell / 2; ++it) {
-                const int e = 2 * (it * 32 + lane);
-                const int row = e / kCell;
-                const int col = e - row * kCell;
-                reinterpret_cast<double2*>(dst)[it * 32 + lane] =
-                    make_double2(jbuf[row * kPitch + col], jbuf[row * kPitch + col + 1]);
-              }
-            } else {
+                  for (int r = 0; r < kRes; ++r) {
+                    const double bw = eigen_order ? B[r][3] : B[r][0];
+                    const double bx = eigen_order ? B[r][0] : B[r][1];
+                    const double by = eigen_order ? B[r][1] : B[r][2];
+                    const double bz = eigen_order ? B[r][2] : B[r][3];
+                    B[r][0] = -bw * qx + bx * qw - by * qz + bz * qy;
+                    B[r][1] = -bw * qy + bx * qz + by * qw - bz * qx;
+                    B[r][2] = -bw * qz - bx * qy + by * qx + bz * qw;
 #pragma unroll
-              for (int it = 0; it < kCell; ++it) {
-                const int e = it * 32 + lane;
-                const int row = e / kCell;
-                dst[e] = jbuf[row * kPitch + (e - row * kCell)];
+                    for (int c = 3; c + 1 < kSize; ++c) B[r][c] = B[r][c + 1];
+                  }
+                  live = kAll >> 1;
+                }
+              } else if (kind[j] == CB200_MANIFOLD_GENERIC && active) {
+                BlockEpilogue<kRes, kSize>::MultiplyPlusJacobian(
+                    B, a.plus_jacobians + plus_off[j], tangent[j]);
+                live = tangent[j] >= 32 ? 0xffffffffu : ((1u << tangent[j]) - 1u);
               }
             }
-            __syncwarp();
-          } else if (valid && active) {
-            double* __restrict__ dst = a.jacobian_values + jpos[j];
-            if (row_stride == kSize && tangent == kSize && ((jpos[j] & 1) == 0) &&
-                (kCell % 2 == 0)) {
-              double2* __restrict__ d2 = reinterpret_cast<double2*>(dst);
+            auto dcol = [&](int c) -> int {
+              return kGeneric ? __popc(live & ((1u << c) - 1u)) : c;
+            };
+            auto is_live = [&](int c) -> bool { return kGeneric ? ((live >> c) & 1u) : true; };
+            const int tan = kGeneric ? tangent[j] : kSize;
+
+            if (correct)
+              BlockEpilogue<kRes, kSize>::Correct(B, res, sqrt_rho1, alpha_sq_norm);
+
+            if (a.output_gradient) {
+              double g[kSize];
 #pragma unroll
-              for (int e = 0; e < kCell; e += 2) {
-                d2[e / 2] = make_double2(B[e / kSize][e % kSize],
-                                         B[(e + 1) / kSize][(e + 1) % kSize]);
+              for (int c = 0; c < kSize; ++c) {
+                double acc = 0.0;
+#pragma unroll
+                for (int r = 0; r < kRes; ++r) acc += B[r][c] * res_corrected[r];
+                g[c] = acc;
               }
-            } else {
+              // Long runs of consecutive blocks sharing this parameter block (few distinct
+              // blocks in the warp) are summed in the warp first, so one lane per run adds
+              // to memory.  Short runs (the 3-10 observations of a BAL point) go out
+              // directly: lanes of one red instruction that hit the same sector share one
+              // L2 request, which is cheaper than 5 shuffle steps per value.
+              const int k_ = (valid && active) ? key[j] : -1 - lane;
+              const int prev_key = __shfl_up_sync(0xffffffffu, k_, 1);
+              bool head = (lane == 0) || (prev_key != k_);
+              const unsigned heads = __ballot_sync(0xffffffffu, head);
+              if (__popc(heads) <= 4) {
 #pragma unroll
-              for (int r = 0; r < kRes; ++r)
+                for (int c = 0; c < kSize; ++c) g[c] = (valid && ok && active) ? g[c] : 0.0;
+                const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+                const int run_end = above ? __ffs(above) - 1 : 32;
+                WarpSegmentedSum<kSize>(run_end, g, lane);
+              } else {
+                head = true;  // every lane adds its own contribution
+              }
+              const bool emit = head && valid && ok && active;
+              const unsigned emit_mask = __ballot_sync(0xffffffffu, emit);
+              if (CB200_KERNEL_STAGE_GRADIENT && __popc(emit_mask) >= 12) {
+                // Most lanes own a distinct block (the cameras of a BAL warp): stage the
+                // per-lane sums and let consecutive lanes add to consecutive addresses, so
+                // one red instruction touches a few sectors instead of 32.
+                constexpr int kPitch = StagePitch(kSize);
+#pragma unroll
+                for (int c = 0; c < kSize; ++c) gbuf[lane * kPitch + c] = g[c];
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < kSize; ++it) {
+                  const int e = it * 32 + lane;
+                  const int row = e / kSize;
+                  const int c = e - row * kSize;
+                  const int d = __shfl_sync(0xffffffffu, delta_off[j], row);
+                  const unsigned lv = kGeneric ? __shfl_sync(0xffffffffu, live, row) : kAll;
+                  if (((emit_mask >> row) & 1u) && ((lv >> c) & 1u))
+                    RedAdd(a.gradient + d + (kGeneric ? __popc(lv & ((1u << c) - 1u)) : c),
+                           gbuf[row * kPitch + c]);
+                }
+                __syncwarp();
+              } else if (emit) {
+                double* __restrict__ dst = a.gradient + delta_off[j];
 #pragma unroll
                 for (int c = 0; c < kSize; ++c)
-                  if (c < tangent) dst[r * row_stride + c] = B[r][c];
+                  if (is_live(c)) RedAdd(dst + dcol(c), g[c]);
+              }
+            }
+
+            if (a.output_jacobian) {
+              const int row_stride = a.crs ? row_stride_crs : tan;
+              if (kStage && (bulk_arg[j] || bulk_all)) {
+                // Stage the cell exactly as it lies in global memory.
+                double* cell = bulk_all ? jbuf + (jpos[j] - bulk_all_base)
+                                        : jbuf + 32 * kRes * Dims::Offset(j) + lane * kRes * tan;
+                if (!kGeneric && !a.crs && (kRes * kSize) % 2 == 0) {
+                  double2* mine = reinterpret_cast<double2*>(cell);  // conflict-free 128-bit
+#pragma unroll
+                  for (int e = 0; e < kRes * kSize; e += 2)
+                    mine[e / 2] = make_double2(B[e / kSize][e % kSize],
+                                               B[(e + 1) / kSize][(e + 1) % kSize]);
+                } else {
+#pragma unroll
+                  for (int r = 0; r < kRes; ++r)
+#pragma unroll
+                    for (int c = 0; c < kSize; ++c)
+                      if (is_live(c)) cell[r * row_stride + dcol(c)] = B[r][c];
+                }
+                if (bulk_arg[j]) {
+                  FenceProxyAsyncShared();
+                  __syncwarp();
+                  if (lane == 0)
+                    BulkStore(a.jacobian_values + bulk_base[j],
+                              jbuf + 32 * kRes * Dims::Offset(j), 32 * kRes * tan * 8);
+                  bulk_issued = true;
+                }
+              } else if (valid && active) {
+                double* __restrict__ dst = a.jacobian_values + jpos[j];
+                if (!kGeneric && row_stride == kSize && ((jpos[j] & 1) == 0) &&
+                    ((kRes * kSize) % 2 == 0)) {
+                  double2* __restrict__ d2 = reinterpret_cast<double2*>(dst);
+#pragma unroll
+                  for (int e = 0; e < kRes * kSize; e += 2)
+                    d2[e / 2] = make_double2(B[e / kSize][e % kSize],
+                                             B[(e + 1) / kSize][(e + 1) % kSize]);
+                } else {
+#pragma unroll
+                  for (int r = 0; r < kRes; ++r)
+#pragma unroll
+                    for (int c = 0; c < kSize; ++c)
+                      if (is_live(c)) dst[r * row_stride + dcol(c)] = B[r][c];
+                }
+              }
             }
           }
-        }
+        };
+        if (a.output_jacobian || a.output_gradient)
+          ForEachBlock(epilogue, std::make_index_sequence<kNB>{});
       };
-      if (a.output_jacobian || a.output_gradient) {
-        ForEachBlock(epilogue, std::make_index_sequence<kNB>{});
-      }
-      if (bulk_issued) {
-        if (lane == 0) BulkCommit();
-        bulk_pending = true;
+      ForEachBlock(pass, std::make_index_sequence<Plan::kNumPasses>{});
+
+      if constexpr (kStage) {
+        if (bulk_all) {
+          FenceProxyAsyncShared();
+          __syncwarp();
+          const int s0 = __shfl_sync(0xffffffffu, row_stride_crs, 0);
+          if (lane == 0)
+            BulkStore(a.jacobian_values + bulk_all_base, jbuf, 32 * kRes * s0 * 8);
+          bulk_issued = true;
+        }
+        if (bulk_issued) {
+          if (lane == 0) BulkCommit();
+          bulk_pending = true;
+        }
       }
 #pragma unroll
       for (int r = 0; r < kRes; ++r) res[r] = res_corrected[r];
@@ -800,32 +937,26 @@ int LaunchEvaluate(const cb200_launch_args* args, void* stream) {
   int grid = needed < persistent_ctas ? needed : persistent_ctas;
   if (grid > args->cost_partial_count) grid = args->cost_partial_count;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  using Dims = BlockDims<Ns...>;
-  using Layout = PrefetchLayout<Functor, Dims::kNumParameters, Dims::kNumBlocks>;
-  constexpr int kPrefetchBytes = Layout::kFits ? Layout::kPrefetchBytes : 0;
-  constexpr int kJetBytes =
-      kPrefetchBytes +
-      (kEvaluateThreads / 32) * WarpStageDoubles(kRes, Dims::MaxSize(), Dims::kNumParameters) * 8;
-  constexpr int kCostBytes = kPrefetchBytes > 0 ? kPrefetchBytes : 16;
+  using Smem = SmemPlan<Functor, kRes, Ns...>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(EvaluateKernel<kVariantCost, Functor, Loss, kRes, Ns...>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, kCostBytes);
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kCostBytes);
     cudaFuncSetAttribute(EvaluateKernel<kVariantPlain, Functor, Loss, kRes, Ns...>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, kJetBytes);
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kJetBytes);
     cudaFuncSetAttribute(EvaluateKernel<kVariantGeneric, Functor, Loss, kRes, Ns...>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, kJetBytes);
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kJetBytes);
     configured = true;
   }
   if (!(args->output_jacobian || args->output_gradient)) {
     EvaluateKernel<kVariantCost, Functor, Loss, kRes, Ns...>
-        <<<grid, kEvaluateThreads, kCostBytes, s>>>(*args);
+        <<<grid, kEvaluateThreads, Smem::kCostBytes, s>>>(*args);
   } else if (args->plain) {
     EvaluateKernel<kVariantPlain, Functor, Loss, kRes, Ns...>
-        <<<grid, kEvaluateThreads, kJetBytes, s>>>(*args);
+        <<<grid, kEvaluateThreads, Smem::kJetBytes, s>>>(*args);
   } else {
     EvaluateKernel<kVariantGeneric, Functor, Loss, kRes, Ns...>
-        <<<grid, kEvaluateThreads, kJetBytes, s>>>(*args);
+        <<<grid, kEvaluateThreads, Smem::kJetBytes, s>>>(*args);
   }
   return static_cast<int>(cudaGetLastError());
 }

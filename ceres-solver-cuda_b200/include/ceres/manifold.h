@@ -11,6 +11,7 @@
 
 #include <cmath>
 #include <tuple>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -23,7 +24,23 @@ class Manifold {
   virtual int TangentSize() const = 0;
   virtual bool Plus(const double* x, const double* delta, double* x_plus_delta) const = 0;
   virtual bool PlusJacobian(const double* x, double* jacobian) const = 0;
+  // Extension (not in the reference): manifolds whose plus-Jacobian the evaluation
+  // kernel can apply by itself describe themselves here (kind = CB200_MANIFOLD_* of
+  // ceres_b200.h, param = kind-specific); the host then neither evaluates nor uploads
+  // their PlusJacobian.  Returning false selects the generic path (PlusJacobian on the
+  // host every Evaluate, as the reference does: parameter_block.h:312-338).
+  virtual bool DeviceDescription(int* kind, int* param) const {
+    (void)kind;
+    (void)param;
+    return false;
+  }
 };
+
+namespace manifold_internal {
+// Values of CB200_MANIFOLD_* (ceres_b200.h), repeated so this header stays stand-alone.
+constexpr int kDeviceNone = 0, kDeviceSubset = 1, kDeviceQuaternionTail = 2,
+              kDeviceEigenQuaternionTail = 3;
+}  // namespace manifold_internal
 
 class EuclideanManifoldBase : public Manifold {
  public:
@@ -37,6 +54,11 @@ class EuclideanManifoldBase : public Manifold {
   bool PlusJacobian(const double*, double* jacobian) const override {
     for (int r = 0; r < size_; ++r)
       for (int c = 0; c < size_; ++c) jacobian[r * size_ + c] = (r == c) ? 1.0 : 0.0;
+    return true;
+  }
+  bool DeviceDescription(int* kind, int* param) const override {
+    *kind = manifold_internal::kDeviceNone;  // identity plus-Jacobian
+    *param = 0;
     return true;
   }
 
@@ -77,6 +99,15 @@ class SubsetManifold : public Manifold {
     return true;
   }
   const std::vector<bool>& constancy_mask() const { return constancy_mask_; }
+  bool DeviceDescription(int* kind, int* param) const override {
+    if (AmbientSize() > 31) return false;
+    unsigned mask = 0;
+    for (int i = 0; i < AmbientSize(); ++i)
+      if (constancy_mask_[i]) mask |= 1u << i;
+    *kind = manifold_internal::kDeviceSubset;
+    *param = static_cast<int>(mask);
+    return true;
+  }
 
  private:
   std::vector<bool> constancy_mask_;
@@ -127,6 +158,11 @@ class QuaternionManifold : public Manifold {
     manifold_internal::QuaternionPlusJacobian<0, 1, 2, 3>(x, jacobian);
     return true;
   }
+  bool DeviceDescription(int* kind, int* param) const override {
+    *kind = manifold_internal::kDeviceQuaternionTail;
+    *param = 0;
+    return true;
+  }
 };
 
 // Unit quaternions stored (x, y, z, w) as Eigen::Quaternion does.
@@ -142,6 +178,11 @@ class EigenQuaternionManifold : public Manifold {
     manifold_internal::QuaternionPlusJacobian<3, 0, 1, 2>(x, jacobian);
     return true;
   }
+  bool DeviceDescription(int* kind, int* param) const override {
+    *kind = manifold_internal::kDeviceEigenQuaternionTail;
+    *param = 0;
+    return true;
+  }
 };
 
 // Cartesian product; the plus-Jacobian is block diagonal.
@@ -152,6 +193,10 @@ class ProductManifold : public Manifold {
   explicit ProductManifold(Ms... ms) : manifolds_(std::move(ms)...) { Init(); }
   int AmbientSize() const override { return ambient_; }
   int TangentSize() const override { return tangent_; }
+  // A quaternion followed by Euclidean factors is a shape the kernel knows.
+  bool DeviceDescription(int* kind, int* param) const override {
+    return DescribeQuaternionTail(kind, param, static_cast<std::tuple<Ms...>*>(nullptr));
+  }
   bool Plus(const double* x, const double* delta, double* out) const override {
     bool ok = true;
     int a = 0, t = 0;
@@ -198,6 +243,23 @@ class ProductManifold : public Manifold {
     t += ts;
     return true;
   }
+  template <typename First, typename... Rest>
+  static bool DescribeQuaternionTail(int* kind, int* param, std::tuple<First, Rest...>*) {
+    constexpr bool tail_is_euclidean =
+        (std::is_base_of<EuclideanManifoldBase, Rest>::value && ...);
+    if (!tail_is_euclidean) return false;
+    *param = 0;
+    if (std::is_same<First, QuaternionManifold>::value) {
+      *kind = manifold_internal::kDeviceQuaternionTail;
+      return true;
+    }
+    if (std::is_same<First, EigenQuaternionManifold>::value) {
+      *kind = manifold_internal::kDeviceEigenQuaternionTail;
+      return true;
+    }
+    return false;
+  }
+  static bool DescribeQuaternionTail(int*, int*, std::tuple<>*) { return false; }
   std::tuple<Ms...> manifolds_;
   int ambient_ = 0, tangent_ = 0;
 };

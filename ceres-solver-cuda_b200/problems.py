@@ -65,6 +65,7 @@ LOSS_SCALED_HUBER, LOSS_SCALED_CAUCHY, LOSS_SCALED_TRIVIAL = 4, 5, 6
 # ---- manifold kinds (internal/ceres/manifold.cc, include/ceres/product_manifold.h)
 MANIFOLD_NONE, MANIFOLD_SUBSET, MANIFOLD_QUATERNION, MANIFOLD_EIGEN_QUATERNION = 0, 1, 2, 3
 MANIFOLD_QUATERNION_X_EUCLIDEAN, MANIFOLD_EIGEN_QUATERNION_X_EUCLIDEAN = 4, 5
+MANIFOLD_OPAQUE_SUBSET = 6  # a SubsetManifold the kernel is not told about (generic path)
 
 JACOBIAN_BLOCK_SPARSE, JACOBIAN_COMPRESSED_ROW = 0, 1
 

@@ -51,9 +51,21 @@ typedef struct cb200_parameter_block {
   int32_t tangent_size;         /* == size without a manifold */
   int32_t state_offset;         /* active: into the state vector; constant: into constant_state */
   int32_t delta_offset;         /* active: into the gradient / Jacobian columns; constant: -1 */
-  int32_t plus_jacobian_offset; /* offset (doubles) of the row-major size x tangent_size plus-Jacobian
-                                   in the pool passed to cb200_engine_evaluate; -1 = no manifold */
+  int32_t plus_jacobian_offset; /* CB200_MANIFOLD_GENERIC: offset (doubles) of the row-major
+                                   size x tangent_size plus-Jacobian in the pool passed to
+                                   cb200_engine_evaluate; -1 otherwise */
+  int32_t manifold_kind;        /* CB200_MANIFOLD_*: manifolds the kernel applies by itself need
+                                   no plus-Jacobian from the host (Manifold::PlusJacobian,
+                                   internal/ceres/manifold.cc:62-79,199-214) */
+  int32_t manifold_param;       /* SUBSET: bit i set = coordinate i held constant (size <= 32) */
 } cb200_parameter_block;
+
+#define CB200_MANIFOLD_NONE 0
+#define CB200_MANIFOLD_SUBSET 1                /* SubsetManifold */
+#define CB200_MANIFOLD_QUATERNION_TAIL 2       /* (w,x,y,z) at [0,4) then Euclidean coordinates:
+                                                  QuaternionManifold, ProductManifold<Quaternion, Euclidean<k>> */
+#define CB200_MANIFOLD_EIGEN_QUATERNION_TAIL 3 /* (x,y,z,w) at [0,4) then Euclidean coordinates */
+#define CB200_MANIFOLD_GENERIC 4               /* any other manifold: plus-Jacobian from the pool */
 
 /* Arguments of one kernel launch for one residual-block type.  All pointers are
  * device pointers owned by the engine.  Structure-of-arrays, argument-major:
@@ -78,8 +90,9 @@ typedef struct cb200_launch_args {
                                      jacobian_values (rank-local), -1 for a constant block */
   const int32_t* jacobian_row_stride; /* [n] compressed-row: values between consecutive rows */
   const int32_t* residual_pos;    /* [n] offset of the block's residuals (rank-local) */
-  const int32_t* parameter_block_table; /* int4 per block: state_offset, delta_offset,
-                                      tangent_size, plus_jacobian_offset; constant blocks have
+  const int32_t* parameter_block_table; /* 8 ints per block: state_offset, delta_offset,
+                                      tangent_size, manifold_kind, manifold_param,
+                                      plus_jacobian_offset, 0, 0; constant blocks have
                                       delta_offset -1 and state_offset already shifted past the
                                       active state */
   const double* state;            /* [num_parameters | constant state] */

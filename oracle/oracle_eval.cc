@@ -256,13 +256,15 @@ enum ManifoldKind {
   kManifoldQuaternion = 2,       // (w, x, y, z)
   kManifoldEigenQuaternion = 3,  // (x, y, z, w)
   kManifoldQuaternionTimesEuclidean = 4,      // ProductManifold<Quaternion, Euclidean<size-4>>
-  kManifoldEigenQuaternionTimesEuclidean = 5  // ProductManifold<EigenQuaternion, Euclidean<size-4>>
+  kManifoldEigenQuaternionTimesEuclidean = 5,  // ProductManifold<EigenQuaternion, Euclidean<size-4>>
+  kManifoldSubsetAlias = 6  // same as kManifoldSubset (the product's tests use it to force its generic path)
 };
 
 static int ManifoldTangentSize(int kind, int param, int ambient) {
   switch (kind) {
     case kManifoldNone: return ambient;
-    case kManifoldSubset: return ambient - __builtin_popcount(static_cast<unsigned>(param));
+    case kManifoldSubset:
+    case kManifoldSubsetAlias: return ambient - __builtin_popcount(static_cast<unsigned>(param));
     case kManifoldQuaternion:
     case kManifoldEigenQuaternion: return 3;
     default: return ambient - 1;
@@ -285,6 +287,7 @@ static void ManifoldPlusJacobian(int kind, int param, int ambient, const double*
   const int tangent = ManifoldTangentSize(kind, param, ambient);
   std::fill(J, J + ambient * tangent, 0.0);
   switch (kind) {
+    case kManifoldSubsetAlias:
     case kManifoldSubset: {
       // manifold.cc:199-214
       for (int r = 0, c = 0; r < ambient; ++r)
@@ -343,6 +346,7 @@ static void ManifoldPlus(int kind, int param, int ambient, const double* x,
     case kManifoldNone:
       for (int i = 0; i < ambient; ++i) out[i] = x[i] + delta[i];
       return;
+    case kManifoldSubsetAlias:
     case kManifoldSubset:
       // manifold.cc:184-197
       for (int i = 0, j = 0; i < ambient; ++i)

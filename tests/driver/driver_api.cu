@@ -8,8 +8,22 @@ using driver::DriverProblem;
 using ceres::internal::Evaluator;
 
 namespace {
+// A SubsetManifold the device is not told about: exercises the generic path
+// (Manifold::PlusJacobian on the host every Evaluate + plus-Jacobian pool upload).
+class OpaqueSubsetManifold : public ceres::SubsetManifold {
+ public:
+  using ceres::SubsetManifold::SubsetManifold;
+  bool DeviceDescription(int*, int*) const override { return false; }
+};
+
 ceres::Manifold* MakeManifold(int kind, int param, int size) {
   switch (kind) {
+    case 6: {
+      std::vector<int> constant;
+      for (int i = 0; i < size; ++i)
+        if ((param >> i) & 1) constant.push_back(i);
+      return new OpaqueSubsetManifold(size, constant);
+    }
     case 1: {  // SubsetManifold, param = bitmask of constant coordinates
       std::vector<int> constant;
       for (int i = 0; i < size; ++i)

@@ -343,3 +343,49 @@ def test_golden_jet_operations_on_device():
         J = cp.dense_jacobian()
         assert np.allclose(r, want[:, 0], rtol=1e-13, atol=1e-300)
         assert np.allclose(J, want[:, 1:], rtol=1e-13, atol=1e-15)
+
+
+def test_generic_manifold_path_matches_device_manifold_path():
+    """A manifold the kernel does not know (plus-Jacobian from the host pool,
+    CB200_MANIFOLD_GENERIC) must give the same Jacobian as the device-side SubsetManifold."""
+    spec = P.bal_problem(10, 150, 600, seed=12, subset_manifold=True)
+    opaque = P.ProblemSpec(
+        pb_size=spec.pb_size, pb_values=spec.pb_values, rb_type=spec.rb_type, rb_pb=spec.rb_pb,
+        fdata=spec.fdata, pb_constant=spec.pb_constant,
+        pb_manifold_kind=np.where(spec.pb_manifold_kind == P.MANIFOLD_SUBSET,
+                                  P.MANIFOLD_OPAQUE_SUBSET, spec.pb_manifold_kind),
+        pb_manifold_param=spec.pb_manifold_param, rb_loss_kind=spec.rb_loss_kind,
+        rb_loss_a=spec.rb_loss_a, rb_loss_b=spec.rb_loss_b,
+        num_eliminate_blocks=spec.num_eliminate_blocks)
+    for fmt in (0, 1):
+        _check(opaque, fmt)
+        _check(spec, fmt)
+
+
+def test_subset_manifold_with_several_fixed_coordinates():
+    spec = P.bal_problem(10, 150, 600, seed=13, subset_manifold=True)
+    spec.pb_manifold_param[spec.pb_manifold_kind == P.MANIFOLD_SUBSET] = 0b101000010
+    for fmt in (0, 1):
+        _check(spec, fmt)
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_pose_graph_3d_error_term(fmt):
+    """<6, 3, 4, 3, 4> with EigenQuaternionManifold on the rotations (two derivative
+    passes, four parameter blocks, 344-byte functor kept in global memory)."""
+    rng = np.random.default_rng(21)
+    n = 60
+    b = P.ProblemBuilder()
+    ps, qs = [], []
+    for i in range(n):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        ps.append(b.add_parameter_block(rng.normal(size=3)))
+        qs.append(b.add_parameter_block(q, manifold=(P.MANIFOLD_EIGEN_QUATERNION, 0)))
+    b.set_constant(ps[0]); b.set_constant(qs[0])
+    for e in range(200):
+        i, j = rng.choice(n, 2, replace=False)
+        mq = rng.normal(size=4); mq /= np.linalg.norm(mq)
+        S = np.eye(6) + 0.1 * rng.normal(size=(6, 6))
+        d = np.concatenate([rng.normal(size=3), mq, S.ravel()])
+        b.add_residual_block(P.POSE_GRAPH_3D, [ps[i], qs[i], ps[j], qs[j]], d)
+    _check(b.build(), fmt)
