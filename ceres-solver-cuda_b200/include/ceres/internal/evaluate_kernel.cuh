@@ -325,12 +325,22 @@ struct SmemPlan {
   // per warp: every argument's cells side by side (Jacobian staging) ...
   static constexpr int kJacobianDoubles = 32 * kRes * Dims::kNumParameters;
   // ... and one padded row per lane for the staged gradient reductions
-  static constexpr int kGradientDoubles = 32 * StagePitch(Dims::MaxSize());
+  // the staged gradient reductions reuse the Jacobian staging buffer: with a single
+  // derivative pass every gradient is out before the first cell is staged.
+  static constexpr bool kGradientAliasesJacobian =
+      PassPlan<kRes, Ns...>::kNumPasses == 1 &&
+      32 * StagePitch(Dims::MaxSize()) <= kJacobianDoubles;
+  static constexpr int kGradientDoubles =
+      kGradientAliasesJacobian ? 0 : 32 * StagePitch(Dims::MaxSize());
   static constexpr int kWarps = kEvaluateThreads / 32;
   static constexpr bool kStageJacobian =
       CB200_KERNEL_STAGE_JACOBIAN &&
       (kPrefetchBytes + kWarps * (kJacobianDoubles + kGradientDoubles) * 8 <= 72 * 1024);
-  static constexpr int kWarpDoubles = (kStageJacobian ? kJacobianDoubles : 0) + kGradientDoubles;
+  static constexpr int kGradientOffset =
+      (kStageJacobian && !kGradientAliasesJacobian) ? kJacobianDoubles : 0;
+  static constexpr int kWarpDoubles =
+      kStageJacobian ? kJacobianDoubles + kGradientDoubles
+                     : 32 * StagePitch(Dims::MaxSize());
   static constexpr int kJetBytes = kPrefetchBytes + kWarps * kWarpDoubles * 8;
   static constexpr int kCostBytes = kPrefetchBytes > 0 ? kPrefetchBytes : 16;
 };
@@ -373,7 +383,7 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
   double* const wbuf = reinterpret_cast<double*>(smem + Smem::kPrefetchBytes) +
                        (threadIdx.x >> 5) * Smem::kWarpDoubles;
   double* const jbuf = wbuf;                                              // Jacobian staging
-  double* const gbuf = wbuf + (kStage ? Smem::kJacobianDoubles : 0);      // gradient staging
+  double* const gbuf = wbuf + Smem::kGradientOffset;                      // gradient staging
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -620,12 +630,6 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
           }
         }
       }
-      // The staging buffer may still be read by last iteration's bulk stores.
-      if (kStage && bulk_pending) {
-        if (lane == 0) BulkWaitRead();
-        __syncwarp();
-        bulk_pending = false;
-      }
       bool bulk_issued = false;
 
       double sqrt_rho1 = 1.0, residual_scaling = 1.0, alpha_sq_norm = 0.0;
@@ -694,8 +698,22 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
           for (int r = 0; r < kRes; ++r) res_corrected[r] = res[r] * residual_scaling;
         }
 
-        // Per parameter block of this pass: project, correct, gradient, scatter.
-        auto epilogue = [&](auto jc) {
+        // The staging buffer may still be read by last iteration's bulk stores: wait
+        // here, after the functor, so the copy has the whole evaluation to complete.
+        if (p == 0 && kStage && bulk_pending) {
+          if (lane == 0) BulkWaitRead();
+          __syncwarp();
+          bulk_pending = false;
+        }
+
+        // Per parameter block of this pass, in three sweeps so that the gradient staging
+        // can reuse the Jacobian staging buffer: (1) project onto the tangent space and
+        // apply the loss correction in place, (2) gradient, (3) scatter.
+        unsigned live[kNB];  // ambient columns that are tangent columns, per argument
+#pragma unroll
+        for (int j = 0; j < kNB; ++j) live[j] = 0u;
+
+        auto prepare = [&](auto jc) {
           constexpr int j = decltype(jc)::value;
           if constexpr (j >= kFirst && j < kEnd) {
             constexpr int kSize = Dims::Size(j);
@@ -707,12 +725,10 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
             for (int r = 0; r < kRes; ++r)
 #pragma unroll
               for (int c = 0; c < kSize; ++c) B[r][c] = out[r].v[kLane0 + c];
-
-            // live: ambient columns of B that are tangent columns, in order.
-            unsigned live = kAll;
+            unsigned lv = kAll;
             if constexpr (kGeneric) {
               if (kind[j] == CB200_MANIFOLD_SUBSET) {
-                live = kAll & ~static_cast<unsigned>(mparam[j]);  // column selection
+                lv = kAll & ~static_cast<unsigned>(mparam[j]);  // column selection
               } else if (kind[j] == CB200_MANIFOLD_QUATERNION_TAIL ||
                          kind[j] == CB200_MANIFOLD_EIGEN_QUATERNION_TAIL) {
                 if constexpr (kSize >= 4) {
@@ -736,129 +752,152 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
 #pragma unroll
                     for (int c = 3; c + 1 < kSize; ++c) B[r][c] = B[r][c + 1];
                   }
-                  live = kAll >> 1;
+                  lv = kAll >> 1;
                 }
               } else if (kind[j] == CB200_MANIFOLD_GENERIC && active) {
                 BlockEpilogue<kRes, kSize>::MultiplyPlusJacobian(
                     B, a.plus_jacobians + plus_off[j], tangent[j]);
-                live = tangent[j] >= 32 ? 0xffffffffu : ((1u << tangent[j]) - 1u);
+                lv = tangent[j] >= 32 ? 0xffffffffu : ((1u << tangent[j]) - 1u);
               }
             }
-            auto dcol = [&](int c) -> int {
-              return kGeneric ? __popc(live & ((1u << c) - 1u)) : c;
-            };
-            auto is_live = [&](int c) -> bool { return kGeneric ? ((live >> c) & 1u) : true; };
-            const int tan = kGeneric ? tangent[j] : kSize;
-
+            live[j] = lv;
             if (correct)
               BlockEpilogue<kRes, kSize>::Correct(B, res, sqrt_rho1, alpha_sq_norm);
+#pragma unroll
+            for (int r = 0; r < kRes; ++r)
+#pragma unroll
+              for (int c = 0; c < kSize; ++c) out[r].v[kLane0 + c] = B[r][c];
+          }
+        };
 
-            if (a.output_gradient) {
-              double g[kSize];
+        auto gradient = [&](auto jc) {
+          constexpr int j = decltype(jc)::value;
+          if constexpr (j >= kFirst && j < kEnd) {
+            constexpr int kSize = Dims::Size(j);
+            constexpr int kLane0 = Plan::Lane(j, 0);
+            constexpr unsigned kAll = kSize >= 32 ? 0xffffffffu : ((1u << kSize) - 1u);
+            const bool active = kGeneric ? delta_off[j] >= 0 : true;
+            const unsigned lv = kGeneric ? live[j] : kAll;
+            double g[kSize];
 #pragma unroll
-              for (int c = 0; c < kSize; ++c) {
-                double acc = 0.0;
+            for (int c = 0; c < kSize; ++c) {
+              double acc = 0.0;
 #pragma unroll
-                for (int r = 0; r < kRes; ++r) acc += B[r][c] * res_corrected[r];
-                g[c] = acc;
-              }
-              // Long runs of consecutive blocks sharing this parameter block (few distinct
-              // blocks in the warp) are summed in the warp first, so one lane per run adds
-              // to memory.  Short runs (the 3-10 observations of a BAL point) go out
-              // directly: lanes of one red instruction that hit the same sector share one
-              // L2 request, which is cheaper than 5 shuffle steps per value.
-              const int k_ = (valid && active) ? key[j] : -1 - lane;
-              const int prev_key = __shfl_up_sync(0xffffffffu, k_, 1);
-              bool head = (lane == 0) || (prev_key != k_);
-              const unsigned heads = __ballot_sync(0xffffffffu, head);
-              if (__popc(heads) <= 4) {
-#pragma unroll
-                for (int c = 0; c < kSize; ++c) g[c] = (valid && ok && active) ? g[c] : 0.0;
-                const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
-                const int run_end = above ? __ffs(above) - 1 : 32;
-                WarpSegmentedSum<kSize>(run_end, g, lane);
-              } else {
-                head = true;  // every lane adds its own contribution
-              }
-              const bool emit = head && valid && ok && active;
-              const unsigned emit_mask = __ballot_sync(0xffffffffu, emit);
-              if (CB200_KERNEL_STAGE_GRADIENT && __popc(emit_mask) >= 12) {
-                // Most lanes own a distinct block (the cameras of a BAL warp): stage the
-                // per-lane sums and let consecutive lanes add to consecutive addresses, so
-                // one red instruction touches a few sectors instead of 32.
-                constexpr int kPitch = StagePitch(kSize);
-#pragma unroll
-                for (int c = 0; c < kSize; ++c) gbuf[lane * kPitch + c] = g[c];
-                __syncwarp();
-#pragma unroll
-                for (int it = 0; it < kSize; ++it) {
-                  const int e = it * 32 + lane;
-                  const int row = e / kSize;
-                  const int c = e - row * kSize;
-                  const int d = __shfl_sync(0xffffffffu, delta_off[j], row);
-                  const unsigned lv = kGeneric ? __shfl_sync(0xffffffffu, live, row) : kAll;
-                  if (((emit_mask >> row) & 1u) && ((lv >> c) & 1u))
-                    RedAdd(a.gradient + d + (kGeneric ? __popc(lv & ((1u << c) - 1u)) : c),
-                           gbuf[row * kPitch + c]);
-                }
-                __syncwarp();
-              } else if (emit) {
-                double* __restrict__ dst = a.gradient + delta_off[j];
-#pragma unroll
-                for (int c = 0; c < kSize; ++c)
-                  if (is_live(c)) RedAdd(dst + dcol(c), g[c]);
-              }
+              for (int r = 0; r < kRes; ++r) acc += out[r].v[kLane0 + c] * res_corrected[r];
+              g[c] = acc;
             }
+            // Long runs of consecutive blocks sharing this parameter block (few distinct
+            // blocks in the warp) are summed in the warp first, so one lane per run adds
+            // to memory.  Short runs (the 3-10 observations of a BAL point) go out
+            // directly: lanes of one red instruction that hit the same sector share one
+            // L2 request, which is cheaper than 5 shuffle steps per value.
+            const int k_ = (valid && active) ? key[j] : -1 - lane;
+            const int prev_key = __shfl_up_sync(0xffffffffu, k_, 1);
+            bool head = (lane == 0) || (prev_key != k_);
+            const unsigned heads = __ballot_sync(0xffffffffu, head);
+            if (__popc(heads) <= 4) {
+#pragma unroll
+              for (int c = 0; c < kSize; ++c) g[c] = (valid && ok && active) ? g[c] : 0.0;
+              const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+              const int run_end = above ? __ffs(above) - 1 : 32;
+              WarpSegmentedSum<kSize>(run_end, g, lane);
+            } else {
+              head = true;  // every lane adds its own contribution
+            }
+            const bool emit = head && valid && ok && active;
+            const unsigned emit_mask = __ballot_sync(0xffffffffu, emit);
+            if (CB200_KERNEL_STAGE_GRADIENT && __popc(emit_mask) >= 12) {
+              // Most lanes own a distinct block (the cameras of a BAL warp): stage the
+              // per-lane sums and let consecutive lanes add to consecutive addresses, so
+              // one red instruction touches a few sectors instead of 32.
+              constexpr int kPitch = StagePitch(kSize);
+#pragma unroll
+              for (int c = 0; c < kSize; ++c) gbuf[lane * kPitch + c] = g[c];
+              __syncwarp();
+#pragma unroll
+              for (int it = 0; it < kSize; ++it) {
+                const int e = it * 32 + lane;
+                const int row = e / kSize;
+                const int c = e - row * kSize;
+                const int d = __shfl_sync(0xffffffffu, delta_off[j], row);
+                const unsigned lr = kGeneric ? __shfl_sync(0xffffffffu, lv, row) : kAll;
+                if (((emit_mask >> row) & 1u) && ((lr >> c) & 1u))
+                  RedAdd(a.gradient + d + (kGeneric ? __popc(lr & ((1u << c) - 1u)) : c),
+                         gbuf[row * kPitch + c]);
+              }
+              __syncwarp();
+            } else if (emit) {
+              double* __restrict__ dst = a.gradient + delta_off[j];
+#pragma unroll
+              for (int c = 0; c < kSize; ++c)
+                if (!kGeneric || ((lv >> c) & 1u))
+                  RedAdd(dst + (kGeneric ? __popc(lv & ((1u << c) - 1u)) : c), g[c]);
+            }
+          }
+        };
 
-            if (a.output_jacobian) {
-              const int row_stride = a.crs ? row_stride_crs : tan;
-              if (kStage && (bulk_arg[j] || bulk_all)) {
-                // Stage the cell exactly as it lies in global memory.
-                double* cell = bulk_all ? jbuf + (jpos[j] - bulk_all_base)
-                                        : jbuf + 32 * kRes * Dims::Offset(j) + lane * kRes * tan;
-                if (!kGeneric && !a.crs && (kRes * kSize) % 2 == 0) {
-                  double2* mine = reinterpret_cast<double2*>(cell);  // conflict-free 128-bit
+        auto scatter = [&](auto jc) {
+          constexpr int j = decltype(jc)::value;
+          if constexpr (j >= kFirst && j < kEnd) {
+            constexpr int kSize = Dims::Size(j);
+            constexpr int kLane0 = Plan::Lane(j, 0);
+            constexpr unsigned kAll = kSize >= 32 ? 0xffffffffu : ((1u << kSize) - 1u);
+            const bool active = kGeneric ? delta_off[j] >= 0 : true;
+            const unsigned lv = kGeneric ? live[j] : kAll;
+            auto dcol = [&](int c) -> int { return kGeneric ? __popc(lv & ((1u << c) - 1u)) : c; };
+            auto is_live = [&](int c) -> bool { return kGeneric ? ((lv >> c) & 1u) : true; };
+            const int tan = kGeneric ? tangent[j] : kSize;
+            const int row_stride = a.crs ? row_stride_crs : tan;
+            if (kStage && (bulk_arg[j] || bulk_all)) {
+              // Stage the cell exactly as it lies in global memory.
+              double* cell = bulk_all ? jbuf + (jpos[j] - bulk_all_base)
+                                      : jbuf + 32 * kRes * Dims::Offset(j) + lane * kRes * tan;
+              if (!kGeneric && !a.crs && (kRes * kSize) % 2 == 0) {
+                double2* mine = reinterpret_cast<double2*>(cell);  // conflict-free 128-bit
 #pragma unroll
-                  for (int e = 0; e < kRes * kSize; e += 2)
-                    mine[e / 2] = make_double2(B[e / kSize][e % kSize],
-                                               B[(e + 1) / kSize][(e + 1) % kSize]);
-                } else {
+                for (int e = 0; e < kRes * kSize; e += 2)
+                  mine[e / 2] = make_double2(out[e / kSize].v[kLane0 + e % kSize],
+                                             out[(e + 1) / kSize].v[kLane0 + (e + 1) % kSize]);
+              } else {
 #pragma unroll
-                  for (int r = 0; r < kRes; ++r)
+                for (int r = 0; r < kRes; ++r)
 #pragma unroll
-                    for (int c = 0; c < kSize; ++c)
-                      if (is_live(c)) cell[r * row_stride + dcol(c)] = B[r][c];
-                }
-                if (bulk_arg[j]) {
-                  FenceProxyAsyncShared();
-                  __syncwarp();
-                  if (lane == 0)
-                    BulkStore(a.jacobian_values + bulk_base[j],
-                              jbuf + 32 * kRes * Dims::Offset(j), 32 * kRes * tan * 8);
-                  bulk_issued = true;
-                }
-              } else if (valid && active) {
-                double* __restrict__ dst = a.jacobian_values + jpos[j];
-                if (!kGeneric && row_stride == kSize && ((jpos[j] & 1) == 0) &&
-                    ((kRes * kSize) % 2 == 0)) {
-                  double2* __restrict__ d2 = reinterpret_cast<double2*>(dst);
+                  for (int c = 0; c < kSize; ++c)
+                    if (is_live(c)) cell[r * row_stride + dcol(c)] = out[r].v[kLane0 + c];
+              }
+              if (bulk_arg[j]) {
+                FenceProxyAsyncShared();
+                __syncwarp();
+                if (lane == 0)
+                  BulkStore(a.jacobian_values + bulk_base[j],
+                            jbuf + 32 * kRes * Dims::Offset(j), 32 * kRes * tan * 8);
+                bulk_issued = true;
+              }
+            } else if (valid && active) {
+              double* __restrict__ dst = a.jacobian_values + jpos[j];
+              if (!kGeneric && row_stride == kSize && ((jpos[j] & 1) == 0) &&
+                  ((kRes * kSize) % 2 == 0)) {
+                double2* __restrict__ d2 = reinterpret_cast<double2*>(dst);
 #pragma unroll
-                  for (int e = 0; e < kRes * kSize; e += 2)
-                    d2[e / 2] = make_double2(B[e / kSize][e % kSize],
-                                             B[(e + 1) / kSize][(e + 1) % kSize]);
-                } else {
+                for (int e = 0; e < kRes * kSize; e += 2)
+                  d2[e / 2] = make_double2(out[e / kSize].v[kLane0 + e % kSize],
+                                           out[(e + 1) / kSize].v[kLane0 + (e + 1) % kSize]);
+              } else {
 #pragma unroll
-                  for (int r = 0; r < kRes; ++r)
+                for (int r = 0; r < kRes; ++r)
 #pragma unroll
-                    for (int c = 0; c < kSize; ++c)
-                      if (is_live(c)) dst[r * row_stride + dcol(c)] = B[r][c];
-                }
+                  for (int c = 0; c < kSize; ++c)
+                    if (is_live(c)) dst[r * row_stride + dcol(c)] = out[r].v[kLane0 + c];
               }
             }
           }
         };
-        if (a.output_jacobian || a.output_gradient)
-          ForEachBlock(epilogue, std::make_index_sequence<kNB>{});
+
+        if (a.output_jacobian || a.output_gradient) {
+          ForEachBlock(prepare, std::make_index_sequence<kNB>{});
+          if (a.output_gradient) ForEachBlock(gradient, std::make_index_sequence<kNB>{});
+          if (a.output_jacobian) ForEachBlock(scatter, std::make_index_sequence<kNB>{});
+        }
       };
       ForEachBlock(pass, std::make_index_sequence<Plan::kNumPasses>{});
 
