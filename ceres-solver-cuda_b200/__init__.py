@@ -5,3 +5,4 @@ workloads (``problems``) and binds the test driver / C ABI for pytest and bench.
 (``binding``)."""
 from . import problems  # noqa: F401
 from . import binding  # noqa: F401
+from . import lm  # noqa: F401

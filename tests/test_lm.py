@@ -1,0 +1,43 @@
+"""A full Levenberg-Marquardt solve driven by the evaluator (ceres-solver-cuda_b200/lm.py):
+CPU test with the oracle as evaluator (host logic), GPU test with the CUDA evaluator, both
+converging to the same final cost."""
+import numpy as np
+import pytest
+
+import oracle_py as O
+from ceres_b200 import binding as B, lm, problems as P
+
+
+def _problem(seed=31):
+    spec = P.bal_problem(12, 600, 2600, seed=seed)
+    # start away from the optimum so LM has work to do
+    rng = np.random.default_rng(seed)
+    spec.pb_values[:] += rng.normal(0, 0.02, spec.pb_values.size) * (np.abs(spec.pb_values) < 50)
+    return spec
+
+
+def test_lm_with_oracle_evaluator_converges():
+    spec = _problem()
+    op = O.OracleProblem(spec, jacobian_format=1)
+    out = lm.solve(op, max_num_iterations=15)
+    costs = [h["cost"] for h in out["iterations"] if h["accepted"]]
+    assert out["cost"] < 0.2 * out["initial_cost"]
+    assert all(b <= a for a, b in zip(costs, costs[1:]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("subset_manifold", [False, True])
+def test_lm_cuda_evaluator_reaches_the_same_cost(subset_manifold):
+    spec = _problem()
+    if subset_manifold:
+        ncam = spec.meta["num_cameras"]
+        spec.pb_manifold_kind[-ncam:] = P.MANIFOLD_SUBSET
+        spec.pb_manifold_param[-ncam:] = 0b1000001   # hold rx and focal fixed
+    op = O.OracleProblem(spec, jacobian_format=1)
+    cp = B.CudaProblem(spec, jacobian_format=1)
+    ref = lm.solve(op, max_num_iterations=15)
+    out = lm.solve(cp, max_num_iterations=15)
+    assert out["cost"] < 0.2 * out["initial_cost"]
+    assert len(out["iterations"]) == len(ref["iterations"])
+    assert abs(out["cost"] - ref["cost"]) <= 1e-8 * ref["cost"]
+    assert np.max(np.abs(out["x"] - ref["x"])) <= 1e-6 * np.max(np.abs(ref["x"]))
