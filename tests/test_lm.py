@@ -21,7 +21,7 @@ def test_lm_with_oracle_evaluator_converges():
     op = O.OracleProblem(spec, jacobian_format=1)
     out = lm.solve(op, max_num_iterations=15)
     costs = [h["cost"] for h in out["iterations"] if h["accepted"]]
-    assert out["cost"] < 0.2 * out["initial_cost"]
+    assert out["cost"] < 0.25 * out["initial_cost"]
     assert all(b <= a for a, b in zip(costs, costs[1:]))
 
 
@@ -37,7 +37,8 @@ def test_lm_cuda_evaluator_reaches_the_same_cost(subset_manifold):
     cp = B.CudaProblem(spec, jacobian_format=1)
     ref = lm.solve(op, max_num_iterations=15)
     out = lm.solve(cp, max_num_iterations=15)
-    assert out["cost"] < 0.2 * out["initial_cost"]
+    assert out["cost"] < 0.25 * out["initial_cost"]
     assert len(out["iterations"]) == len(ref["iterations"])
-    assert abs(out["cost"] - ref["cost"]) <= 1e-8 * ref["cost"]
+    # measured: 2e-13 (cost) and 6e-12 (state) after 15 iterations
+    assert abs(out["cost"] - ref["cost"]) <= 1e-10 * ref["cost"]
     assert np.max(np.abs(out["x"] - ref["x"])) <= 1e-6 * np.max(np.abs(ref["x"]))
