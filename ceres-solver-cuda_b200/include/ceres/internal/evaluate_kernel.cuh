@@ -62,6 +62,12 @@ struct BlockDims {
     for (int i = 0; i < j; ++i) o += Size(i);
     return o;
   }
+  // sum over the blocks before j of their size rounded up to odd (shared-memory pitch)
+  __host__ __device__ static constexpr int PitchBefore(int j) {
+    int o = 0;
+    for (int i = 0; i < j; ++i) o += Size(i) | 1;
+    return o;
+  }
   __host__ __device__ static constexpr int MaxSize() {
     int m = 0;
     for (int i = 0; i < kNumBlocks; ++i) m = Size(i) > m ? Size(i) : m;
@@ -200,6 +206,9 @@ __device__ __forceinline__ void CpAsyncWait() {
 #ifndef CB200_KERNEL_STAGE_JACOBIAN
 #define CB200_KERNEL_STAGE_JACOBIAN 1 // warp-staged, fully coalesced Jacobian stores
 #endif
+#ifndef CB200_KERNEL_COOP_GATHER
+#define CB200_KERNEL_COOP_GATHER 1    // warp-cooperative, sector-coalesced parameter gather
+#endif
 #ifndef CB200_KERNEL_BULK_STORE
 #define CB200_KERNEL_BULK_STORE 1     // staged cells leave through TMA bulk copies (UBLKCP)
 #endif
@@ -298,7 +307,11 @@ struct PassPlan {
 
 template <typename Functor, int kNumParameters, int kNumBlocks>
 struct PrefetchLayout {
-  static constexpr int kParamBytes = kNumParameters * 8;
+  // doubles per thread for the parameters; the cooperative gather pads every block to an
+  // odd pitch (at most one extra double per block) so both its writes and the owner
+  // lane's reads are bank-conflict free
+  static constexpr int kParamBytes =
+      (kNumParameters + (CB200_KERNEL_COOP_GATHER ? kNumBlocks : 0)) * 8;
   // Per-block int tables that travel with the parameters: [delta offset or block id]
   // and [Jacobian position] per argument, residual position, CRS row stride, loss index.
   static constexpr int kIntSlots = 2 * kNumBlocks + 3;
@@ -394,6 +407,7 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
   const int cta_first = blockIdx.x * kEvaluateThreads;
   const int iterations = cta_first < n ? (n - cta_first + stride - 1) / stride : 0;
 
+  constexpr int kPitchSum = Dims::PitchBefore(kNB);  // cooperative gather: odd pitches
   auto clamp = [&](int rb) { return rb < n ? rb : n - 1; };
   auto stage_params = [&](int stage) {
     return reinterpret_cast<double*>(smem + stage * Layout::kStageBytes);
@@ -415,12 +429,33 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
   auto prefetch = [&](int stage, int rb, const int (&soff)[kNB]) {
     if constexpr (kPrefetch) {
       double* dst = stage_params(stage);
+      if constexpr (CB200_KERNEL_COOP_GATHER) {
+        // The warp copies its 32 blocks of argument j as one stream of 32 * Size(j)
+        // doubles: consecutive lanes fetch consecutive doubles of a block, so a copy
+        // instruction touches ~Size(j)*8*32/32 sectors instead of 32 (one per lane).
+        // Shared layout per warp: [argument][lane][pitch], pitch odd.
+        double* wdst = dst + (tid >> 5) * 32 * kPitchSum;
 #pragma unroll
-      for (int j = 0; j < kNB; ++j) {
-        const double* __restrict__ src = a.state + soff[j];
+        for (int j = 0; j < kNB; ++j) {
+          const int kS = Dims::Size(j);  // constants after unrolling
+          const int kP = kS | 1;
 #pragma unroll
-        for (int i = 0; i < Dims::Size(j); ++i)
-          CpAsync8(dst + (Dims::Offset(j) + i) * kEvaluateThreads + tid, src + i);
+          for (int it = 0; it < kS; ++it) {
+            const int e = it * 32 + lane;
+            const int owner = e / kS;
+            const int i = e - owner * kS;
+            const int so = __shfl_sync(0xffffffffu, soff[j], owner);
+            CpAsync8(wdst + 32 * Dims::PitchBefore(j) + owner * kP + i, a.state + so + i);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kNB; ++j) {
+          const double* __restrict__ src = a.state + soff[j];
+#pragma unroll
+          for (int i = 0; i < Dims::Size(j); ++i)
+            CpAsync8(dst + (Dims::Offset(j) + i) * kEvaluateThreads + tid, src + i);
+        }
       }
       // The int tables of the block (consumed in the epilogue, from shared memory, so
       // no register is held across the functor).
@@ -488,6 +523,7 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
     load_offsets(rb + 2 * stride, soff_next);
 
     CpAsyncWait<1>();  // this thread's copies for `stage` have landed
+    if constexpr (kPrefetch && CB200_KERNEL_COOP_GATHER) __syncwarp();  // ... and its warp's
 
     // Per-block int tables: from the prefetched stage (or straight from global memory
     // when the parameters do not fit in shared memory).
@@ -538,7 +574,10 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
 
     const double* sp = stage_params(stage);
     auto param = [&](int j, int i) -> double {
-      if constexpr (kPrefetch) {
+      if constexpr (kPrefetch && CB200_KERNEL_COOP_GATHER) {
+        return sp[(tid >> 5) * 32 * kPitchSum + 32 * Dims::PitchBefore(j) +
+                  lane * (Dims::Size(j) | 1) + i];
+      } else if constexpr (kPrefetch) {
         return sp[(Dims::Offset(j) + i) * kEvaluateThreads + tid];
       } else {
         return __ldg(a.state + soff_cur[j] + i);
