@@ -45,6 +45,9 @@ struct NcclApi {
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, /* ncclUniqueId by value */ Uid, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -68,6 +71,11 @@ NcclApi* GetNccl() {
       api.AllReduce =
           reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(
               dlsym(api.handle, "ncclAllReduce"));
+      api.Broadcast =
+          reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(
+              dlsym(api.handle, "ncclBroadcast"));
+      api.GroupStart = reinterpret_cast<int (*)()>(dlsym(api.handle, "ncclGroupStart"));
+      api.GroupEnd = reinterpret_cast<int (*)()>(dlsym(api.handle, "ncclGroupEnd"));
       api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(api.handle, "ncclCommDestroy"));
       api.GetErrorString =
           reinterpret_cast<const char* (*)(int)>(dlsym(api.handle, "ncclGetErrorString"));
@@ -102,6 +110,14 @@ struct DeviceBuffer {
 
 struct Segment {
   int64_t global_begin, length, local_begin;
+};
+
+// One interval of the gradient in the exchange plan: owner >= 0 means only that rank's
+// residual blocks touch these entries (its values are broadcast), owner < 0 means several
+// ranks contribute (all-reduce).
+struct GradientInterval {
+  int64_t begin, length;
+  int32_t owner;
 };
 
 struct ResidualType {
@@ -163,6 +179,8 @@ struct cb200_engine {
   int32_t rb_begin = 0, rb_end = 0, res_begin = 0, res_end = 0;
   std::vector<Segment> segments;
   int64_t local_jacobian_values = 0;
+  // Gradient exchange plan (empty = one all-reduce over [gradient | cost]).
+  std::vector<GradientInterval> exchange;
 
   std::vector<ResidualType*> types;
 
@@ -351,6 +369,52 @@ int cb200_engine_finalize(cb200_engine* e) {
     table[8 * i + 3] = constant ? CB200_MANIFOLD_NONE : b.manifold_kind;
     table[8 * i + 4] = b.manifold_param;
     table[8 * i + 5] = constant ? -1 : b.plus_jacobian_offset;
+  }
+
+  // Gradient exchange plan.  After a Schur ordering the residual blocks of one point
+  // are consecutive, so all but a handful of gradient entries are touched by a single
+  // rank: those need no reduction, only distribution.  Every rank sees the whole
+  // problem here, so all ranks derive the same plan without communicating.
+  e->exchange.clear();
+  if (e->world > 1 && e->num_active > 0) {
+    std::vector<int32_t> bound(e->world + 1);
+    for (int r = 0; r <= e->world; ++r) bound[r] = static_cast<int32_t>(nrb * r / e->world);
+    std::vector<int16_t> lo(e->num_active, INT16_MAX), hi(e->num_active, -1);
+    for (ResidualType* t : e->types) {
+      const int nb = t->desc.num_parameter_blocks;
+      for (size_t k = 0; k < t->position.size(); ++k) {
+        const int32_t p = t->position[k];
+        if (p < 0 || p >= nrb) continue;  // reported below
+        int r = static_cast<int>(static_cast<int64_t>(p) * e->world / std::max<int64_t>(nrb, 1));
+        while (r > 0 && p < bound[r]) --r;
+        while (r + 1 < e->world && p >= bound[r + 1]) ++r;
+        for (int j = 0; j < nb; ++j) {
+          const int32_t id = t->pb_ids[k * nb + j];
+          if (id < 0 || id >= e->num_active) continue;
+          lo[id] = std::min<int16_t>(lo[id], static_cast<int16_t>(r));
+          hi[id] = std::max<int16_t>(hi[id], static_cast<int16_t>(r));
+        }
+      }
+    }
+    // Active blocks are in delta_offset order: merge neighbours of the same class.
+    std::vector<GradientInterval> plan;
+    for (int i = 0; i < e->num_active; ++i) {
+      const cb200_parameter_block& b = e->blocks[i];
+      if (b.tangent_size == 0) continue;
+      int32_t owner = hi[i] < 0 ? 0 : (lo[i] == hi[i] ? lo[i] : -1);  // untouched: zeros from rank 0
+      if (!plan.empty() && plan.back().owner == owner &&
+          plan.back().begin + plan.back().length == b.delta_offset) {
+        plan.back().length += b.tangent_size;
+      } else if (!plan.empty() && hi[i] < 0 &&
+                 plan.back().begin + plan.back().length == b.delta_offset) {
+        plan.back().length += b.tangent_size;  // untouched entries ride with their neighbour
+      } else {
+        plan.push_back(GradientInterval{b.delta_offset, b.tangent_size, owner});
+      }
+    }
+    int64_t covered = 0;
+    for (const auto& g : plan) covered += g.length;
+    if (plan.size() <= 96 && covered == e->num_effective) e->exchange.swap(plan);
   }
 
   // Pass 1: per type, pick this rank's blocks and find what part of the values
@@ -592,11 +656,37 @@ static int EvaluateOnDevice(cb200_engine* e, uint32_t flags, bool want_r, bool w
   }
   if (e->comm && e->world > 1) {
     NcclApi* n = GetNccl();
-    // One all-reduce over [gradient | cost]; cost-only evaluations reduce 1 double.
-    double* buf = want_g ? e->d_gradcost.ptr : e->d_gradcost.ptr + e->num_effective;
-    const size_t count = want_g ? static_cast<size_t>(e->num_effective) + 1 : 1;
-    const int r = n->AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, e->comm, s);
-    if (r != 0) return e->Fail(CB200_ERROR_NCCL, "ncclAllReduce failed (%d)", r);
+    double* g = e->d_gradcost.ptr;
+    double* cost_slot = g + e->num_effective;
+    int r = 0;
+    if (!want_g) {
+      // cost-only evaluation: one double
+      r = n->AllReduce(cost_slot, cost_slot, 1, kNcclFloat64, kNcclSum, e->comm, s);
+    } else if (e->exchange.empty() || !n->Broadcast || !n->GroupStart || !n->GroupEnd ||
+               getenv("CB200_FORCE_ALLREDUCE")) {
+      // one all-reduce over [gradient | cost]
+      r = n->AllReduce(g, g, static_cast<size_t>(e->num_effective) + 1, kNcclFloat64, kNcclSum,
+                       e->comm, s);
+    } else {
+      // Exchange plan: entries owned by one rank are broadcast from it, shared entries
+      // (the cameras of a BAL problem, boundary points) are all-reduced; the cost rides
+      // with the last shared interval when it is adjacent, else on its own.
+      n->GroupStart();
+      bool cost_done = false;
+      for (const GradientInterval& iv : e->exchange) {
+        size_t len = static_cast<size_t>(iv.length);
+        if (iv.owner >= 0) {
+          r |= n->Broadcast(g + iv.begin, g + iv.begin, len, kNcclFloat64, iv.owner, e->comm, s);
+        } else {
+          if (iv.begin + iv.length == e->num_effective) { ++len; cost_done = true; }
+          r |= n->AllReduce(g + iv.begin, g + iv.begin, len, kNcclFloat64, kNcclSum, e->comm, s);
+        }
+      }
+      if (!cost_done)
+        r |= n->AllReduce(cost_slot, cost_slot, 1, kNcclFloat64, kNcclSum, e->comm, s);
+      r |= n->GroupEnd();
+    }
+    if (r != 0) return e->Fail(CB200_ERROR_NCCL, "NCCL collective failed (%d)", r);
   }
   CB200_CUDA(e, cudaEventRecord(e->ev[3], s));
   e->timing[3] = launches;

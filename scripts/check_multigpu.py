@@ -1,0 +1,42 @@
+"""Run under torchrun on N GPUs: evaluates a sharded problem (NCCL exchange of the
+gradient and cost) and checks every rank's result against an unsharded evaluation on the
+same GPU.  Prints one line per rank."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT]
+import numpy as np
+import torch, torch.distributed as dist
+import ceres_b200
+from ceres_b200 import binding as B, problems as P
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    buf.copy_(torch.frombuffer(bytearray(B.nccl_unique_id()), dtype=torch.uint8))
+dist.broadcast(buf, 0)
+nccl_id = bytes(buf.cpu().numpy().tobytes())
+scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.05
+for fmt, kw in ((0, {}), (1, {"subset_manifold": True})):
+    spec = P.bal_shape("L", scale=scale, **kw)
+    full = B.CudaProblem(spec, jacobian_format=fmt, device=local)
+    x = full.initial_state()
+    ok, c0, r0, g0, j0 = full.evaluate(x)
+    j0 = j0.copy()
+    sh = B.CudaProblem(spec, jacobian_format=fmt, device=local, rank=rank, world_size=world, nccl_id=nccl_id)
+    r = np.full(full.num_residuals, np.nan)
+    ok, c, r, g, j = sh.evaluate(x, out_residuals=r)
+    info = sh.shard_info()
+    e_cost = abs(c - c0) / abs(c0)
+    e_grad = np.max(np.abs(g - g0)) / np.max(np.abs(g0))
+    rs = slice(info["residual_begin"], info["residual_end"])
+    e_res = np.max(np.abs(r[rs] - r0[rs])) / np.max(np.abs(r0))
+    e_jac = max(np.max(np.abs(j[gb:gb + ln] - j0[gb:gb + ln])) for gb, ln, _ in info["segments"]) / np.max(np.abs(j0))
+    t = sh.timing()
+    print(f"rank {rank}/{world} fmt {fmt}: cost {e_cost:.1e} grad {e_grad:.1e} res {e_res:.1e} jac {e_jac:.1e} "
+          f"segments {len(info['segments'])} kernel {t['kernel_ms']:.3f} device {t['device_ms']:.3f} ms "
+          f"{'OK' if max(e_cost, e_grad) <= 1e-10 and max(e_res, e_jac) <= 1e-12 else 'MISMATCH'}", flush=True)
+    full.close(); sh.close()
+dist.barrier()
+dist.destroy_process_group()
