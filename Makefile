@@ -16,7 +16,9 @@ HDRS := $(wildcard include/*.h $(PKG)/include/ceres/*.h $(PKG)/include/ceres/int
 DRV_SRCS := driver_api driver_bal driver_pose driver_tests
 DRV_OBJS := $(patsubst %,build/driver/%.o,$(DRV_SRCS))
 
-all: $(LIB) $(DRV)
+EXAMPLE := build/examples/bundle_adjuster
+
+all: $(LIB) $(DRV) $(EXAMPLE)
 
 build/engine.o: $(PKG)/csrc/engine.cu $(HDRS)
 	@mkdir -p build
@@ -26,7 +28,11 @@ build/host.o: $(PKG)/csrc/host.cc $(HDRS)
 	@mkdir -p build
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
-$(LIB): build/engine.o build/host.o
+build/solver.o: $(PKG)/csrc/solver.cc $(HDRS)
+	@mkdir -p build
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(LIB): build/engine.o build/host.o build/solver.o
 	@mkdir -p $(PKG)/lib
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart -ldl
 
@@ -36,6 +42,10 @@ build/driver/%.o: tests/driver/%.cu tests/driver/driver.h tests/driver/test_func
 
 $(DRV): $(DRV_OBJS) $(LIB)
 	$(NVCC) $(ARCH) -shared -o $@ $(DRV_OBJS) -L$(PKG)/lib -lceres_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../../$(PKG)/lib' -lcudart
+
+$(EXAMPLE): $(PKG)/examples/bundle_adjuster.cu $(HDRS) $(wildcard $(PKG)/examples/*.h) $(LIB)
+	@mkdir -p build/examples
+	$(NVCC) $(NVFLAGS) -I$(PKG)/examples -o $@ $< -L$(PKG)/lib -lceres_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../../$(PKG)/lib' -lcudart
 
 clean:
 	rm -rf build $(LIB) $(DRV)

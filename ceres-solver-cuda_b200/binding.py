@@ -104,6 +104,9 @@ def driver():
         L.drv_shard_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.drv_plus.argtypes = [C.c_void_p] * 4
         L.drv_dense_jacobian.argtypes = [C.c_void_p, C.c_void_p]
+        L.drv_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.drv_user_values.argtypes = [C.c_void_p, C.c_void_p]
+        L.drv_options_is_valid.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         _DRV = L
     return _DRV
 
@@ -127,6 +130,52 @@ _INT_ARRAYS = {
     "cell_position": 11, "crs_rows": 12, "crs_cols": 13, "constant_pbs": 14,
     "jacobian_layout_storage": 15,
 }
+
+
+# ceres::LinearSolverType values (include/ceres/types.h of this repository)
+SPARSE_NORMAL_CHOLESKY, DENSE_SCHUR, SPARSE_SCHUR, ITERATIVE_SCHUR, CGNR = 2, 3, 4, 5, 6
+
+
+def solve(spec, linear_solver_type=ITERATIVE_SCHUR, max_num_iterations=20, ordering=None,
+          device=0, bulk=False):
+    """ceres::Solve(options, ProblemCUDA*, summary) (reference: problem_cuda.h:490-502) on
+    a ProblemSpec built through the per-block C++ API.  Returns a dict with the summary
+    and the solution in the specification's parameter-block order."""
+    L = driver()
+    h = L.drv_create(
+        spec.num_pb, _p(spec.pb_size), _p(spec.pb_values), _p(spec.pb_constant),
+        _p(spec.pb_manifold_kind), _p(spec.pb_manifold_param), spec.num_rb,
+        _p(spec.rb_type), _p(spec.rb_pb), _p(spec.rb_loss_kind), _p(spec.rb_loss_a),
+        _p(spec.rb_loss_b), _p(spec.fdata), int(bulk))
+    err = L.drv_error(h)
+    if err:
+        raise RuntimeError(err.decode())
+    out = np.zeros(8)
+    o = None if ordering is None else np.ascontiguousarray(ordering, dtype=np.int32)
+    ok = L.drv_solve(h, int(linear_solver_type), int(max_num_iterations), _p(o), int(device), _p(out))
+    x = np.zeros(spec.pb_values.size)
+    L.drv_user_values(h, _p(x))
+    msg = L.drv_error(h).decode()
+    L.drv_destroy(h)
+    return dict(usable=bool(ok), initial_cost=out[0], final_cost=out[1], iterations=int(out[2]),
+                successful_steps=int(out[3]), termination_type=int(out[4]),
+                jacobian_evaluations=int(out[5]), residual_evaluations=int(out[6]), message=msg,
+                x=x)
+
+
+def options_is_valid(spec, minimizer_type):
+    """Solver::Options::IsValid with use_cuda_for_evaluator (reference solver.cc:702-708).
+    Returns (valid, message)."""
+    L = driver()
+    h = L.drv_create(
+        spec.num_pb, _p(spec.pb_size), _p(spec.pb_values), _p(spec.pb_constant),
+        _p(spec.pb_manifold_kind), _p(spec.pb_manifold_param), spec.num_rb,
+        _p(spec.rb_type), _p(spec.rb_pb), _p(spec.rb_loss_kind), _p(spec.rb_loss_a),
+        _p(spec.rb_loss_b), _p(spec.fdata), 0)
+    msg = C.create_string_buffer(512)
+    ok = L.drv_options_is_valid(h, int(minimizer_type), msg, 512)
+    L.drv_destroy(h)
+    return bool(ok), msg.value.decode()
 
 
 class CudaProblem:

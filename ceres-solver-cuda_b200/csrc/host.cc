@@ -147,20 +147,25 @@ ResidualBlock* ProblemImpl::AddResidualBlock(int type, CostFunction* cost_functi
   }
   const char* f = static_cast<const char*>(functor);
   t.functors.insert(t.functors.end(), f, f + t.desc.functor_size);
-  // Deduplicate loss objects by address: the reference copies one loss object per
-  // residual block to the device (autodiff_residual_block_cuda_evaluator.h:96-133).
+  // Deduplicate loss objects by CONTENT: user code typically does
+  // `new HuberLossCUDA(1.0)` per residual block (examples/bundle_adjuster.cu.cc:323-324)
+  // and the reference then copies one loss object per block to the device
+  // (autodiff_residual_block_cuda_evaluator.h:96-133).  Loss functors are plain data
+  // evaluated by value on the device, so equal bytes mean the same loss.
   int loss_id = -1;
   if (!t.loss_objects.empty() && t.loss_objects.back() == loss) {
     loss_id = static_cast<int>(t.loss_objects.size()) - 1;
   } else {
-    for (size_t i = 0; i < t.loss_objects.size(); ++i)
-      if (t.loss_objects[i] == loss) { loss_id = static_cast<int>(i); break; }
-  }
-  if (loss_id < 0) {
-    t.loss_objects.push_back(loss);
-    const char* l = static_cast<const char*>(loss);
-    t.loss_table.insert(t.loss_table.end(), l, l + t.desc.loss_size);
-    loss_id = static_cast<int>(t.loss_objects.size()) - 1;
+    const std::string bytes(static_cast<const char*>(loss), t.desc.loss_size);
+    auto it = t.loss_by_bytes.find(bytes);
+    if (it != t.loss_by_bytes.end()) {
+      loss_id = it->second;
+    } else {
+      loss_id = static_cast<int>(t.loss_objects.size());
+      t.loss_objects.push_back(loss);
+      t.loss_table.insert(t.loss_table.end(), bytes.begin(), bytes.end());
+      t.loss_by_bytes.emplace(bytes, loss_id);
+    }
   }
   t.loss_index.push_back(loss_id);
   t.cost_functions.push_back(cost_function);

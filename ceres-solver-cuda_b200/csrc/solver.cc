@@ -1,0 +1,333 @@
+// Minimal TRUST_REGION driver around the CUDA evaluator; see ceres/solver.h for scope.
+#include "ceres/solver.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace ceres {
+namespace {
+
+double Seconds() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch())
+      .count();
+}
+
+// Solves (J'J + D^2) y = J'r with Jacobi-preconditioned conjugate gradients (CGNR);
+// stand-in for the reference's linear solvers.  Returns the iteration count.
+int SolveNormalEquations(const internal::SparseMatrix& J, const double* D2, const double* r,
+                         int max_iterations, double tolerance, std::vector<double>* y) {
+  const int n = J.num_cols(), m = J.num_rows();
+  std::vector<double> b(n, 0.0), res(n), z(n), p(n), Ap(n), tmp(m), precond(n);
+  J.LeftMultiplyAndAccumulate(r, b.data());
+  J.SquaredColumnNorm(precond.data());
+  for (int i = 0; i < n; ++i) precond[i] = 1.0 / (precond[i] + D2[i]);
+  y->assign(n, 0.0);
+  res = b;
+  double norm_b = 0.0;
+  for (int i = 0; i < n; ++i) norm_b += b[i] * b[i];
+  norm_b = std::sqrt(norm_b);
+  if (norm_b == 0.0) return 0;
+  double rho = 0.0;
+  int it = 0;
+  for (; it < max_iterations; ++it) {
+    for (int i = 0; i < n; ++i) z[i] = precond[i] * res[i];
+    double rho_new = 0.0;
+    for (int i = 0; i < n; ++i) rho_new += res[i] * z[i];
+    if (it == 0) {
+      p = z;
+    } else {
+      const double beta = rho_new / rho;
+      for (int i = 0; i < n; ++i) p[i] = z[i] + beta * p[i];
+    }
+    rho = rho_new;
+    std::fill(tmp.begin(), tmp.end(), 0.0);
+    J.RightMultiplyAndAccumulate(p.data(), tmp.data());
+    for (int i = 0; i < n; ++i) Ap[i] = D2[i] * p[i];
+    J.LeftMultiplyAndAccumulate(tmp.data(), Ap.data());
+    double pAp = 0.0;
+    for (int i = 0; i < n; ++i) pAp += p[i] * Ap[i];
+    if (!(pAp > 0.0)) break;
+    const double alpha = rho / pAp;
+    double norm_res = 0.0;
+    for (int i = 0; i < n; ++i) {
+      (*y)[i] += alpha * p[i];
+      res[i] -= alpha * Ap[i];
+      norm_res += res[i] * res[i];
+    }
+    if (std::sqrt(norm_res) <= tolerance * norm_b) { ++it; break; }
+  }
+  return it;
+}
+
+}  // namespace
+
+bool Solver::Options::IsValid(std::string* error) const {
+  // solver.cc:702-708: the CUDA evaluator supports TRUST_REGION only.
+  if (use_cuda_for_evaluator && minimizer_type != TRUST_REGION) {
+    *error = "Using CUDA for cost function evaluation is currently only supported for "
+             "TRUST_REGION minimizers.";
+    return false;
+  }
+  if (minimizer_type != TRUST_REGION) {
+    *error = "Only TRUST_REGION minimization is provided by this library.";
+    return false;
+  }
+  if (use_cuda_for_evaluator && registered_cuda_evaluators == nullptr) {
+    *error = "use_cuda_for_evaluator requires registered_cuda_evaluators (use "
+             "ceres::Solve(options, ProblemCUDA*, summary)).";
+    return false;
+  }
+  if (max_num_iterations < 0) { *error = "max_num_iterations < 0"; return false; }
+  return true;
+}
+
+std::string Solver::Summary::BriefReport() const {
+  char buf[256];
+  std::snprintf(buf, sizeof(buf), "Ceres Solver Report: Iterations: %d, Initial cost: %e, "
+                "Final cost: %e, Termination: %s",
+                num_successful_steps + num_unsuccessful_steps, initial_cost, final_cost,
+                termination_type == CONVERGENCE ? "CONVERGENCE"
+                : termination_type == NO_CONVERGENCE ? "NO_CONVERGENCE" : "FAILURE");
+  return buf;
+}
+
+std::string Solver::Summary::FullReport() const {
+  char buf[2048];
+  std::snprintf(
+      buf, sizeof(buf),
+      "\nSolver Summary (B200 evaluation engine)\n\n"
+      "                                     Original                  Reduced\n"
+      "Parameter blocks                 %12d             %12d\n"
+      "Parameters                       %12d             %12d\n"
+      "Effective parameters             %12d             %12d\n"
+      "Residual blocks                  %12d             %12d\n"
+      "Residuals                        %12d             %12d\n\n"
+      "Cost:\nInitial                          %e\nFinal                            %e\n"
+      "Change                           %e\n\n"
+      "Minimizer iterations             %12d\nSuccessful steps                 %12d\n"
+      "Unsuccessful steps               %12d\n\n"
+      "Time (in seconds):\nPreprocessor                     %12.6f\n\n"
+      "  Residual only evaluation       %12.6f (%d)\n"
+      "  Jacobian & residual evaluation %12.6f (%d)\n"
+      "  Linear solver                  %12.6f\n"
+      "Minimizer                        %12.6f\n\nTotal                            %12.6f\n\n"
+      "Termination:                     %s (%s)\n",
+      num_parameter_blocks, num_parameter_blocks_reduced, num_parameters, num_parameters_reduced,
+      num_effective_parameters, num_effective_parameters_reduced, num_residual_blocks,
+      num_residual_blocks_reduced, num_residuals, num_residuals_reduced, initial_cost, final_cost,
+      initial_cost - final_cost, num_successful_steps + num_unsuccessful_steps,
+      num_successful_steps, num_unsuccessful_steps, preprocessor_time_in_seconds,
+      residual_evaluation_time_in_seconds, num_residual_evaluations,
+      jacobian_evaluation_time_in_seconds, num_jacobian_evaluations,
+      linear_solver_time_in_seconds, minimizer_time_in_seconds, total_time_in_seconds,
+      termination_type == CONVERGENCE ? "CONVERGENCE"
+      : termination_type == NO_CONVERGENCE ? "NO_CONVERGENCE" : "FAILURE",
+      message.c_str());
+  return buf;
+}
+
+void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
+  const double start = Seconds();
+  *summary = Summary();
+  if (!options.IsValid(&summary->message)) {
+    summary->termination_type = FAILURE;
+    return;
+  }
+  if (!options.use_cuda_for_evaluator) {
+    summary->message = "This library only provides the CUDA evaluator: solve a ProblemCUDA "
+                       "with ceres::Solve(options, ProblemCUDA*, summary).";
+    return;
+  }
+  internal::ProblemImpl* impl = problem->mutable_impl();
+  summary->num_parameter_blocks = impl->NumParameterBlocks();
+  summary->num_parameters = impl->NumParameters();
+  summary->num_residual_blocks = impl->NumResidualBlocks();
+  summary->num_residuals = impl->NumResiduals();
+  for (const auto& pb : impl->parameter_blocks())
+    summary->num_effective_parameters += pb->TangentSize();
+
+  // ---- preprocessing (trust_region_preprocessor.cc:373-407)
+  internal::Program full(impl);
+  std::vector<double*> removed;
+  double fixed_cost = 0.0;
+  std::unique_ptr<internal::Program> program =
+      full.CreateReducedProgram(&removed, &fixed_cost, &summary->message);
+  if (!program) return;
+  summary->fixed_cost = fixed_cost;
+  if (program->NumParameterBlocks() == 0) {
+    summary->termination_type = CONVERGENCE;
+    summary->message = "Function tolerance reached. No non-constant parameter blocks found.";
+    summary->initial_cost = summary->final_cost = fixed_cost;
+    return;
+  }
+  const bool schur = options.linear_solver_type == DENSE_SCHUR ||
+                     options.linear_solver_type == SPARSE_SCHUR ||
+                     options.linear_solver_type == ITERATIVE_SCHUR;
+  int num_eliminate_blocks = 0;
+  if (schur && options.linear_solver_ordering) {
+    // ApplyOrdering + size of the first elimination group (reorder_program.cc:469-560).
+    program->ReorderParameterBlocksByGroup(options.linear_solver_ordering->element_to_group());
+    const int first = options.linear_solver_ordering->MinGroup();
+    for (const internal::ParameterBlock* pb : program->parameter_blocks())
+      num_eliminate_blocks += options.linear_solver_ordering->GroupId(pb->user_state) == first;
+    if (num_eliminate_blocks > 0 && num_eliminate_blocks < program->NumParameterBlocks())
+      program->LexicographicallyOrderResidualBlocks(num_eliminate_blocks);
+    else
+      num_eliminate_blocks = 0;
+  }
+  internal::Evaluator::Options eo;
+  eo.num_threads = options.num_threads;
+  eo.num_eliminate_blocks = num_eliminate_blocks;
+  eo.linear_solver_type = options.linear_solver_type;
+  eo.sparse_linear_algebra_library_type = options.sparse_linear_algebra_library_type;
+  eo.use_cuda = true;
+  eo.registered_cuda_evaluators = options.registered_cuda_evaluators;
+  eo.device = options.cuda_device;
+  std::unique_ptr<internal::Evaluator> evaluator =
+      internal::Evaluator::Create(eo, program.get(), &summary->message);
+  if (!evaluator) return;
+  std::unique_ptr<internal::SparseMatrix> jacobian = evaluator->CreateJacobian();
+  summary->num_parameter_blocks_reduced = program->NumParameterBlocks();
+  summary->num_parameters_reduced = program->NumParameters();
+  summary->num_effective_parameters_reduced = program->NumEffectiveParameters();
+  summary->num_residual_blocks_reduced = program->NumResidualBlocks();
+  summary->num_residuals_reduced = program->NumResiduals();
+  summary->preprocessor_time_in_seconds = Seconds() - start;
+
+  // ---- trust-region loop
+  const double minimizer_start = Seconds();
+  const int n = program->NumParameters(), ne = program->NumEffectiveParameters();
+  const int m = program->NumResiduals();
+  std::vector<double> x(n), x_plus(n), residuals(m), gradient(ne), scale(ne, 1.0);
+  std::vector<double> diagonal(ne), D2(ne), y, delta(ne), model(m);
+  program->ParameterBlocksToStateVector(x.data());
+  double cost = 0.0;
+  if (!evaluator->Evaluate(x.data(), &cost, residuals.data(), gradient.data(), jacobian.get())) {
+    summary->message = "Initial residual and Jacobian evaluation failed.";
+    return;
+  }
+  summary->initial_cost = cost + fixed_cost;
+  if (options.jacobi_scaling) {
+    jacobian->SquaredColumnNorm(scale.data());
+    for (double& s : scale) s = 1.0 / (1.0 + std::sqrt(s));
+    jacobian->ScaleColumns(scale.data());
+  }
+  double radius = options.initial_trust_region_radius, decrease_factor = 2.0;
+  bool reuse_diagonal = false;
+  summary->termination_type = NO_CONVERGENCE;
+  summary->message = "Maximum number of iterations reached.";
+  if (options.minimizer_progress_to_stdout)
+    std::printf("iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius  ls_iter\n"
+                "%4d  %.6e    %.2e   %.2e   %.2e  %.2e  %.2e   %5d\n",
+                0, cost + fixed_cost, 0.0, 0.0, 0.0, 0.0, radius, 0);
+  for (int it = 1; it <= options.max_num_iterations; ++it) {
+    if (Seconds() - start > options.max_solver_time_in_seconds) {
+      summary->message = "Maximum solver time reached.";
+      break;
+    }
+    if (!reuse_diagonal) {
+      jacobian->SquaredColumnNorm(diagonal.data());
+      for (double& d : diagonal)
+        d = std::min(std::max(d, options.min_lm_diagonal), options.max_lm_diagonal);
+    }
+    for (int i = 0; i < ne; ++i) D2[i] = diagonal[i] / radius;
+    const double ls_start = Seconds();
+    const int ls_iterations = SolveNormalEquations(*jacobian, D2.data(), residuals.data(),
+                                                   options.max_linear_solver_iterations,
+                                                   1e-2 * options.eta, &y);
+    summary->linear_solver_time_in_seconds += Seconds() - ls_start;
+    // step = -y (scaled space); model cost change = -m'(r + m/2), m = J step
+    std::fill(model.begin(), model.end(), 0.0);
+    for (int i = 0; i < ne; ++i) y[i] = -y[i];
+    jacobian->RightMultiplyAndAccumulate(y.data(), model.data());
+    double model_cost_change = 0.0, step_norm = 0.0, x_norm = 0.0;
+    for (int i = 0; i < m; ++i) model_cost_change -= model[i] * (residuals[i] + 0.5 * model[i]);
+    for (int i = 0; i < ne; ++i) { delta[i] = y[i] * scale[i]; step_norm += delta[i] * delta[i]; }
+    for (int i = 0; i < n; ++i) x_norm += x[i] * x[i];
+    step_norm = std::sqrt(step_norm);
+    IterationSummary is;
+    is.iteration = it;
+    is.linear_solver_iterations = ls_iterations;
+    is.step_norm = step_norm;
+    double new_cost = 0.0;
+    bool ok = model_cost_change > 0.0 && evaluator->Plus(x.data(), delta.data(), x_plus.data()) &&
+              evaluator->Evaluate(x_plus.data(), &new_cost, nullptr, nullptr, nullptr);
+    const double relative_decrease = ok ? (cost - new_cost) / model_cost_change : -1.0;
+    is.relative_decrease = relative_decrease;
+    if (ok && relative_decrease > options.min_relative_decrease) {
+      is.step_is_successful = true;
+      is.cost_change = cost - new_cost;
+      x = x_plus;
+      if (!evaluator->Evaluate(x.data(), &cost, residuals.data(), gradient.data(),
+                               jacobian.get())) {
+        summary->termination_type = FAILURE;
+        summary->message = "Residual and Jacobian evaluation failed.";
+        break;
+      }
+      if (options.jacobi_scaling) jacobian->ScaleColumns(scale.data());
+      radius = std::min(options.max_trust_region_radius,
+                        radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * relative_decrease - 1.0, 3)));
+      decrease_factor = 2.0;
+      reuse_diagonal = false;
+      ++summary->num_successful_steps;
+    } else {
+      radius /= decrease_factor;
+      decrease_factor *= 2.0;
+      reuse_diagonal = true;
+      ++summary->num_unsuccessful_steps;
+    }
+    double gmax = 0.0;
+    for (double g : gradient) gmax = std::max(gmax, std::fabs(g));
+    is.cost = cost + fixed_cost;
+    is.gradient_max_norm = gmax;
+    is.trust_region_radius = radius;
+    summary->iterations.push_back(is);
+    if (options.minimizer_progress_to_stdout)
+      std::printf("%4d  %.6e    %.2e   %.2e   %.2e  %.2e  %.2e   %5d\n", it, is.cost, is.cost_change,
+                  gmax, step_norm, relative_decrease, radius, ls_iterations);
+    if (is.step_is_successful) {
+      if (std::fabs(is.cost_change) <= options.function_tolerance * cost) {
+        summary->termination_type = CONVERGENCE;
+        summary->message = "Function tolerance reached.";
+        break;
+      }
+      if (gmax <= options.gradient_tolerance) {
+        summary->termination_type = CONVERGENCE;
+        summary->message = "Gradient tolerance reached.";
+        break;
+      }
+      if (step_norm <= options.parameter_tolerance * (std::sqrt(x_norm) + options.parameter_tolerance)) {
+        summary->termination_type = CONVERGENCE;
+        summary->message = "Parameter tolerance reached.";
+        break;
+      }
+    } else if (radius < options.min_trust_region_radius) {
+      summary->termination_type = CONVERGENCE;
+      summary->message = "Minimum trust region radius reached.";
+      break;
+    }
+  }
+  program->StateVectorToParameterBlocks(x.data());  // results back into the user's arrays
+  summary->final_cost = cost + fixed_cost;
+  for (const auto& kv : evaluator->Statistics()) {
+    if (kv.first == "Evaluator::Residual") {
+      summary->residual_evaluation_time_in_seconds = kv.second.time;
+      summary->num_residual_evaluations = kv.second.calls;
+    } else if (kv.first == "Evaluator::Jacobian") {
+      summary->jacobian_evaluation_time_in_seconds = kv.second.time;
+      summary->num_jacobian_evaluations = kv.second.calls;
+    }
+  }
+  summary->minimizer_time_in_seconds = Seconds() - minimizer_start;
+  summary->total_time_in_seconds = Seconds() - start;
+}
+
+void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* summary) {
+  Solver solver;
+  solver.Solve(options, problem, summary);
+}
+
+}  // namespace ceres

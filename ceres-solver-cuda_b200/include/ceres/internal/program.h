@@ -55,8 +55,9 @@ struct ResidualTypeStore {
   std::type_index key = std::type_index(typeid(void));
   std::vector<int32_t> parameter_blocks;  // [n][num_parameter_blocks] ParameterBlock::id
   std::vector<char> functors;             // n * desc.functor_size bytes
-  std::vector<const void*> loss_objects;  // distinct loss objects (host addresses)
+  std::vector<const void*> loss_objects;  // one representative host object per distinct loss
   std::vector<char> loss_table;           // their bytes, desc.loss_size each
+  std::unordered_map<std::string, int> loss_by_bytes;  // content -> index into loss_table
   std::vector<int32_t> loss_index;        // [n] index into loss_table
   std::vector<CostFunction*> cost_functions;  // [n] (null for bulk-added blocks)
   std::vector<int32_t> residual_block_id;     // [n] global id

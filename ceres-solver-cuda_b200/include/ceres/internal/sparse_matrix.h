@@ -57,6 +57,13 @@ class SparseMatrix {
   void SetZero() { std::memset(values_, 0, sizeof(double) * values_size_); }
   // Row-major num_rows x num_cols.
   virtual void ToDenseMatrix(std::vector<double>* dense) const = 0;
+  // The operations the trust-region loop needs from a Jacobian
+  // (internal/ceres/sparse_matrix.h): y += A x, y += A' x, squared column norms,
+  // A <- A diag(scale).
+  virtual void RightMultiplyAndAccumulate(const double* x, double* y) const = 0;
+  virtual void LeftMultiplyAndAccumulate(const double* x, double* y) const = 0;
+  virtual void SquaredColumnNorm(double* x) const = 0;
+  virtual void ScaleColumns(const double* scale) = 0;
 
  protected:
   SparseMatrix() {}
@@ -96,6 +103,32 @@ class BlockSparseMatrix final : public SparseMatrix {
     }
   }
 
+  template <typename F>  // f(row, col, value&) over every stored entry
+  void ForEachEntry(F&& f) const {
+    const auto& bs = *block_structure_;
+    for (size_t i = 0; i < bs.rows.size(); ++i)
+      for (int32_t c = bs.row_cell_begin[i]; c < bs.row_cell_begin[i + 1]; ++c) {
+        const Block& col = bs.cols[bs.cells[c].block_id];
+        double* v = values_ + bs.cells[c].position;
+        for (int r = 0; r < bs.rows[i].size; ++r)
+          for (int k = 0; k < col.size; ++k)
+            f(bs.rows[i].position + r, col.position + k, v[r * col.size + k]);
+      }
+  }
+  void RightMultiplyAndAccumulate(const double* x, double* y) const override {
+    ForEachEntry([&](int r, int c, double& v) { y[r] += v * x[c]; });
+  }
+  void LeftMultiplyAndAccumulate(const double* x, double* y) const override {
+    ForEachEntry([&](int r, int c, double& v) { y[c] += v * x[r]; });
+  }
+  void SquaredColumnNorm(double* x) const override {
+    std::memset(x, 0, sizeof(double) * num_cols_);
+    ForEachEntry([&](int, int c, double& v) { x[c] += v * v; });
+  }
+  void ScaleColumns(const double* scale) override {
+    ForEachEntry([&](int, int c, double& v) { v *= scale[c]; });
+  }
+
  private:
   CompressedRowBlockStructure* block_structure_;
 };
@@ -122,6 +155,25 @@ class CompressedRowSparseMatrix final : public SparseMatrix {
     for (int r = 0; r < num_rows_; ++r)
       for (int k = rows_[r]; k < rows_[r + 1]; ++k)
         (*dense)[static_cast<size_t>(r) * num_cols_ + cols_[k]] += values_[k];
+  }
+
+  void RightMultiplyAndAccumulate(const double* x, double* y) const override {
+    for (int r = 0; r < num_rows_; ++r) {
+      double acc = 0.0;
+      for (int k = rows_[r]; k < rows_[r + 1]; ++k) acc += values_[k] * x[cols_[k]];
+      y[r] += acc;
+    }
+  }
+  void LeftMultiplyAndAccumulate(const double* x, double* y) const override {
+    for (int r = 0; r < num_rows_; ++r)
+      for (int k = rows_[r]; k < rows_[r + 1]; ++k) y[cols_[k]] += values_[k] * x[r];
+  }
+  void SquaredColumnNorm(double* x) const override {
+    std::memset(x, 0, sizeof(double) * num_cols_);
+    for (int64_t k = 0; k < num_nonzeros_; ++k) x[cols_[k]] += values_[k] * values_[k];
+  }
+  void ScaleColumns(const double* scale) override {
+    for (int64_t k = 0; k < num_nonzeros_; ++k) values_[k] *= scale[cols_[k]];
   }
 
  private:

@@ -34,6 +34,7 @@
 #include "ceres/loss_function_cuda.h"
 #include "ceres/manifold.h"
 #include "ceres/problem.h"
+#include "ceres/solver.h"
 #include "ceres/types.h"
 
 namespace ceres {
@@ -217,6 +218,18 @@ class ProblemCUDA {
   std::unordered_map<LossFunctionCUDABase*, std::unique_ptr<LossFunctionCUDABase>>
       loss_function_ptrs_;
 };
+
+// Same helper as the reference's (include/ceres/problem_cuda.h:490-502): solve with the
+// CUDA evaluator of this problem.
+inline void Solve(const Solver::Options& options, ProblemCUDA* problem_cuda,
+                  Solver::Summary* summary) {
+  Solver solver;
+  Solver::Options options_with_cuda = options;
+  options_with_cuda.use_cuda_for_evaluator = true;
+  options_with_cuda.registered_cuda_evaluators =
+      problem_cuda->mutable_registered_cuda_evaluators();
+  solver.Solve(options_with_cuda, problem_cuda->mutable_problem(), summary);
+}
 
 }  // namespace ceres
 

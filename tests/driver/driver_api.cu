@@ -276,6 +276,55 @@ int drv_plus(void* h, const double* state, const double* delta, double* out) {
   return static_cast<DriverProblem*>(h)->program->Plus(state, delta, out) ? 1 : 0;
 }
 
+// ceres::Solve(options, ProblemCUDA*, summary) on the driver's problem.  ordering: group id
+// per parameter block (or NULL).  out: [initial_cost, final_cost, iterations,
+// successful_steps, termination_type, num_jacobian_evaluations, num_residual_evaluations].
+// The solution is written to the driver's parameter values (drv_user_values).
+int drv_solve(void* h, int linear_solver_type, int max_num_iterations, const int* ordering,
+              int device, double* out) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  ceres::Solver::Options options;
+  options.linear_solver_type = static_cast<ceres::LinearSolverType>(linear_solver_type);
+  options.max_num_iterations = max_num_iterations;
+  options.cuda_device = device;
+  if (ordering) {
+    auto* o = new ceres::ParameterBlockOrdering;
+    for (size_t k = 0; k < dp->pb_offset.size(); ++k)
+      o->AddElementToGroup(dp->pb(static_cast<int>(k)), ordering[k]);
+    options.linear_solver_ordering.reset(o);
+  }
+  ceres::Solver::Summary summary;
+  ceres::Solve(options, &dp->problem, &summary);
+  dp->error = summary.message;
+  out[0] = summary.initial_cost;
+  out[1] = summary.final_cost;
+  out[2] = static_cast<double>(summary.iterations.size());
+  out[3] = summary.num_successful_steps;
+  out[4] = static_cast<double>(summary.termination_type);
+  out[5] = summary.num_jacobian_evaluations;
+  out[6] = summary.num_residual_evaluations;
+  return summary.IsSolutionUsable() ? 1 : 0;
+}
+
+// Solver::Options::IsValid for a given minimizer type (0 LINE_SEARCH, 1 TRUST_REGION) with
+// the CUDA evaluator requested.  Returns 1 when valid; the message is copied to msg.
+int drv_options_is_valid(void* h, int minimizer_type, char* msg, int msg_size) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  ceres::Solver::Options options;
+  options.minimizer_type = static_cast<ceres::MinimizerType>(minimizer_type);
+  options.use_cuda_for_evaluator = true;
+  options.registered_cuda_evaluators = dp->problem.mutable_registered_cuda_evaluators();
+  std::string error;
+  const bool ok = options.IsValid(&error);
+  std::snprintf(msg, msg_size, "%s", error.c_str());
+  return ok ? 1 : 0;
+}
+
+void drv_user_values(void* h, double* out) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  std::memcpy(out, dp->values.data(), dp->values.size() * sizeof(double));
+}
+
 void drv_dense_jacobian(void* h, double* dense) {
   auto* dp = static_cast<DriverProblem*>(h);
   std::vector<double> d;
