@@ -110,6 +110,18 @@ __device__ __forceinline__ void RedAdd(double* address, double value) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(address), "d"(value) : "memory");
 }
 
+// Predicated form: the compiler branches around an atomic inside an `if`; one predicated
+// instruction avoids the BSSY / BRA / BSYNC per reduction round.
+__device__ __forceinline__ void RedAddIf(bool condition, double* address, double value) {
+  asm volatile(
+      "{\n"
+      "  .reg .pred p;\n"
+      "  setp.ne.u32 p, %2, 0;\n"
+      "  @p red.global.add.f64 [%0], %1;\n"
+      "}" ::"l"(address), "d"(value), "r"(static_cast<unsigned>(condition))
+      : "memory");
+}
+
 // Jacobian block helpers.  B is the kRes x kSize ambient block.
 template <int kRes, int kSize>
 struct BlockEpilogue {
@@ -200,6 +212,9 @@ __device__ __forceinline__ void CpAsyncWait() {
 #ifndef CB200_KERNEL_FMA_CHECK
 #define CB200_KERNEL_FMA_CHECK 1      // finite check: 1 = FMA chain (FP64 pipe), 0 = integer max
 #endif
+#ifndef CB200_KERNEL_FMA_CHECK_CHAINS
+#define CB200_KERNEL_FMA_CHECK_CHAINS 1
+#endif
 #ifndef CB200_KERNEL_STAGE_GRADIENT
 #define CB200_KERNEL_STAGE_GRADIENT 1 // warp-staged, sector-coalesced gradient reductions
 #endif
@@ -246,9 +261,22 @@ __host__ __device__ constexpr int WarpStageDoubles(int num_residuals, int max_bl
 // Accumulates evidence of a non-finite value; Bad() is true iff one was seen.
 struct FiniteCheck {
 #if CB200_KERNEL_FMA_CHECK
-  double acc = 0.0;  // stays 0 iff every value is finite (0 * Inf = NaN)
-  __device__ __forceinline__ void Add(double x) { acc = ::fma(x, 0.0, acc); }
-  __device__ __forceinline__ bool Bad() const { return !(acc == 0.0); }
+  // Every accumulator stays 0 iff its values are finite (0 * Inf = NaN).  The number of
+  // independent chains is a tuning knob; one chain measured fastest on B200 (BAL L:
+  // 2.28 ms against 2.32 ms with four - the extra accumulators cost registers).
+  static constexpr int kChains = CB200_KERNEL_FMA_CHECK_CHAINS;
+  double acc[kChains] = {};
+  int next = 0;  // folds to a constant once the callers' loops are unrolled
+  __device__ __forceinline__ void Add(double x) {
+    acc[next] = ::fma(x, 0.0, acc[next]);
+    next = next + 1 == kChains ? 0 : next + 1;
+  }
+  __device__ __forceinline__ bool Bad() const {
+    double sum = acc[0];
+#pragma unroll
+    for (int k = 1; k < kChains; ++k) sum += acc[k];
+    return !(sum == 0.0);
+  }
 #else
   unsigned worst = 0;  // max of the high words with the sign shifted out
   __device__ __forceinline__ void Add(double x) {
@@ -340,11 +368,12 @@ struct SmemPlan {
   // ... and one padded row per lane for the staged gradient reductions
   // the staged gradient reductions reuse the Jacobian staging buffer: with a single
   // derivative pass every gradient is out before the first cell is staged.
+  // (plus, per lane, the destination offset and the live-column mask: 2 x 32 ints)
+  static constexpr int kGradientStage = 32 * StagePitch(Dims::MaxSize()) + 32;
   static constexpr bool kGradientAliasesJacobian =
       PassPlan<kRes, Ns...>::kNumPasses == 1 &&
-      32 * StagePitch(Dims::MaxSize()) <= kJacobianDoubles;
-  static constexpr int kGradientDoubles =
-      kGradientAliasesJacobian ? 0 : 32 * StagePitch(Dims::MaxSize());
+      kGradientStage <= kJacobianDoubles;
+  static constexpr int kGradientDoubles = kGradientAliasesJacobian ? 0 : kGradientStage;
   static constexpr int kWarps = kEvaluateThreads / 32;
   static constexpr bool kStageJacobian =
       CB200_KERNEL_STAGE_JACOBIAN &&
@@ -352,8 +381,7 @@ struct SmemPlan {
   static constexpr int kGradientOffset =
       (kStageJacobian && !kGradientAliasesJacobian) ? kJacobianDoubles : 0;
   static constexpr int kWarpDoubles =
-      kStageJacobian ? kJacobianDoubles + kGradientDoubles
-                     : 32 * StagePitch(Dims::MaxSize());
+      kStageJacobian ? kJacobianDoubles + kGradientDoubles : kGradientStage;
   static constexpr int kJetBytes = kPrefetchBytes + kWarps * kWarpDoubles * 8;
   static constexpr int kCostBytes = kPrefetchBytes > 0 ? kPrefetchBytes : 16;
 };
@@ -397,6 +425,7 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
                        (threadIdx.x >> 5) * Smem::kWarpDoubles;
   double* const jbuf = wbuf;                                              // Jacobian staging
   double* const gbuf = wbuf + Smem::kGradientOffset;                      // gradient staging
+  int* const obuf = reinterpret_cast<int*>(gbuf + 32 * StagePitch(Dims::MaxSize()));
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -445,7 +474,8 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
             const int owner = e / kS;
             const int i = e - owner * kS;
             const int so = __shfl_sync(0xffffffffu, soff[j], owner);
-            CpAsync8(wdst + 32 * Dims::PitchBefore(j) + owner * kP + i, a.state + so + i);
+            CpAsync8(wdst + 32 * Dims::PitchBefore(j) + (kP == kS ? e : owner * kP + i),
+                     a.state + (so + i));
           }
         }
       } else {
@@ -852,17 +882,38 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
               constexpr int kPitch = StagePitch(kSize);
 #pragma unroll
               for (int c = 0; c < kSize; ++c) gbuf[lane * kPitch + c] = g[c];
+              // destination of every lane's sums (or -1) and, with manifolds, its live
+              // columns: the reduction rounds read them back by row, so a round is two
+              // shared loads, an address and one predicated red (v7 fetched them with
+              // shuffles inside a divergent branch: 19 instructions a round, now 9)
+              obuf[lane] = emit ? delta_off[j] : -1;
+              if constexpr (kGeneric) obuf[32 + lane] = static_cast<int>(lv);
               __syncwarp();
+              if (!kGeneric && emit_mask == 0xffffffffu) {
+                // every lane emits (the usual case): straight-line, no per-round branch
+#pragma unroll
+                for (int it = 0; it < kSize; ++it) {
+                  const int e = it * 32 + lane;
+                  const int row = e / kSize;
+                  const int c = e - row * kSize;
+                  RedAdd(a.gradient + (obuf[row] + c),
+                         gbuf[kPitch == kSize ? e : row * kPitch + c]);
+                }
+              } else
 #pragma unroll
               for (int it = 0; it < kSize; ++it) {
                 const int e = it * 32 + lane;
                 const int row = e / kSize;
                 const int c = e - row * kSize;
-                const int d = __shfl_sync(0xffffffffu, delta_off[j], row);
-                const unsigned lr = kGeneric ? __shfl_sync(0xffffffffu, lv, row) : kAll;
-                if (((emit_mask >> row) & 1u) && ((lr >> c) & 1u))
-                  RedAdd(a.gradient + d + (kGeneric ? __popc(lr & ((1u << c) - 1u)) : c),
-                         gbuf[row * kPitch + c]);
+                const int d = obuf[row];
+                const double sum = gbuf[kPitch == kSize ? e : row * kPitch + c];
+                if constexpr (kGeneric) {
+                  const unsigned lr = static_cast<unsigned>(obuf[32 + row]);
+                  RedAddIf(d >= 0 && ((lr >> c) & 1u),
+                           a.gradient + d + __popc(lr & ((1u << c) - 1u)), sum);
+                } else {
+                  RedAddIf(d >= 0, a.gradient + (d + c), sum);
+                }
               }
               __syncwarp();
             } else if (emit) {

@@ -364,13 +364,28 @@ template <typename T, int N>
 CERES_B200_JET_FN Jet<T, N> cbrt(const Jet<T, N>& f) {
   return jet_internal::Chain(f, T(::cbrt(f.a)), T(1.0) / (T(3.0) * ::cbrt(f.a * f.a)));
 }
+// On the device sin and cos come from one sincos(): the argument reduction is shared, and
+// when a functor takes both of the same angle (AngleAxisRotatePoint) the two calls fold
+// into one.
 template <typename T, int N>
 CERES_B200_JET_FN Jet<T, N> cos(const Jet<T, N>& f) {
+#ifdef __CUDA_ARCH__
+  double s, c;
+  ::sincos(f.a, &s, &c);
+  return jet_internal::Chain(f, T(c), -T(s));
+#else
   return jet_internal::Chain(f, T(::cos(f.a)), -T(::sin(f.a)));
+#endif
 }
 template <typename T, int N>
 CERES_B200_JET_FN Jet<T, N> sin(const Jet<T, N>& f) {
+#ifdef __CUDA_ARCH__
+  double s, c;
+  ::sincos(f.a, &s, &c);
+  return jet_internal::Chain(f, T(s), T(c));
+#else
   return jet_internal::Chain(f, T(::sin(f.a)), T(::cos(f.a)));
+#endif
 }
 template <typename T, int N>
 CERES_B200_JET_FN Jet<T, N> tan(const Jet<T, N>& f) {

@@ -101,6 +101,15 @@ int main(int argc, char** argv) {
   int st; CK(cudaMemcpy(&st, status, 4, cudaMemcpyDeviceToHost));
   std::vector<double> part(grid_max); CK(cudaMemcpy(part.data(), cp, 8 * (size_t)grid_max, cudaMemcpyDeviceToHost));
   double cost = 0; for (double v : part) cost += v;
+  {
+    std::vector<double> gh(state.size()), jh(1 << 16);
+    CK(cudaMemcpy(gh.data(), grad, 8 * gh.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(jh.data(), jac + 6 * (size_t)n, 8 * jh.size(), cudaMemcpyDeviceToHost));
+    double gs = 0, ga = 0, js = 0;
+    for (double v : gh) { gs += v; ga += std::fabs(v); }
+    for (double v : jh) js += std::fabs(v);
+    std::printf("checksums: gradient sum %.12e abs %.12e  jacobian abs %.12e\n", gs, ga, js);
+  }
   std::printf("KBENCH %s ctas=%d ints_smem=%d fma_check=%d stage_g=%d stage_j=%d g=%d j=%d : mean %.3f ms best %.3f ms  (%.2f G blocks/s)  status=%d cost=%.6e\n",
               argc > 6 ? argv[6] : "", CB200_RESIDENT_CTAS_SMALL, CB200_KERNEL_INTS_IN_SMEM, CB200_KERNEL_FMA_CHECK,
               CB200_KERNEL_STAGE_GRADIENT, CB200_KERNEL_STAGE_JACOBIAN, want_g, want_j, sum / reps, best, n / (sum / reps) / 1e6, st, cost);
