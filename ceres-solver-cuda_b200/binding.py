@@ -23,7 +23,9 @@ ABI_SYMBOLS = [
     "cb200_engine_set_layout", "cb200_engine_set_shard", "cb200_engine_finalize",
     "cb200_nccl_unique_id", "cb200_engine_comm_init", "cb200_engine_evaluate",
     "cb200_engine_evaluate_device", "cb200_engine_device_ptr", "cb200_engine_shard_info",
-    "cb200_engine_last_timing", "cb200_host_alloc", "cb200_host_pin", "cb200_host_free",
+    "cb200_engine_last_timing", "cb200_engine_jacobian_multiply",
+    "cb200_engine_jacobian_squared_column_norm", "cb200_engine_jacobian_scale_columns",
+    "cb200_engine_cgnr_solve", "cb200_host_alloc", "cb200_host_pin", "cb200_host_free",
     "cb200_version",
 ]
 
@@ -104,7 +106,12 @@ def driver():
         L.drv_shard_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.drv_plus.argtypes = [C.c_void_p] * 4
         L.drv_dense_jacobian.argtypes = [C.c_void_p, C.c_void_p]
-        L.drv_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.drv_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.drv_jacobian_multiply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.drv_jacobian_squared_column_norm.argtypes = [C.c_void_p, C.c_void_p]
+        L.drv_jacobian_scale_columns.argtypes = [C.c_void_p, C.c_void_p]
+        L.drv_cgnr_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double,
+                                     C.c_double, C.c_void_p, C.c_void_p]
         L.drv_user_values.argtypes = [C.c_void_p, C.c_void_p]
         L.drv_options_is_valid.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         _DRV = L
@@ -137,7 +144,7 @@ SPARSE_NORMAL_CHOLESKY, DENSE_SCHUR, SPARSE_SCHUR, ITERATIVE_SCHUR, CGNR = 2, 3,
 
 
 def solve(spec, linear_solver_type=ITERATIVE_SCHUR, max_num_iterations=20, ordering=None,
-          device=0, bulk=False):
+          device=0, bulk=False, cuda_sparse=False):
     """ceres::Solve(options, ProblemCUDA*, summary) (reference: problem_cuda.h:490-502) on
     a ProblemSpec built through the per-block C++ API.  Returns a dict with the summary
     and the solution in the specification's parameter-block order."""
@@ -152,14 +159,16 @@ def solve(spec, linear_solver_type=ITERATIVE_SCHUR, max_num_iterations=20, order
         raise RuntimeError(err.decode())
     out = np.zeros(8)
     o = None if ordering is None else np.ascontiguousarray(ordering, dtype=np.int32)
-    ok = L.drv_solve(h, int(linear_solver_type), int(max_num_iterations), _p(o), int(device), _p(out))
+    ok = L.drv_solve(h, int(linear_solver_type), int(cuda_sparse), int(max_num_iterations), _p(o),
+                     int(device), _p(out))
     x = np.zeros(spec.pb_values.size)
     L.drv_user_values(h, _p(x))
     msg = L.drv_error(h).decode()
     L.drv_destroy(h)
     return dict(usable=bool(ok), initial_cost=out[0], final_cost=out[1], iterations=int(out[2]),
                 successful_steps=int(out[3]), termination_type=int(out[4]),
-                jacobian_evaluations=int(out[5]), residual_evaluations=int(out[6]), message=msg,
+                jacobian_evaluations=int(out[5]), residual_evaluations=int(out[6]),
+                linear_solver_seconds=float(out[7]), message=msg,
                 x=x)
 
 
@@ -279,6 +288,40 @@ class CudaProblem:
         if rc < 0:
             raise RuntimeError(f"evaluate_device failed ({rc})")
         return rc == 0, float(cost[0])
+
+    # ---- linear algebra on the Jacobian the last evaluation left in HBM
+    def _la_check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"device Jacobian operation failed ({rc}): "
+                               f"{driver().drv_error(self.h).decode()}")
+
+    def jacobian_multiply(self, x, transpose=False):
+        """y = J x (or J' x) with the device-resident Jacobian of the last evaluation."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros(self.num_effective_parameters if transpose else self.num_residuals)
+        self._la_check(driver().drv_jacobian_multiply(self.h, int(transpose), _p(x), _p(y)))
+        return y
+
+    def jacobian_squared_column_norm(self):
+        out = np.zeros(self.num_effective_parameters)
+        self._la_check(driver().drv_jacobian_squared_column_norm(self.h, _p(out)))
+        return out
+
+    def jacobian_scale_columns(self, scale):
+        scale = np.ascontiguousarray(scale, dtype=np.float64)
+        self._la_check(driver().drv_jacobian_scale_columns(self.h, _p(scale)))
+
+    def cgnr_solve(self, d_squared=None, min_iterations=0, max_iterations=500, r_tolerance=-1.0,
+                   q_tolerance=0.1):
+        """(J'J + diag(d_squared)) y = J'r on the device; returns (y, summary dict)."""
+        d2 = None if d_squared is None else np.ascontiguousarray(d_squared, dtype=np.float64)
+        y = np.zeros(self.num_effective_parameters)
+        out = np.zeros(8)
+        self._la_check(driver().drv_cgnr_solve(self.h, _p(d2), int(min_iterations),
+                                               int(max_iterations), float(r_tolerance),
+                                               float(q_tolerance), _p(y), _p(out)))
+        return y, dict(iterations=int(out[0]), termination=int(out[1]), gradient_norm=out[2],
+                       residual_norm=out[3], jy_dot_b=out[4], jy_squared_norm=out[5], ms=out[6])
 
     def timing(self):
         """ms of the last evaluation: kernels, kernels+reductions+allreduce, whole call; launches."""

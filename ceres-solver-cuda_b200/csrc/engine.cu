@@ -22,6 +22,7 @@
 #include <sys/mman.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -153,6 +154,189 @@ __global__ void ReduceCostKernel(const double* __restrict__ partials, int n, dou
   if (threadIdx.x == 0) *out = sm[0];
 }
 
+// ---- linear algebra on the device-resident Jacobian.
+// The kernels walk the same per-type tables the evaluation kernel writes through:
+// block (j, i) of a type is a dense num_residuals x tangent cell at jacobian_pos, row
+// stride = tangent (block sparse) or the block's CRS row stride, columns starting at
+// delta_offset.  They are bandwidth bound (one pass over the values), so sizes are
+// runtime arguments and one instantiation serves every residual-block type.
+struct JacobianWalk {
+  int32_t n, nb, kres, crs, plain;
+  int32_t sizes[CB200_MAX_PARAMETER_BLOCKS];
+  const int32_t* doff;     // [nb][n]
+  const int32_t* jpos;     // [nb][n]
+  const int32_t* pb;       // [nb][n]
+  const int32_t* jstride;  // [n]
+  const int32_t* respos;   // [n]
+  const int32_t* pb_table;
+  double* values;
+};
+
+__device__ __forceinline__ void RedAddF64(double* address, double value) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(address), "d"(value) : "memory");
+}
+
+enum { kOpRight = 0, kOpLeft = 1, kOpColumnNorm = 2, kOpScale = 3 };
+
+// One thread per residual block.  x / y meaning per operation:
+//   kOpRight:      y[rows] = sum_c J(r, c) x[c]        (y indexed by local residual)
+//   kOpLeft:       y[c]   += sum_r J(r, c) x[r]        (atomic; x indexed by local residual)
+//   kOpColumnNorm: y[c]   += sum_r J(r, c)^2           (atomic)
+//   kOpScale:      J(r, c) *= x[c]
+template <int kOp>
+__global__ void __launch_bounds__(256) JacobianWalkKernel(const JacobianWalk w,
+                                                          const double* __restrict__ x,
+                                                          double* __restrict__ y) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.n; i += gridDim.x * blockDim.x) {
+    const int row0 = w.respos[i];
+    if (kOp == kOpRight) {
+      for (int r = 0; r < w.kres; ++r) {
+        double acc = 0.0;
+        for (int j = 0; j < w.nb; ++j) {
+          const size_t at = static_cast<size_t>(j) * w.n + i;
+          const int jp = w.jpos[at];
+          if (jp < 0) continue;
+          const int col = w.doff[at];
+          const int tan = w.plain ? w.sizes[j] : w.pb_table[8 * w.pb[at] + 2];
+          const int rs = w.crs ? w.jstride[i] : tan;
+          const double* __restrict__ v = w.values + jp + static_cast<size_t>(r) * rs;
+          for (int c = 0; c < tan; ++c) acc = fma(v[c], x[col + c], acc);
+        }
+        y[row0 + r] = acc;
+      }
+    } else {
+      for (int j = 0; j < w.nb; ++j) {
+        const size_t at = static_cast<size_t>(j) * w.n + i;
+        const int jp = w.jpos[at];
+        if (jp < 0) continue;
+        const int col = w.doff[at];
+        const int tan = w.plain ? w.sizes[j] : w.pb_table[8 * w.pb[at] + 2];
+        const int rs = w.crs ? w.jstride[i] : tan;
+        double* v = w.values + jp;
+        for (int c = 0; c < tan; ++c) {
+          if (kOp == kOpScale) {
+            const double sc = x[col + c];
+            for (int r = 0; r < w.kres; ++r) v[static_cast<size_t>(r) * rs + c] *= sc;
+          } else {
+            double acc = 0.0;
+            for (int r = 0; r < w.kres; ++r) {
+              const double a = v[static_cast<size_t>(r) * rs + c];
+              acc = fma(a, kOp == kOpLeft ? x[row0 + r] : a, acc);
+            }
+            RedAddF64(y + col + c, acc);
+          }
+        }
+      }
+    }
+  }
+}
+
+// Conjugate-gradient vector kernels.  S is a small array of device scalars:
+enum { kSRho = 0, kSLastRho, kSPq, kSRnorm2, kSXbr, kSJyB, kSJy2, kSCount };
+
+__device__ __forceinline__ double BlockSum(double v) {
+  __shared__ double sm[8];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = threadIdx.x < 8 ? sm[threadIdx.x] : 0.0;
+  if (threadIdx.x < 32)
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;  // valid in thread 0
+}
+
+// minv = 1 / (colnorm + d2);  r = b;  z = minv r;  p = z;  x = 0;  rho = r.z;  rnorm2 = r.r
+__global__ void __launch_bounds__(256) CgInitKernel(int n, const double* __restrict__ colnorm,
+                                                    const double* __restrict__ d2,
+                                                    const double* __restrict__ b, double* minv,
+                                                    double* r, double* p, double* x, double* S) {
+  double rho = 0.0, rr = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double m = 1.0 / (colnorm[i] + (d2 ? d2[i] : 0.0));
+    const double ri = b[i], zi = (isfinite(m) ? m : 1.0) * ri;
+    minv[i] = isfinite(m) ? m : 1.0;
+    r[i] = ri;
+    p[i] = zi;
+    x[i] = 0.0;
+    rho += ri * zi;
+    rr += ri * ri;
+  }
+  rho = BlockSum(rho);
+  rr = BlockSum(rr);
+  if (threadIdx.x == 0) {
+    atomicAdd(S + kSRho, rho);
+    atomicAdd(S + kSRnorm2, rr);
+  }
+}
+
+// pq = p.(q + d2 p)
+__global__ void __launch_bounds__(256) CgDotKernel(int n, const double* __restrict__ p,
+                                                   const double* __restrict__ q,
+                                                   const double* __restrict__ d2, double* S) {
+  double acc = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    acc += p[i] * (q[i] + (d2 ? d2[i] : 0.0) * p[i]);
+  acc = BlockSum(acc);
+  if (threadIdx.x == 0) atomicAdd(S + kSPq, acc);
+}
+
+// alpha = rho / pq;  x += alpha p;  r -= alpha (q + d2 p);  accumulates the next rho = r.(minv r),
+// |r|^2 and x.(b + r) into Snext
+__global__ void __launch_bounds__(256) CgUpdateKernel(int n, const double* __restrict__ p,
+                                                      const double* __restrict__ q,
+                                                      const double* __restrict__ d2,
+                                                      const double* __restrict__ minv,
+                                                      const double* __restrict__ b, double* x,
+                                                      double* r, const double* S, double* Snext) {
+  const double alpha = S[kSRho] / S[kSPq];
+  double rho = 0.0, rr = 0.0, xbr = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double pi = p[i];
+    const double xi = x[i] + alpha * pi;
+    const double ri = r[i] - alpha * (q[i] + (d2 ? d2[i] : 0.0) * pi);
+    x[i] = xi;
+    r[i] = ri;
+    rho += ri * ri * minv[i];
+    rr += ri * ri;
+    xbr += xi * (b[i] + ri);
+  }
+  rho = BlockSum(rho);
+  rr = BlockSum(rr);
+  xbr = BlockSum(xbr);
+  if (threadIdx.x == 0) {
+    atomicAdd(Snext + kSRho, rho);
+    atomicAdd(Snext + kSRnorm2, rr);
+    atomicAdd(Snext + kSXbr, xbr);
+  }
+}
+
+// p = minv r + (rho_next / rho) p
+__global__ void __launch_bounds__(256) CgDirectionKernel(int n, const double* __restrict__ r,
+                                                         const double* __restrict__ minv,
+                                                         double* p, const double* S,
+                                                         const double* Snext) {
+  const double beta = Snext[kSRho] / S[kSRho];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    p[i] = minv[i] * r[i] + beta * p[i];
+}
+
+// jy.b and |jy|^2 over this rank's residuals
+__global__ void __launch_bounds__(256) CgModelKernel(int n, const double* __restrict__ jy,
+                                                     const double* __restrict__ b, double* S) {
+  double d = 0.0, s = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    d += jy[i] * b[i];
+    s += jy[i] * jy[i];
+  }
+  d = BlockSum(d);
+  s = BlockSum(s);
+  if (threadIdx.x == 0) {
+    atomicAdd(S + kSJyB, d);
+    atomicAdd(S + kSJy2, s);
+  }
+}
+
 }  // namespace
 
 struct cb200_engine {
@@ -190,6 +374,14 @@ struct cb200_engine {
 
   // pinned scalars: [cost, status]
   double* h_scalars = nullptr;
+
+  // device-resident Jacobian linear algebra: which outputs of the last evaluation are
+  // on the device, and the conjugate-gradient work vectors (allocated on first use)
+  bool jacobian_resident = false, residuals_resident = false;
+  DeviceBuffer<double> la_col[8];   // x-like: num_effective + 1 each
+  DeviceBuffer<double> la_row;      // residual-like: this rank's residuals
+  DeviceBuffer<double> la_scalars;  // 3 x kSCount
+  double* h_la_scalars = nullptr;   // pinned, 3 x kSCount
 
   void* comm = nullptr;
   double timing[4] = {0, 0, 0, 0};
@@ -262,6 +454,9 @@ void cb200_engine_destroy(cb200_engine* e) {
     t->d_jpos.Free(); t->d_jstride.Free(); t->d_respos.Free(); t->d_soff.Free(); t->d_doff.Free();
     delete t;
   }
+  for (auto& b : e->la_col) b.Free();
+  e->la_row.Free(); e->la_scalars.Free();
+  if (e->h_la_scalars) cudaFreeHost(e->h_la_scalars);
   e->d_state.Free(); e->d_plus.Free(); e->d_residuals.Free(); e->d_jacobian.Free();
   e->d_gradcost.Free(); e->d_cost_partials.Free(); e->d_pb_table.Free(); e->d_status.Free();
   if (e->h_scalars) cudaFreeHost(e->h_scalars);
@@ -607,6 +802,8 @@ int cb200_engine_comm_init(cb200_engine* e, const void* unique_id, int32_t rank,
 static int EvaluateOnDevice(cb200_engine* e, uint32_t flags, bool want_r, bool want_g,
                             bool want_j) {
   cudaStream_t s = e->stream;
+  if (want_j) e->jacobian_resident = true;   // values of an older evaluation are overwritten
+  if (want_r) e->residuals_resident = true;
   CB200_CUDA(e, cudaMemsetAsync(e->d_status.ptr, 0, sizeof(int32_t), s));
   // Only the gradient accumulates; residuals and Jacobian cells are each written
   // exactly once.  Cost slot and padding are zeroed with it.
@@ -718,22 +915,24 @@ int cb200_engine_evaluate(cb200_engine* e, const double* state, const double* pl
   if (e->plus_pool > 0)
     CB200_CUDA(e, cudaMemcpyAsync(e->d_plus.ptr, plus_jacobians, sizeof(double) * e->plus_pool,
                                   cudaMemcpyHostToDevice, s));
-  const int rc = EvaluateOnDevice(e, flags, residuals != nullptr, gradient != nullptr,
-                                  jacobian_values != nullptr);
+  const bool keep_r = (flags & CB200_KEEP_RESIDUALS_ON_DEVICE) != 0;
+  const bool keep_j = (flags & CB200_KEEP_JACOBIAN_ON_DEVICE) != 0;
+  const int rc = EvaluateOnDevice(e, flags, residuals != nullptr || keep_r, gradient != nullptr,
+                                  jacobian_values != nullptr || keep_j);
   if (rc != CB200_OK) return rc;
   CB200_CUDA(e, cudaMemcpyAsync(e->h_scalars, e->d_gradcost.ptr + e->num_effective,
                                 sizeof(double), cudaMemcpyDeviceToHost, s));
   CB200_CUDA(e, cudaMemcpyAsync(e->h_scalars + 1, e->d_status.ptr, sizeof(int32_t),
                                 cudaMemcpyDeviceToHost, s));
   if (!(flags & CB200_SKIP_HOST_COPY)) {
-    if (residuals && e->res_end > e->res_begin)
+    if (residuals && !keep_r && e->res_end > e->res_begin)
       CB200_CUDA(e, cudaMemcpyAsync(residuals + e->res_begin, e->d_residuals.ptr,
                                     sizeof(double) * (e->res_end - e->res_begin),
                                     cudaMemcpyDeviceToHost, s));
     if (gradient && e->num_effective > 0)
       CB200_CUDA(e, cudaMemcpyAsync(gradient, e->d_gradcost.ptr,
                                     sizeof(double) * e->num_effective, cudaMemcpyDeviceToHost, s));
-    if (jacobian_values)
+    if (jacobian_values && !keep_j)
       for (const Segment& seg : e->segments)
         CB200_CUDA(e, cudaMemcpyAsync(jacobian_values + seg.global_begin,
                                       e->d_jacobian.ptr + seg.local_begin,
@@ -791,6 +990,223 @@ void* cb200_engine_device_ptr(cb200_engine* e, int which) {
     case 4: return e->d_plus.ptr;
     default: return nullptr;
   }
+}
+
+// ---- device-resident Jacobian linear algebra --------------------------------------------
+
+static int RunJacobianWalk(cb200_engine* e, int op, const double* x, double* y) {
+  cudaStream_t s = e->stream;
+  for (ResidualType* t : e->types) {
+    if (t->n_local == 0) continue;
+    JacobianWalk w{};
+    w.n = t->n_local;
+    w.nb = t->desc.num_parameter_blocks;
+    w.kres = t->desc.num_residuals;
+    w.crs = e->jacobian_format == CB200_JACOBIAN_COMPRESSED_ROW;
+    w.plain = t->plain;
+    for (int j = 0; j < w.nb; ++j) w.sizes[j] = t->desc.parameter_block_sizes[j];
+    w.doff = t->d_doff.ptr;
+    w.jpos = t->d_jpos.ptr;
+    w.pb = t->d_pb.ptr;
+    w.jstride = t->d_jstride.ptr;
+    w.respos = t->d_respos.ptr;
+    w.pb_table = e->d_pb_table.ptr;
+    w.values = e->d_jacobian.ptr;
+    const int grid = std::min((t->n_local + 255) / 256, 148 * 16);
+    switch (op) {
+      case kOpRight: JacobianWalkKernel<kOpRight><<<grid, 256, 0, s>>>(w, x, y); break;
+      case kOpLeft: JacobianWalkKernel<kOpLeft><<<grid, 256, 0, s>>>(w, x, y); break;
+      case kOpColumnNorm: JacobianWalkKernel<kOpColumnNorm><<<grid, 256, 0, s>>>(w, x, y); break;
+      default: JacobianWalkKernel<kOpScale><<<grid, 256, 0, s>>>(w, x, y); break;
+    }
+  }
+  CB200_CUDA(e, cudaGetLastError());
+  return CB200_OK;
+}
+
+// Sums a column-space vector over the ranks (each holds the contribution of its blocks).
+static int SumOverRanks(cb200_engine* e, double* v, size_t count) {
+  if (!e->comm || e->world <= 1) return CB200_OK;
+  NcclApi* n = GetNccl();
+  if (n->AllReduce(v, v, count, kNcclFloat64, kNcclSum, e->comm, e->stream) != 0)
+    return e->Fail(CB200_ERROR_NCCL, "NCCL all-reduce failed");
+  return CB200_OK;
+}
+
+static int PrepareLinearAlgebra(cb200_engine* e, bool need_residuals) {
+  if (!e) return CB200_ERROR_INVALID_ARGUMENT;
+  if (!e->finalized) return e->Fail(CB200_ERROR_NOT_FINALIZED, "not finalized");
+  if (e->planning) return e->Fail(CB200_ERROR_CUDA, "planning-only engine: no device, no CPU fallback");
+  if (!e->jacobian_resident)
+    return e->Fail(CB200_ERROR_INVALID_ARGUMENT,
+                   "no Jacobian on the device: evaluate with a Jacobian first");
+  if (need_residuals && !e->residuals_resident)
+    return e->Fail(CB200_ERROR_INVALID_ARGUMENT,
+                   "no residuals on the device: evaluate with residuals first");
+  CB200_CUDA(e, cudaSetDevice(e->device));
+  for (auto& b : e->la_col) CB200_CUDA(e, b.Resize(static_cast<size_t>(e->num_effective) + 1));
+  CB200_CUDA(e, e->la_row.Resize(static_cast<size_t>(e->res_end - e->res_begin) + 1));
+  CB200_CUDA(e, e->la_scalars.Resize(3 * kSCount));
+  if (!e->h_la_scalars)
+    CB200_CUDA(e, cudaHostAlloc(reinterpret_cast<void**>(&e->h_la_scalars),
+                                3 * kSCount * sizeof(double), cudaHostAllocDefault));
+  return CB200_OK;
+}
+
+int cb200_engine_jacobian_multiply(cb200_engine* e, int transpose, const double* x, double* y) {
+  int rc = PrepareLinearAlgebra(e, false);
+  if (rc != CB200_OK) return rc;
+  if (!x || !y) return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "x and y are required");
+  cudaStream_t s = e->stream;
+  const size_t ne = e->num_effective, m = e->res_end - e->res_begin;
+  double* col = e->la_col[0].ptr;
+  double* row = e->la_row.ptr;
+  if (!transpose) {
+    CB200_CUDA(e, cudaMemcpyAsync(col, x, ne * sizeof(double), cudaMemcpyHostToDevice, s));
+    if ((rc = RunJacobianWalk(e, kOpRight, col, row)) != CB200_OK) return rc;
+    if (m) CB200_CUDA(e, cudaMemcpyAsync(y + e->res_begin, row, m * sizeof(double),
+                                         cudaMemcpyDeviceToHost, s));
+  } else {
+    if (m) CB200_CUDA(e, cudaMemcpyAsync(row, x + e->res_begin, m * sizeof(double),
+                                         cudaMemcpyHostToDevice, s));
+    CB200_CUDA(e, cudaMemsetAsync(col, 0, ne * sizeof(double), s));
+    if ((rc = RunJacobianWalk(e, kOpLeft, row, col)) != CB200_OK) return rc;
+    if ((rc = SumOverRanks(e, col, ne)) != CB200_OK) return rc;
+    CB200_CUDA(e, cudaMemcpyAsync(y, col, ne * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
+  CB200_CUDA(e, cudaStreamSynchronize(s));
+  return CB200_OK;
+}
+
+int cb200_engine_jacobian_squared_column_norm(cb200_engine* e, double* out) {
+  int rc = PrepareLinearAlgebra(e, false);
+  if (rc != CB200_OK) return rc;
+  if (!out) return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "out is required");
+  cudaStream_t s = e->stream;
+  const size_t ne = e->num_effective;
+  double* col = e->la_col[0].ptr;
+  CB200_CUDA(e, cudaMemsetAsync(col, 0, ne * sizeof(double), s));
+  if ((rc = RunJacobianWalk(e, kOpColumnNorm, nullptr, col)) != CB200_OK) return rc;
+  if ((rc = SumOverRanks(e, col, ne)) != CB200_OK) return rc;
+  CB200_CUDA(e, cudaMemcpyAsync(out, col, ne * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CB200_CUDA(e, cudaStreamSynchronize(s));
+  return CB200_OK;
+}
+
+int cb200_engine_jacobian_scale_columns(cb200_engine* e, const double* scale) {
+  int rc = PrepareLinearAlgebra(e, false);
+  if (rc != CB200_OK) return rc;
+  if (!scale) return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "scale is required");
+  cudaStream_t s = e->stream;
+  double* col = e->la_col[0].ptr;
+  CB200_CUDA(e, cudaMemcpyAsync(col, scale, static_cast<size_t>(e->num_effective) * sizeof(double),
+                                cudaMemcpyHostToDevice, s));
+  if ((rc = RunJacobianWalk(e, kOpScale, col, nullptr)) != CB200_OK) return rc;
+  CB200_CUDA(e, cudaStreamSynchronize(s));
+  return CB200_OK;
+}
+
+int cb200_engine_cgnr_solve(cb200_engine* e, const double* d_squared,
+                            const cb200_cgnr_options* options, double* solution,
+                            cb200_cgnr_summary* summary) {
+  int rc = PrepareLinearAlgebra(e, true);
+  if (rc != CB200_OK) return rc;
+  if (!options || !solution || !summary)
+    return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "options, solution and summary are required");
+  cudaStream_t s = e->stream;
+  const int ne = e->num_effective, m = e->res_end - e->res_begin;
+  const size_t col_bytes = static_cast<size_t>(ne) * sizeof(double);
+  double *x = e->la_col[0].ptr, *r = e->la_col[1].ptr, *p = e->la_col[2].ptr,
+         *q = e->la_col[3].ptr, *b = e->la_col[4].ptr, *minv = e->la_col[5].ptr,
+         *d2 = d_squared ? e->la_col[6].ptr : nullptr, *colnorm = e->la_col[7].ptr;
+  double* w = e->la_row.ptr;
+  const double* residuals = e->d_residuals.ptr;
+  double* S = e->la_scalars.ptr;  // three rotating sets of scalars
+  const int vgrid = std::max(1, std::min((ne + 255) / 256, 148 * 8));
+  const int rgrid = std::max(1, std::min((m + 255) / 256, 148 * 8));
+  std::memset(summary, 0, sizeof(*summary));
+
+  CB200_CUDA(e, cudaEventRecord(e->ev[0], s));
+  if (d2) CB200_CUDA(e, cudaMemcpyAsync(d2, d_squared, col_bytes, cudaMemcpyHostToDevice, s));
+  // b = J' residuals, preconditioner from the column norms
+  CB200_CUDA(e, cudaMemsetAsync(b, 0, col_bytes, s));
+  CB200_CUDA(e, cudaMemsetAsync(colnorm, 0, col_bytes, s));
+  if ((rc = RunJacobianWalk(e, kOpLeft, residuals, b)) != CB200_OK) return rc;
+  if ((rc = RunJacobianWalk(e, kOpColumnNorm, nullptr, colnorm)) != CB200_OK) return rc;
+  if ((rc = SumOverRanks(e, b, ne)) != CB200_OK) return rc;
+  if ((rc = SumOverRanks(e, colnorm, ne)) != CB200_OK) return rc;
+  CB200_CUDA(e, cudaMemsetAsync(S, 0, 3 * kSCount * sizeof(double), s));
+  CgInitKernel<<<vgrid, 256, 0, s>>>(ne, colnorm, d2, b, minv, r, p, x, S);
+  CB200_CUDA(e, cudaMemcpyAsync(e->h_la_scalars, S, kSCount * sizeof(double),
+                                cudaMemcpyDeviceToHost, s));
+  CB200_CUDA(e, cudaStreamSynchronize(s));
+  const double norm_b = std::sqrt(e->h_la_scalars[kSRnorm2]);
+  summary->initial_gradient_norm = norm_b;
+  summary->final_residual_norm = norm_b;
+  summary->termination = 1;
+  double q0 = 0.0;  // Q(x) = -x.(b + r) / 2 at x = 0
+  int cur = 0;
+  if (!(norm_b > 0.0) || !std::isfinite(norm_b)) {
+    summary->termination = std::isfinite(norm_b) ? 0 : 2;
+  } else {
+    for (int it = 1; it <= options->max_num_iterations; ++it) {
+      double* Sc = S + cur * kSCount;
+      const int nxt = (cur + 1) % 3;
+      double* Sn = S + nxt * kSCount;
+      // q = J'(J p)
+      if ((rc = RunJacobianWalk(e, kOpRight, p, w)) != CB200_OK) return rc;
+      CB200_CUDA(e, cudaMemsetAsync(q, 0, col_bytes, s));
+      if ((rc = RunJacobianWalk(e, kOpLeft, w, q)) != CB200_OK) return rc;
+      if ((rc = SumOverRanks(e, q, ne)) != CB200_OK) return rc;
+      CgDotKernel<<<vgrid, 256, 0, s>>>(ne, p, q, d2, Sc);
+      CB200_CUDA(e, cudaMemsetAsync(Sn, 0, kSCount * sizeof(double), s));
+      CgUpdateKernel<<<vgrid, 256, 0, s>>>(ne, p, q, d2, minv, b, x, r, Sc, Sn);
+      CgDirectionKernel<<<vgrid, 256, 0, s>>>(ne, r, minv, p, Sc, Sn);
+      CB200_CUDA(e, cudaMemcpyAsync(e->h_la_scalars, S, 3 * kSCount * sizeof(double),
+                                    cudaMemcpyDeviceToHost, s));
+      CB200_CUDA(e, cudaStreamSynchronize(s));
+      const double* hc = e->h_la_scalars + cur * kSCount;
+      const double* hn = e->h_la_scalars + nxt * kSCount;
+      summary->num_iterations = it;
+      const double pq = hc[kSPq], rho = hc[kSRho];
+      if (!(pq > 0.0) || !std::isfinite(pq) || !std::isfinite(rho) || !std::isfinite(hn[kSRho])) {
+        summary->termination = 2;  // the update used a bad alpha: the caller rejects the step
+        break;
+      }
+      summary->final_residual_norm = std::sqrt(hn[kSRnorm2]);
+      const double q1 = -0.5 * hn[kSXbr];
+      const double zeta = it * (q1 - q0) / q1;
+      q0 = q1;
+      cur = nxt;
+      if (it >= options->min_num_iterations &&
+          (summary->final_residual_norm <= options->r_tolerance * norm_b ||
+           zeta < options->q_tolerance)) {
+        summary->termination = 0;
+        break;
+      }
+    }
+  }
+  // model terms for the trust-region step: (J y).b and |J y|^2 over the residuals
+  double* Sm = S + ((cur + 2) % 3) * kSCount;
+  CB200_CUDA(e, cudaMemsetAsync(Sm, 0, kSCount * sizeof(double), s));
+  if ((rc = RunJacobianWalk(e, kOpRight, x, w)) != CB200_OK) return rc;
+  CgModelKernel<<<rgrid, 256, 0, s>>>(m, w, residuals, Sm);
+  if (e->comm && e->world > 1) {
+    NcclApi* n = GetNccl();
+    if (n->AllReduce(Sm + kSJyB, Sm + kSJyB, 2, kNcclFloat64, kNcclSum, e->comm, s) != 0)
+      return e->Fail(CB200_ERROR_NCCL, "NCCL all-reduce failed");
+  }
+  CB200_CUDA(e, cudaMemcpyAsync(e->h_la_scalars, Sm, kSCount * sizeof(double),
+                                cudaMemcpyDeviceToHost, s));
+  CB200_CUDA(e, cudaMemcpyAsync(solution, x, col_bytes, cudaMemcpyDeviceToHost, s));
+  CB200_CUDA(e, cudaEventRecord(e->ev[4], s));
+  CB200_CUDA(e, cudaStreamSynchronize(s));
+  summary->jy_dot_b = e->h_la_scalars[kSJyB];
+  summary->jy_squared_norm = e->h_la_scalars[kSJy2];
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev[0], e->ev[4]);
+  summary->solve_ms = ms;
+  return CB200_OK;
 }
 
 int cb200_engine_shard_info(cb200_engine* e, int32_t* rb_begin, int32_t* rb_end,

@@ -723,6 +723,10 @@ class ProgramEvaluatorCUDA final : public Evaluator {
   }
 
   std::unique_ptr<SparseMatrix> CreateJacobian() const override {
+    if (options_.jacobian_on_device)
+      return std::make_unique<DeviceResidentJacobian>(engine_, layout_.num_residuals,
+                                                      program_->NumEffectiveParameters(),
+                                                      layout_.num_jacobian_values);
     std::unique_ptr<SparseMatrix> m = CreateJacobianFromLayout(*program_, layout_);
     // Page-lock the slices this rank's device writes into.
     int64_t segments[3 * 32];
@@ -751,7 +755,10 @@ class ProgramEvaluatorCUDA final : public Evaluator {
         cursor += n;
       }
     }
-    const uint32_t flags = evaluate_options.apply_loss_function ? CB200_APPLY_LOSS_FUNCTION : 0u;
+    uint32_t flags = evaluate_options.apply_loss_function ? CB200_APPLY_LOSS_FUNCTION : 0u;
+    // A device-resident Jacobian keeps its values, and the residuals its solver reads, in HBM.
+    if (dynamic_cast<DeviceResidentJacobian*>(jacobian) != nullptr)
+      flags |= CB200_KEEP_JACOBIAN_ON_DEVICE | CB200_KEEP_RESIDUALS_ON_DEVICE;
     const int rc = cb200_engine_evaluate(engine_, state, plus_jacobians_, flags, cost, residuals,
                                          gradient, jacobian ? jacobian->mutable_values() : nullptr);
     const double seconds =
@@ -806,7 +813,8 @@ std::unique_ptr<Evaluator> Evaluator::Create(const Evaluator::Options& options, 
     case SPARSE_SCHUR:
     case ITERATIVE_SCHUR:
     case CGNR:
-      format = options.sparse_linear_algebra_library_type == CUDA_SPARSE
+      format = (options.sparse_linear_algebra_library_type == CUDA_SPARSE &&
+                !options.jacobian_on_device)
                    ? CB200_JACOBIAN_COMPRESSED_ROW
                    : CB200_JACOBIAN_BLOCK_SPARSE;
       break;

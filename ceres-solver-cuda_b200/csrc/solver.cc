@@ -186,6 +186,11 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
   eo.use_cuda = true;
   eo.registered_cuda_evaluators = options.registered_cuda_evaluators;
   eo.device = options.cuda_device;
+  // CGNR with CUDA_SPARSE is the reference's device-resident combination
+  // (cgnr_solver.cc CudaCgnrSolver): the Jacobian stays in HBM and conjugate gradients on
+  // the normal equations run there (cb200_engine_cgnr_solve).
+  eo.jacobian_on_device = options.linear_solver_type == CGNR &&
+                          options.sparse_linear_algebra_library_type == CUDA_SPARSE;
   std::unique_ptr<internal::Evaluator> evaluator =
       internal::Evaluator::Create(eo, program.get(), &summary->message);
   if (!evaluator) return;
@@ -204,8 +209,11 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
   std::vector<double> x(n), x_plus(n), residuals(m), gradient(ne), scale(ne, 1.0);
   std::vector<double> diagonal(ne), D2(ne), y, delta(ne), model(m);
   program->ParameterBlocksToStateVector(x.data());
+  auto* resident = dynamic_cast<internal::DeviceResidentJacobian*>(jacobian.get());
+  // with a device-resident Jacobian the residuals stay on the device as well
+  double* const residuals_out = resident ? nullptr : residuals.data();
   double cost = 0.0;
-  if (!evaluator->Evaluate(x.data(), &cost, residuals.data(), gradient.data(), jacobian.get())) {
+  if (!evaluator->Evaluate(x.data(), &cost, residuals_out, gradient.data(), jacobian.get())) {
     summary->message = "Initial residual and Jacobian evaluation failed.";
     return;
   }
@@ -235,16 +243,42 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
     }
     for (int i = 0; i < ne; ++i) D2[i] = diagonal[i] / radius;
     const double ls_start = Seconds();
-    const int ls_iterations = SolveNormalEquations(*jacobian, D2.data(), residuals.data(),
-                                                   options.max_linear_solver_iterations,
-                                                   1e-2 * options.eta, &y);
-    summary->linear_solver_time_in_seconds += Seconds() - ls_start;
-    // step = -y (scaled space); model cost change = -m'(r + m/2), m = J step
-    std::fill(model.begin(), model.end(), 0.0);
-    for (int i = 0; i < ne; ++i) y[i] = -y[i];
-    jacobian->RightMultiplyAndAccumulate(y.data(), model.data());
+    int ls_iterations = 0;
     double model_cost_change = 0.0, step_norm = 0.0, x_norm = 0.0;
-    for (int i = 0; i < m; ++i) model_cost_change -= model[i] * (residuals[i] + 0.5 * model[i]);
+    bool linear_solver_ok = true;
+    if (resident) {
+      // levenberg_marquardt_strategy.cc:97-118: inexact step, stopped by the relative
+      // decrease of the quadratic model (eta)
+      cb200_cgnr_options cg_options;
+      cg_options.min_num_iterations = options.min_linear_solver_iterations;
+      cg_options.max_num_iterations = options.max_linear_solver_iterations;
+      cg_options.r_tolerance = -1.0;
+      cg_options.q_tolerance = options.eta;
+      cb200_cgnr_summary cg;
+      y.assign(ne, 0.0);
+      if (cb200_engine_cgnr_solve(resident->engine(), D2.data(), &cg_options, y.data(), &cg) !=
+          CB200_OK) {
+        summary->termination_type = FAILURE;
+        summary->message = std::string("cb200_engine_cgnr_solve: ") +
+                           cb200_engine_last_error(resident->engine());
+        break;
+      }
+      ls_iterations = cg.num_iterations;
+      linear_solver_ok = cg.termination != 2;
+      // step = -y: model cost change = (J y).r - |J y|^2 / 2
+      model_cost_change = cg.jy_dot_b - 0.5 * cg.jy_squared_norm;
+      for (int i = 0; i < ne; ++i) y[i] = -y[i];
+    } else {
+      ls_iterations = SolveNormalEquations(*jacobian, D2.data(), residuals.data(),
+                                           options.max_linear_solver_iterations,
+                                           1e-2 * options.eta, &y);
+      // step = -y (scaled space); model cost change = -m'(r + m/2), m = J step
+      std::fill(model.begin(), model.end(), 0.0);
+      for (int i = 0; i < ne; ++i) y[i] = -y[i];
+      jacobian->RightMultiplyAndAccumulate(y.data(), model.data());
+      for (int i = 0; i < m; ++i) model_cost_change -= model[i] * (residuals[i] + 0.5 * model[i]);
+    }
+    summary->linear_solver_time_in_seconds += Seconds() - ls_start;
     for (int i = 0; i < ne; ++i) { delta[i] = y[i] * scale[i]; step_norm += delta[i] * delta[i]; }
     for (int i = 0; i < n; ++i) x_norm += x[i] * x[i];
     step_norm = std::sqrt(step_norm);
@@ -253,7 +287,7 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
     is.linear_solver_iterations = ls_iterations;
     is.step_norm = step_norm;
     double new_cost = 0.0;
-    bool ok = model_cost_change > 0.0 && evaluator->Plus(x.data(), delta.data(), x_plus.data()) &&
+    bool ok = linear_solver_ok && model_cost_change > 0.0 && evaluator->Plus(x.data(), delta.data(), x_plus.data()) &&
               evaluator->Evaluate(x_plus.data(), &new_cost, nullptr, nullptr, nullptr);
     const double relative_decrease = ok ? (cost - new_cost) / model_cost_change : -1.0;
     is.relative_decrease = relative_decrease;
@@ -261,7 +295,7 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
       is.step_is_successful = true;
       is.cost_change = cost - new_cost;
       x = x_plus;
-      if (!evaluator->Evaluate(x.data(), &cost, residuals.data(), gradient.data(),
+      if (!evaluator->Evaluate(x.data(), &cost, residuals_out, gradient.data(),
                                jacobian.get())) {
         summary->termination_type = FAILURE;
         summary->message = "Residual and Jacobian evaluation failed.";

@@ -4,7 +4,7 @@
 // observation, HuberLossCUDA when --robustify, points eliminated before cameras.
 //
 //   bundle_adjuster --input=problem.txt [--robustify] [--num_iterations=20]
-//                   [--linear_solver=iterative_schur|cgnr] [--constant_first_camera]
+//                   [--linear_solver=iterative_schur|cgnr|cgnr_cuda] [--constant_first_camera]
 //   bundle_adjuster --synthetic=16,2000,8000 ...
 //
 // The input is a BAL text file (https://grail.cs.washington.edu/projects/bal/):
@@ -91,7 +91,7 @@ int main(int argc, char** argv) {
     bal.Synthesize(nc, np, nobs, 1);
   } else {
     std::fprintf(stderr, "usage: %s --input=<bal file> | --synthetic=nc,np,nobs [--robustify] "
-                 "[--num_iterations=N] [--linear_solver=iterative_schur|cgnr]\n", argv[0]);
+                 "[--num_iterations=N] [--linear_solver=iterative_schur|cgnr|cgnr_cuda]\n", argv[0]);
     return 1;
   }
   const bool robustify = Flag(argc, argv, "--robustify") != nullptr;
@@ -113,7 +113,13 @@ int main(int argc, char** argv) {
   ceres::Solver::Options options;
   options.max_num_iterations = iters ? std::atoi(iters) : 20;
   options.minimizer_progress_to_stdout = true;
-  options.linear_solver_type = (ls && !std::strcmp(ls, "cgnr")) ? ceres::CGNR : ceres::ITERATIVE_SCHUR;
+  options.linear_solver_type = ceres::ITERATIVE_SCHUR;
+  if (ls && !std::strcmp(ls, "cgnr")) options.linear_solver_type = ceres::CGNR;
+  if (ls && !std::strcmp(ls, "cgnr_cuda")) {
+    // the Jacobian never leaves the device: evaluation and conjugate gradients both run there
+    options.linear_solver_type = ceres::CGNR;
+    options.sparse_linear_algebra_library_type = ceres::CUDA_SPARSE;
+  }
   // The points come before the cameras.
   auto* ordering = new ceres::ParameterBlockOrdering;
   for (int i = 0; i < bal.num_points; ++i) ordering->AddElementToGroup(&bal.points[3 * i], 0);

@@ -83,6 +83,9 @@ class Evaluator {
     int shard_rank = 0;
     int shard_world_size = 1;
     const void* nccl_unique_id = nullptr;  // 128 bytes, enables the all-reduce
+    // CreateJacobian() returns a DeviceResidentJacobian: values stay in HBM and the linear
+    // algebra runs there (block-sparse value layout, whatever the solver type).
+    bool jacobian_on_device = false;
   };
 
   static std::unique_ptr<Evaluator> Create(const Options& options, Program* program,

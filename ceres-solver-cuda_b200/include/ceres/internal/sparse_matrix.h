@@ -16,6 +16,8 @@
 #define CERES_B200_INTERNAL_SPARSE_MATRIX_H_
 
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -54,7 +56,7 @@ class SparseMatrix {
   int num_cols() const { return num_cols_; }
   int64_t num_nonzeros() const { return num_nonzeros_; }
   int64_t values_size() const { return values_size_; }
-  void SetZero() { std::memset(values_, 0, sizeof(double) * values_size_); }
+  void SetZero() { if (values_) std::memset(values_, 0, sizeof(double) * values_size_); }
   // Row-major num_rows x num_cols.
   virtual void ToDenseMatrix(std::vector<double>* dense) const = 0;
   // The operations the trust-region loop needs from a Jacobian
@@ -179,6 +181,57 @@ class CompressedRowSparseMatrix final : public SparseMatrix {
  private:
   std::vector<int> rows_, cols_;
   std::vector<Block> row_blocks_, col_blocks_;
+};
+
+// A Jacobian whose values never leave the device: the
+// evaluator leaves them in HBM (CB200_KEEP_JACOBIAN_ON_DEVICE) and every operation the
+// trust-region loop needs runs there through the C ABI.  Counterpart of the reference's
+// CudaSparseMatrix (internal/ceres/cuda_sparse_matrix.h) for the evaluator's own layout,
+// so no conversion and no host copy of the values exists.  values() is null.
+class DeviceResidentJacobian final : public SparseMatrix {
+ public:
+  DeviceResidentJacobian(cb200_engine* engine, int num_rows, int num_cols, int64_t num_nonzeros)
+      : engine_(engine) {
+    num_rows_ = num_rows;
+    num_cols_ = num_cols;
+    num_nonzeros_ = num_nonzeros;
+  }
+  cb200_engine* engine() const { return engine_; }
+  void RightMultiplyAndAccumulate(const double* x, double* y) const override {
+    std::vector<double> t(num_rows_);
+    Check(cb200_engine_jacobian_multiply(engine_, 0, x, t.data()));
+    for (int i = 0; i < num_rows_; ++i) y[i] += t[i];
+  }
+  void LeftMultiplyAndAccumulate(const double* x, double* y) const override {
+    std::vector<double> t(num_cols_);
+    Check(cb200_engine_jacobian_multiply(engine_, 1, x, t.data()));
+    for (int i = 0; i < num_cols_; ++i) y[i] += t[i];
+  }
+  void SquaredColumnNorm(double* x) const override {
+    Check(cb200_engine_jacobian_squared_column_norm(engine_, x));
+  }
+  void ScaleColumns(const double* scale) override {
+    Check(cb200_engine_jacobian_scale_columns(engine_, scale));
+  }
+  // Column by column through J e_c; meant for tests on small problems.
+  void ToDenseMatrix(std::vector<double>* dense) const override {
+    dense->assign(static_cast<size_t>(num_rows_) * num_cols_, 0.0);
+    std::vector<double> e(num_cols_, 0.0), col(num_rows_);
+    for (int c = 0; c < num_cols_; ++c) {
+      e[c] = 1.0;
+      Check(cb200_engine_jacobian_multiply(engine_, 0, e.data(), col.data()));
+      e[c] = 0.0;
+      for (int r = 0; r < num_rows_; ++r) (*dense)[static_cast<size_t>(r) * num_cols_ + c] = col[r];
+    }
+  }
+
+ private:
+  void Check(int rc) const {
+    if (rc == CB200_OK) return;
+    std::fprintf(stderr, "device Jacobian operation failed: %s\n", cb200_engine_last_error(engine_));
+    std::abort();  // like the reference's CHECK on CUDA failures
+  }
+  cb200_engine* engine_;
 };
 
 }  // namespace internal

@@ -81,6 +81,7 @@ class Solver {
     LinearSolverType linear_solver_type = SPARSE_NORMAL_CHOLESKY;
     SparseLinearAlgebraLibraryType sparse_linear_algebra_library_type = NO_SPARSE;
     std::shared_ptr<ParameterBlockOrdering> linear_solver_ordering;
+    int min_linear_solver_iterations = 0;
     int max_linear_solver_iterations = 500;
     double eta = 1e-1;
     bool jacobi_scaling = true;

@@ -36,6 +36,11 @@ extern "C" {
 /* cb200_engine_evaluate flags */
 #define CB200_APPLY_LOSS_FUNCTION 1u /* Evaluator::EvaluateOptions::apply_loss_function */
 #define CB200_SKIP_HOST_COPY 2u      /* leave outputs on the device (see cb200_engine_device_ptr) */
+#define CB200_KEEP_RESIDUALS_ON_DEVICE 4u /* compute the residuals, do not copy them to the host
+                                             (the residuals argument may then be NULL) */
+#define CB200_KEEP_JACOBIAN_ON_DEVICE 8u  /* compute the Jacobian and leave it on the device for the
+                                             cb200_engine_jacobian_* / cb200_engine_cgnr_solve calls
+                                             (the jacobian_values argument may then be NULL) */
 
 #define CB200_JACOBIAN_BLOCK_SPARSE 0   /* BlockJacobianWriter  (internal/ceres/block_jacobian_writer.cc) */
 #define CB200_JACOBIAN_COMPRESSED_ROW 1 /* CompressedRowJacobianWriter (compressed_row_jacobian_writer.cc) */
@@ -215,6 +220,50 @@ void* cb200_engine_device_ptr(cb200_engine* engine, int which);
 int cb200_engine_shard_info(cb200_engine* engine, int32_t* rb_begin, int32_t* rb_end,
                             int32_t* residual_begin, int32_t* residual_end,
                             int64_t* segments, int32_t max_segments);
+
+/* ---- linear algebra on the device-resident Jacobian of the last evaluation
+ * (SURVEY.md section 8(f) items 1-2).  The 5.6 GB of Jacobian values of a large bundle
+ * adjustment problem then never cross PCIe.  They replace, for a Jacobian that stays in HBM,
+ * BlockSparseMatrix / CompressedRowSparseMatrix::{RightMultiplyAndAccumulate,
+ * LeftMultiplyAndAccumulate, SquaredColumnNorm, ScaleColumns}
+ * (internal/ceres/block_sparse_matrix.cc:150-280, compressed_row_sparse_matrix.cc:300-470),
+ * their CUDA counterparts (internal/ceres/cuda_sparse_matrix.cc) and the CUDA CGNR solver
+ * (internal/ceres/cgnr_solver.cc:190-330).  Vectors are HOST pointers: x-like vectors have
+ * num_effective_parameters entries, residual-like vectors num_residuals (with sharding a
+ * rank reads / writes only its residual slice; column-space results are summed over ranks). */
+
+/* transpose == 0: y = J x;  transpose != 0: y = J' x. */
+int cb200_engine_jacobian_multiply(cb200_engine* engine, int transpose, const double* x,
+                                   double* y);
+/* out[c] = sum over rows of J(r, c)^2 */
+int cb200_engine_jacobian_squared_column_norm(cb200_engine* engine, double* out);
+/* J <- J diag(scale) */
+int cb200_engine_jacobian_scale_columns(cb200_engine* engine, const double* scale);
+
+typedef struct cb200_cgnr_options {
+  int32_t min_num_iterations;
+  int32_t max_num_iterations;
+  double r_tolerance; /* stop when |residual| <= r_tolerance * |J'b|  (conjugate_gradients_solver.h) */
+  double q_tolerance; /* stop when the relative decrease of the quadratic model falls below this */
+} cb200_cgnr_options;
+
+typedef struct cb200_cgnr_summary {
+  int32_t num_iterations;
+  int32_t termination;        /* 0 converged, 1 iteration limit, 2 breakdown (non-positive curvature / non-finite) */
+  double initial_gradient_norm; /* |J'b| */
+  double final_residual_norm;
+  double jy_dot_b;            /* (J y).b and |J y|^2 for the trust-region model: with the step */
+  double jy_squared_norm;     /* -y, model_cost_change = (J y).b - |J y|^2 / 2 */
+  double solve_ms;            /* device time of the call */
+} cb200_cgnr_summary;
+
+/* Solves (J'J + diag(d_squared)) y = J'b by preconditioned conjugate gradients on the
+ * normal equations without forming them, b = the residuals of the last evaluation (on the
+ * device) and J its Jacobian (CB200_KEEP_*_ON_DEVICE), preconditioner
+ * diag(J'J + d_squared)^-1.  d_squared may be NULL (zero).  solution: num_effective doubles. */
+int cb200_engine_cgnr_solve(cb200_engine* engine, const double* d_squared,
+                            const cb200_cgnr_options* options, double* solution,
+                            cb200_cgnr_summary* summary);
 
 /* Timing of the last evaluation in milliseconds (CUDA events on the engine's
  * stream): out[0] kernels only, out[1] kernels + reductions + all-reduce,

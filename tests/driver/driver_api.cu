@@ -259,6 +259,41 @@ int drv_evaluate_device(void* h, int apply_loss_function, int want_residuals, in
                                       want_residuals, want_gradient, want_jacobian, cost);
 }
 
+// Linear algebra on the Jacobian the last evaluation left on the device (C ABI pass-through).
+static int LaResult(DriverProblem* dp, int rc) {
+  if (rc != CB200_OK) dp->error = cb200_engine_last_error(dp->evaluator->engine());
+  return rc;
+}
+int drv_jacobian_multiply(void* h, int transpose, const double* x, double* y) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  if (!dp->evaluator) return -100;
+  return LaResult(dp, cb200_engine_jacobian_multiply(dp->evaluator->engine(), transpose, x, y));
+}
+int drv_jacobian_squared_column_norm(void* h, double* out) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  if (!dp->evaluator) return -100;
+  return LaResult(dp, cb200_engine_jacobian_squared_column_norm(dp->evaluator->engine(), out));
+}
+int drv_jacobian_scale_columns(void* h, const double* scale) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  if (!dp->evaluator) return -100;
+  return LaResult(dp, cb200_engine_jacobian_scale_columns(dp->evaluator->engine(), scale));
+}
+// out: [iterations, termination, |J'b|, final residual norm, (Jy).b, |Jy|^2, ms]
+int drv_cgnr_solve(void* h, const double* d_squared, int min_iterations, int max_iterations,
+                   double r_tolerance, double q_tolerance, double* solution, double* out) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  if (!dp->evaluator) return -100;
+  cb200_cgnr_options o{min_iterations, max_iterations, r_tolerance, q_tolerance};
+  cb200_cgnr_summary s;
+  const int rc = cb200_engine_cgnr_solve(dp->evaluator->engine(), d_squared, &o, solution, &s);
+  if (rc != CB200_OK) { dp->error = cb200_engine_last_error(dp->evaluator->engine()); return rc; }
+  out[0] = s.num_iterations; out[1] = s.termination; out[2] = s.initial_gradient_norm;
+  out[3] = s.final_residual_norm; out[4] = s.jy_dot_b; out[5] = s.jy_squared_norm;
+  out[6] = s.solve_ms;
+  return rc;
+}
+
 int drv_timing(void* h, double* out4) {
   auto* dp = static_cast<DriverProblem*>(h);
   if (!dp->evaluator) return -1;
@@ -280,11 +315,12 @@ int drv_plus(void* h, const double* state, const double* delta, double* out) {
 // per parameter block (or NULL).  out: [initial_cost, final_cost, iterations,
 // successful_steps, termination_type, num_jacobian_evaluations, num_residual_evaluations].
 // The solution is written to the driver's parameter values (drv_user_values).
-int drv_solve(void* h, int linear_solver_type, int max_num_iterations, const int* ordering,
-              int device, double* out) {
+int drv_solve(void* h, int linear_solver_type, int cuda_sparse, int max_num_iterations,
+              const int* ordering, int device, double* out) {
   auto* dp = static_cast<DriverProblem*>(h);
   ceres::Solver::Options options;
   options.linear_solver_type = static_cast<ceres::LinearSolverType>(linear_solver_type);
+  if (cuda_sparse) options.sparse_linear_algebra_library_type = ceres::CUDA_SPARSE;
   options.max_num_iterations = max_num_iterations;
   options.cuda_device = device;
   if (ordering) {
@@ -303,6 +339,7 @@ int drv_solve(void* h, int linear_solver_type, int max_num_iterations, const int
   out[4] = static_cast<double>(summary.termination_type);
   out[5] = summary.num_jacobian_evaluations;
   out[6] = summary.num_residual_evaluations;
+  out[7] = summary.linear_solver_time_in_seconds;
   return summary.IsSolutionUsable() ? 1 : 0;
 }
 
