@@ -176,7 +176,7 @@ __device__ __forceinline__ void RedAddF64(double* address, double value) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(address), "d"(value) : "memory");
 }
 
-enum { kOpRight = 0, kOpLeft = 1, kOpColumnNorm = 2, kOpScale = 3 };
+enum { kOpRight = 0, kOpLeft = 1, kOpColumnNorm = 2, kOpScale = 3, kOpNormal = 4 };
 
 // One thread per residual block.  x / y meaning per operation:
 //   kOpRight:      y[rows] = sum_c J(r, c) x[c]        (y indexed by local residual)
@@ -187,11 +187,19 @@ template <int kOp>
 __global__ void __launch_bounds__(256) JacobianWalkKernel(const JacobianWalk w,
                                                           const double* __restrict__ x,
                                                           double* __restrict__ y) {
+  // Columns are handled in chunks of kChunk with the loads of a chunk issued back to back:
+  // a thread's row of a cell is contiguous, so its sectors are requested together and
+  // used once, instead of being re-fetched after other warps evicted them.
+  constexpr int kChunk = 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.n; i += gridDim.x * blockDim.x) {
     const int row0 = w.respos[i];
     if (kOp == kOpRight) {
-      for (int r = 0; r < w.kres; ++r) {
-        double acc = 0.0;
+      // rows in groups of kRows accumulators; x is loaded once per column and group
+      constexpr int kRows = 8;
+      for (int r0 = 0; r0 < w.kres; r0 += kRows) {
+        double acc[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) acc[r] = 0.0;
         for (int j = 0; j < w.nb; ++j) {
           const size_t at = static_cast<size_t>(j) * w.n + i;
           const int jp = w.jpos[at];
@@ -199,10 +207,28 @@ __global__ void __launch_bounds__(256) JacobianWalkKernel(const JacobianWalk w,
           const int col = w.doff[at];
           const int tan = w.plain ? w.sizes[j] : w.pb_table[8 * w.pb[at] + 2];
           const int rs = w.crs ? w.jstride[i] : tan;
-          const double* __restrict__ v = w.values + jp + static_cast<size_t>(r) * rs;
-          for (int c = 0; c < tan; ++c) acc = fma(v[c], x[col + c], acc);
+          const double* __restrict__ v = w.values + jp + static_cast<size_t>(r0) * rs;
+          const double* __restrict__ xs = x + col;
+          for (int c0 = 0; c0 < tan; c0 += kChunk) {
+            double b[kChunk];
+#pragma unroll
+            for (int k = 0; k < kChunk; ++k) b[k] = c0 + k < tan ? xs[c0 + k] : 0.0;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+              if (r0 + r < w.kres) {
+                double a[kChunk];
+#pragma unroll
+                for (int k = 0; k < kChunk; ++k)
+                  a[k] = c0 + k < tan ? v[static_cast<size_t>(r) * rs + c0 + k] : 0.0;
+#pragma unroll
+                for (int k = 0; k < kChunk; ++k) acc[r] = fma(a[k], b[k], acc[r]);
+              }
+            }
+          }
         }
-        y[row0 + r] = acc;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+          if (r0 + r < w.kres) y[row0 + r0 + r] = acc[r];
       }
     } else {
       for (int j = 0; j < w.nb; ++j) {
@@ -213,19 +239,104 @@ __global__ void __launch_bounds__(256) JacobianWalkKernel(const JacobianWalk w,
         const int tan = w.plain ? w.sizes[j] : w.pb_table[8 * w.pb[at] + 2];
         const int rs = w.crs ? w.jstride[i] : tan;
         double* v = w.values + jp;
-        for (int c = 0; c < tan; ++c) {
+        for (int c0 = 0; c0 < tan; c0 += kChunk) {
           if (kOp == kOpScale) {
-            const double sc = x[col + c];
-            for (int r = 0; r < w.kres; ++r) v[static_cast<size_t>(r) * rs + c] *= sc;
-          } else {
-            double acc = 0.0;
+            double sc[kChunk];
+#pragma unroll
+            for (int k = 0; k < kChunk; ++k) sc[k] = c0 + k < tan ? x[col + c0 + k] : 1.0;
             for (int r = 0; r < w.kres; ++r) {
-              const double a = v[static_cast<size_t>(r) * rs + c];
-              acc = fma(a, kOp == kOpLeft ? x[row0 + r] : a, acc);
+              double* row = v + static_cast<size_t>(r) * rs + c0;
+#pragma unroll
+              for (int k = 0; k < kChunk; ++k)
+                if (c0 + k < tan) row[k] *= sc[k];
             }
-            RedAddF64(y + col + c, acc);
+          } else {
+            double acc[kChunk];
+#pragma unroll
+            for (int k = 0; k < kChunk; ++k) acc[k] = 0.0;
+            for (int r = 0; r < w.kres; ++r) {
+              const double* row = v + static_cast<size_t>(r) * rs + c0;
+              const double wr = kOp == kOpLeft ? x[row0 + r] : 0.0;
+#pragma unroll
+              for (int k = 0; k < kChunk; ++k) {
+                const double a = c0 + k < tan ? row[k] : 0.0;
+                acc[k] = fma(a, kOp == kOpLeft ? wr : a, acc[k]);
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < kChunk; ++k)
+              if (c0 + k < tan) RedAddF64(y + col + c0 + k, acc[k]);
           }
         }
+      }
+    }
+  }
+}
+
+
+// y += J'(J x) with ONE pass over the values: a residual block's rows of J x stay in
+// registers and are multiplied straight back through the same cells (second read from
+// cache), so a conjugate-gradient iteration on the normal equations reads the Jacobian once
+// instead of twice.  Needs num_residuals <= kNormalRows.
+constexpr int kNormalRows = 8;
+__global__ void __launch_bounds__(256) JacobianNormalKernel(const JacobianWalk w,
+                                                            const double* __restrict__ x,
+                                                            double* __restrict__ y) {
+  constexpr int kChunk = 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.n; i += gridDim.x * blockDim.x) {
+    double wr[kNormalRows];
+#pragma unroll
+    for (int r = 0; r < kNormalRows; ++r) wr[r] = 0.0;
+    for (int j = 0; j < w.nb; ++j) {
+      const size_t at = static_cast<size_t>(j) * w.n + i;
+      const int jp = w.jpos[at];
+      if (jp < 0) continue;
+      const int tan = w.plain ? w.sizes[j] : w.pb_table[8 * w.pb[at] + 2];
+      const int rs = w.crs ? w.jstride[i] : tan;
+      const double* __restrict__ v = w.values + jp;
+      const double* __restrict__ xs = x + w.doff[at];
+      for (int c0 = 0; c0 < tan; c0 += kChunk) {
+        double b[kChunk];
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k) b[k] = c0 + k < tan ? xs[c0 + k] : 0.0;
+#pragma unroll
+        for (int r = 0; r < kNormalRows; ++r) {
+          if (r < w.kres) {
+            double a[kChunk];
+#pragma unroll
+            for (int k = 0; k < kChunk; ++k)
+              a[k] = c0 + k < tan ? v[static_cast<size_t>(r) * rs + c0 + k] : 0.0;
+#pragma unroll
+            for (int k = 0; k < kChunk; ++k) wr[r] = fma(a[k], b[k], wr[r]);
+          }
+        }
+      }
+    }
+    for (int j = 0; j < w.nb; ++j) {
+      const size_t at = static_cast<size_t>(j) * w.n + i;
+      const int jp = w.jpos[at];
+      if (jp < 0) continue;
+      const int col = w.doff[at];
+      const int tan = w.plain ? w.sizes[j] : w.pb_table[8 * w.pb[at] + 2];
+      const int rs = w.crs ? w.jstride[i] : tan;
+      const double* __restrict__ v = w.values + jp;
+      for (int c0 = 0; c0 < tan; c0 += kChunk) {
+        double acc[kChunk];
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k) acc[k] = 0.0;
+#pragma unroll
+        for (int r = 0; r < kNormalRows; ++r) {
+          if (r < w.kres) {
+#pragma unroll
+            for (int k = 0; k < kChunk; ++k) {
+              const double a = c0 + k < tan ? v[static_cast<size_t>(r) * rs + c0 + k] : 0.0;
+              acc[k] = fma(a, wr[r], acc[k]);
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k)
+          if (c0 + k < tan) RedAddF64(y + col + c0 + k, acc[k]);
       }
     }
   }
@@ -1017,6 +1128,7 @@ static int RunJacobianWalk(cb200_engine* e, int op, const double* x, double* y) 
       case kOpRight: JacobianWalkKernel<kOpRight><<<grid, 256, 0, s>>>(w, x, y); break;
       case kOpLeft: JacobianWalkKernel<kOpLeft><<<grid, 256, 0, s>>>(w, x, y); break;
       case kOpColumnNorm: JacobianWalkKernel<kOpColumnNorm><<<grid, 256, 0, s>>>(w, x, y); break;
+      case kOpNormal: JacobianNormalKernel<<<grid, 256, 0, s>>>(w, x, y); break;
       default: JacobianWalkKernel<kOpScale><<<grid, 256, 0, s>>>(w, x, y); break;
     }
   }
@@ -1125,6 +1237,9 @@ int cb200_engine_cgnr_solve(cb200_engine* e, const double* d_squared,
   const int vgrid = std::max(1, std::min((ne + 255) / 256, 148 * 8));
   const int rgrid = std::max(1, std::min((m + 255) / 256, 148 * 8));
   std::memset(summary, 0, sizeof(*summary));
+  bool one_pass = true;
+  for (const ResidualType* t : e->types)
+    if (t->n_local > 0 && t->desc.num_residuals > kNormalRows) one_pass = false;
 
   CB200_CUDA(e, cudaEventRecord(e->ev[0], s));
   if (d2) CB200_CUDA(e, cudaMemcpyAsync(d2, d_squared, col_bytes, cudaMemcpyHostToDevice, s));
@@ -1153,10 +1268,14 @@ int cb200_engine_cgnr_solve(cb200_engine* e, const double* d_squared,
       double* Sc = S + cur * kSCount;
       const int nxt = (cur + 1) % 3;
       double* Sn = S + nxt * kSCount;
-      // q = J'(J p)
-      if ((rc = RunJacobianWalk(e, kOpRight, p, w)) != CB200_OK) return rc;
+      // q = J'(J p): one pass over the values when every type's rows fit in registers
       CB200_CUDA(e, cudaMemsetAsync(q, 0, col_bytes, s));
-      if ((rc = RunJacobianWalk(e, kOpLeft, w, q)) != CB200_OK) return rc;
+      if (one_pass) {
+        if ((rc = RunJacobianWalk(e, kOpNormal, p, q)) != CB200_OK) return rc;
+      } else {
+        if ((rc = RunJacobianWalk(e, kOpRight, p, w)) != CB200_OK) return rc;
+        if ((rc = RunJacobianWalk(e, kOpLeft, w, q)) != CB200_OK) return rc;
+      }
       if ((rc = SumOverRanks(e, q, ne)) != CB200_OK) return rc;
       CgDotKernel<<<vgrid, 256, 0, s>>>(ne, p, q, d2, Sc);
       CB200_CUDA(e, cudaMemsetAsync(Sn, 0, kSCount * sizeof(double), s));
