@@ -38,6 +38,22 @@ for fmt, kw in ((0, {}), (1, {"subset_manifold": True})):
     rs = slice(info["residual_begin"], info["residual_end"])
     e_res = np.max(np.abs(r[rs] - r0[rs])) / np.max(np.abs(r0))
     e_jac = max(np.max(np.abs(j[gb:gb + ln] - j0[gb:gb + ln])) for gb, ln, _ in info["segments"]) / np.max(np.abs(j0))
+    # device-resident linear algebra on the sharded Jacobian: column-space results are
+    # summed over the ranks, so every rank must reproduce the unsharded numbers
+    rng = np.random.default_rng(7)
+    xv = rng.normal(size=full.num_effective_parameters)
+    wv = rng.normal(size=full.num_residuals)
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+    e_la = max(rel(sh.jacobian_multiply(wv, transpose=True), full.jacobian_multiply(wv, transpose=True)),
+               rel(sh.jacobian_squared_column_norm(), full.jacobian_squared_column_norm()),
+               rel(sh.jacobian_multiply(xv)[rs], full.jacobian_multiply(xv)[rs]))
+    d2 = full.jacobian_squared_column_norm() / 1e4
+    y0, s0 = full.cgnr_solve(d2, max_iterations=30, r_tolerance=-1, q_tolerance=-1)
+    y1, s1 = sh.cgnr_solve(d2, max_iterations=30, r_tolerance=-1, q_tolerance=-1)
+    e_cg = max(rel(y1, y0), abs(s1["jy_dot_b"] - s0["jy_dot_b"]) / abs(s0["jy_dot_b"]))
+    print(f"rank {rank}/{world} fmt {fmt}: device linear algebra {e_la:.1e}, 30 CG iterations {e_cg:.1e} "
+          f"({s1['ms'] / 30:.3f} ms/iteration sharded, {s0['ms'] / 30:.3f} unsharded) "
+          f"{'OK' if e_la <= 1e-11 and e_cg <= 1e-8 else 'MISMATCH'}", flush=True)
     t = sh.timing()
     print(f"rank {rank}/{world} fmt {fmt}: cost {e_cost:.1e} grad {e_grad:.1e} res {e_res:.1e} jac {e_jac:.1e} "
           f"segments {len(info['segments'])} kernel {t['kernel_ms']:.3f} device {t['device_ms']:.3f} ms "
