@@ -15,10 +15,53 @@ double Seconds() {
       .count();
 }
 
+// The vectors that cross PCIe every iteration (state, gradient, step, LM diagonal) live in
+// page-locked memory: pageable copies of 108 MB run at a fraction of the link rate.
+class PinnedVector {
+ public:
+  explicit PinnedVector(size_t n = 0, double value = 0.0) { assign(n, value); }
+  ~PinnedVector() { Release(); }
+  PinnedVector(const PinnedVector&) = delete;
+  PinnedVector& operator=(const PinnedVector& other) {
+    if (size_ != other.size_) assign(other.size_, 0.0);
+    std::copy(other.begin(), other.end(), begin());
+    return *this;
+  }
+  void assign(size_t n, double value) {
+    if (n != size_) {
+      Release();
+      size_ = n;
+      if (n > 0) {
+        data_ = static_cast<double*>(cb200_host_alloc(n * sizeof(double)));
+        cb200_host_pin(data_, n * sizeof(double));
+      }
+    }
+    std::fill(begin(), end(), value);
+  }
+  size_t size() const { return size_; }
+  double* data() { return data_; }
+  const double* data() const { return data_; }
+  double& operator[](size_t i) { return data_[i]; }
+  const double& operator[](size_t i) const { return data_[i]; }
+  double* begin() { return data_; }
+  double* end() { return data_ + size_; }
+  const double* begin() const { return data_; }
+  const double* end() const { return data_ + size_; }
+
+ private:
+  void Release() {
+    if (data_) cb200_host_free(data_);
+    data_ = nullptr;
+    size_ = 0;
+  }
+  double* data_ = nullptr;
+  size_t size_ = 0;
+};
+
 // Solves (J'J + D^2) y = J'r with Jacobi-preconditioned conjugate gradients (CGNR);
 // stand-in for the reference's linear solvers.  Returns the iteration count.
 int SolveNormalEquations(const internal::SparseMatrix& J, const double* D2, const double* r,
-                         int max_iterations, double tolerance, std::vector<double>* y) {
+                         int max_iterations, double tolerance, PinnedVector* y) {
   const int n = J.num_cols(), m = J.num_rows();
   std::vector<double> b(n, 0.0), res(n), z(n), p(n), Ap(n), tmp(m), precond(n);
   J.LeftMultiplyAndAccumulate(r, b.data());
@@ -206,11 +249,17 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
   const double minimizer_start = Seconds();
   const int n = program->NumParameters(), ne = program->NumEffectiveParameters();
   const int m = program->NumResiduals();
-  std::vector<double> x(n), x_plus(n), residuals(m), gradient(ne), scale(ne, 1.0);
-  std::vector<double> diagonal(ne), D2(ne), y, delta(ne), model(m);
+  PinnedVector x(n), x_plus(n), gradient(ne), scale(ne, 1.0), diagonal(ne), D2(ne), y(ne);
+  std::vector<double> delta(ne);
+  // only the host linear solver reads the residuals and the model on the host
+  std::vector<double> residuals, model;
   program->ParameterBlocksToStateVector(x.data());
   auto* resident = dynamic_cast<internal::DeviceResidentJacobian*>(jacobian.get());
   // with a device-resident Jacobian the residuals stay on the device as well
+  if (!resident) {
+    residuals.resize(m);
+    model.resize(m);
+  }
   double* const residuals_out = resident ? nullptr : residuals.data();
   double cost = 0.0;
   if (!evaluator->Evaluate(x.data(), &cost, residuals_out, gradient.data(), jacobian.get())) {
