@@ -36,6 +36,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 #include <utility>
 
 #include "ceres/jet.h"
@@ -215,6 +216,9 @@ __device__ __forceinline__ void CpAsyncWait() {
 #ifndef CB200_KERNEL_FMA_CHECK_CHAINS
 #define CB200_KERNEL_FMA_CHECK_CHAINS 1
 #endif
+#ifndef CB200_KERNEL_SPECIALISE_ALL_OUTPUTS
+#define CB200_KERNEL_SPECIALISE_ALL_OUTPUTS 1  // extra instantiation for the all-outputs call
+#endif
 #ifndef CB200_KERNEL_STAGE_GRADIENT
 #define CB200_KERNEL_STAGE_GRADIENT 1 // warp-staged, sector-coalesced gradient reductions
 #endif
@@ -286,10 +290,26 @@ struct FiniteCheck {
 #endif
 };
 
+// Loss classes may declare `static constexpr bool kNonPositiveCurvature = true` (rho'' <= 0
+// for every s, e.g. Huber, Cauchy): the Corrector's alpha branch is then dead code.
+template <typename Loss, typename = void>
+struct LossCurvature {
+  static constexpr bool kNonPositive = false;
+};
+template <typename Loss>
+struct LossCurvature<Loss, std::enable_if_t<Loss::kNonPositiveCurvature || true>> {
+  static constexpr bool kNonPositive = Loss::kNonPositiveCurvature;
+};
+
 // Kernel variants.
 constexpr int kVariantCost = 0;     // cost / residuals only: plain doubles, no Jets
 constexpr int kVariantPlain = 1;    // Jets; no manifold and no constant block in this type
 constexpr int kVariantGeneric = 2;  // Jets; per-block manifold projection / constant blocks
+// kVariantPlain specialised for the call the minimizer makes after every accepted step: all
+// outputs, loss applied, block-sparse values.  The output flags become compile-time
+// constants, which removes their (uniform) branches and lets the compiler schedule across.
+constexpr int kVariantPlainAll = 3;
+constexpr int kVariantGenericAll = 4;  // kVariantGeneric with all outputs (either value layout)
 
 // ---- derivative passes.  Wide problems (pose graphs: 14 derivative lanes x 6 residuals
 // = 90 live doubles of output alone) are differentiated in several passes, each seeding
@@ -414,7 +434,13 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
   constexpr int kNB = Dims::kNumBlocks;
   constexpr int kNP = Dims::kNumParameters;
   constexpr bool kJets = kVariant != kVariantCost;
-  constexpr bool kGeneric = kVariant == kVariantGeneric;
+  constexpr bool kGeneric = kVariant == kVariantGeneric || kVariant == kVariantGenericAll;
+  constexpr bool kAll = kVariant == kVariantPlainAll || kVariant == kVariantGenericAll;
+  const bool out_residuals = kAll || a.output_residuals;
+  const bool out_jacobian = kAll || a.output_jacobian;
+  const bool out_gradient = kAll || a.output_gradient;
+  const bool apply_loss = kAll || a.apply_loss_function;
+  const bool crs = kVariant != kVariantPlainAll && a.crs;
   using Layout = PrefetchLayout<Functor, kNP, kNB>;
   constexpr bool kPrefetch = Layout::kFits;
   constexpr bool kStage = kJets && Smem::kStageJacobian;
@@ -498,14 +524,14 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
             const int32_t* tab = kGeneric ? a.parameter_block : a.delta_offset;
             CpAsync4(idst + (Layout::kSlotDelta + j) * kEvaluateThreads,
                      tab + static_cast<size_t>(j) * n + r);
-            if (a.output_jacobian)
+            if (out_jacobian)
               CpAsync4(idst + (Layout::kSlotJpos + j) * kEvaluateThreads,
                        a.jacobian_pos + static_cast<size_t>(j) * n + r);
           }
-          if (a.crs && a.output_jacobian)
+          if (crs && out_jacobian)
             CpAsync4(idst + Layout::kSlotRowStride * kEvaluateThreads, a.jacobian_row_stride + r);
         }
-        if (a.output_residuals)
+        if (out_residuals)
           CpAsync4(idst + Layout::kSlotResidual * kEvaluateThreads, a.residual_pos + r);
         if (a.loss_index)
           CpAsync4(idst + Layout::kSlotLoss * kEvaluateThreads, a.loss_index + r);
@@ -590,13 +616,13 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
           plus_off[j] = -1;
           key[j] = delta_off[j];
         }
-        jpos[j] = a.output_jacobian ? table(Layout::kSlotJpos + j, a.jacobian_pos, at) : 0;
+        jpos[j] = out_jacobian ? table(Layout::kSlotJpos + j, a.jacobian_pos, at) : 0;
       }
     }
-    const int respos = a.output_residuals ? table(Layout::kSlotResidual, a.residual_pos, tt) : 0;
+    const int respos = out_residuals ? table(Layout::kSlotResidual, a.residual_pos, tt) : 0;
     int row_stride_crs = 0;
     if constexpr (kJets) {
-      if (a.crs && a.output_jacobian)
+      if (crs && out_jacobian)
         row_stride_crs = table(Layout::kSlotRowStride, a.jacobian_row_stride, tt);
     }
     const Loss* __restrict__ losses = static_cast<const Loss*>(a.loss_table);
@@ -645,11 +671,11 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
       double s = 0.0;
 #pragma unroll
       for (int r = 0; r < kRes; ++r) s += res[r] * res[r];
-      if (a.apply_loss_function) {
+      if (apply_loss) {
         double rho[3];
         loss.Evaluate(s, rho);
         cost = 0.5 * rho[0];
-        if (a.output_residuals) {
+        if (out_residuals) {
           // corrector.h:82-147 then :159-166
           const double sqrt_rho1 = ::sqrt(rho[1]);
           double scaling = sqrt_rho1;
@@ -675,8 +701,8 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
 #pragma unroll
       for (int j = 0; j < kNB; ++j) { bulk_arg[j] = false; bulk_base[j] = 0; }
       if constexpr (kStage) {
-        if (a.output_jacobian && CB200_KERNEL_BULK_STORE) {
-          if (!a.crs) {
+        if (out_jacobian && CB200_KERNEL_BULK_STORE) {
+          if (!crs) {
 #pragma unroll
             for (int j = 0; j < kNB; ++j) {
               const int t0 = __shfl_sync(0xffffffffu, tangent[j], 0);
@@ -745,13 +771,13 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
             res[r] = out[r].a;
             s += res[r] * res[r];
           }
-          if (a.apply_loss_function) {
+          if (apply_loss) {
             double rho[3];
             loss.Evaluate(s, rho);
             cost = 0.5 * rho[0];
             sqrt_rho1 = ::sqrt(rho[1]);
             residual_scaling = sqrt_rho1;
-            if (!(s == 0.0 || rho[2] <= 0.0)) {
+            if (!LossCurvature<Loss>::kNonPositive && !(s == 0.0 || rho[2] <= 0.0)) {
               const double D = 1.0 + 2.0 * s * rho[2] / rho[1];
               const double alpha = 1.0 - ::sqrt(D);
               residual_scaling = sqrt_rho1 / (1 - alpha);
@@ -937,12 +963,12 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
             auto dcol = [&](int c) -> int { return kGeneric ? __popc(lv & ((1u << c) - 1u)) : c; };
             auto is_live = [&](int c) -> bool { return kGeneric ? ((lv >> c) & 1u) : true; };
             const int tan = kGeneric ? tangent[j] : kSize;
-            const int row_stride = a.crs ? row_stride_crs : tan;
+            const int row_stride = crs ? row_stride_crs : tan;
             if (kStage && (bulk_arg[j] || bulk_all)) {
               // Stage the cell exactly as it lies in global memory.
               double* cell = bulk_all ? jbuf + (jpos[j] - bulk_all_base)
                                       : jbuf + 32 * kRes * Dims::Offset(j) + lane * kRes * tan;
-              if (!kGeneric && !a.crs && (kRes * kSize) % 2 == 0) {
+              if (!kGeneric && !crs && (kRes * kSize) % 2 == 0) {
                 double2* mine = reinterpret_cast<double2*>(cell);  // conflict-free 128-bit
 #pragma unroll
                 for (int e = 0; e < kRes * kSize; e += 2)
@@ -983,10 +1009,10 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
           }
         };
 
-        if (a.output_jacobian || a.output_gradient) {
+        if (out_jacobian || out_gradient) {
           ForEachBlock(prepare, std::make_index_sequence<kNB>{});
-          if (a.output_gradient) ForEachBlock(gradient, std::make_index_sequence<kNB>{});
-          if (a.output_jacobian) ForEachBlock(scatter, std::make_index_sequence<kNB>{});
+          if (out_gradient) ForEachBlock(gradient, std::make_index_sequence<kNB>{});
+          if (out_jacobian) ForEachBlock(scatter, std::make_index_sequence<kNB>{});
         }
       };
       ForEachBlock(pass, std::make_index_sequence<Plan::kNumPasses>{});
@@ -1012,7 +1038,7 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
     if (valid) {
       all_ok = all_ok && ok;
       if (ok) cost_sum += cost;
-      if (a.output_residuals) {
+      if (out_residuals) {
         double* __restrict__ dst = a.residuals + respos;
         if ((kRes % 2 == 0) && ((respos & 1) == 0)) {
 #pragma unroll
@@ -1075,11 +1101,27 @@ int LaunchEvaluate(const cb200_launch_args* args, void* stream) {
                          cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kJetBytes);
     cudaFuncSetAttribute(EvaluateKernel<kVariantGeneric, Functor, Loss, kRes, Ns...>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kJetBytes);
+#if CB200_KERNEL_SPECIALISE_ALL_OUTPUTS
+    cudaFuncSetAttribute(EvaluateKernel<kVariantPlainAll, Functor, Loss, kRes, Ns...>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kJetBytes);
+    cudaFuncSetAttribute(EvaluateKernel<kVariantGenericAll, Functor, Loss, kRes, Ns...>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kJetBytes);
+#endif
     configured = true;
   }
   if (!(args->output_jacobian || args->output_gradient)) {
     EvaluateKernel<kVariantCost, Functor, Loss, kRes, Ns...>
         <<<grid, kEvaluateThreads, Smem::kCostBytes, s>>>(*args);
+#if CB200_KERNEL_SPECIALISE_ALL_OUTPUTS
+  } else if (args->plain && args->output_residuals && args->output_jacobian &&
+             args->output_gradient && args->apply_loss_function && !args->crs) {
+    EvaluateKernel<kVariantPlainAll, Functor, Loss, kRes, Ns...>
+        <<<grid, kEvaluateThreads, Smem::kJetBytes, s>>>(*args);
+  } else if (!args->plain && args->output_residuals && args->output_jacobian &&
+             args->output_gradient && args->apply_loss_function) {
+    EvaluateKernel<kVariantGenericAll, Functor, Loss, kRes, Ns...>
+        <<<grid, kEvaluateThreads, Smem::kJetBytes, s>>>(*args);
+#endif
   } else if (args->plain) {
     EvaluateKernel<kVariantPlain, Functor, Loss, kRes, Ns...>
         <<<grid, kEvaluateThreads, Smem::kJetBytes, s>>>(*args);

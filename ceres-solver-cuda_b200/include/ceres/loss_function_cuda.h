@@ -24,6 +24,9 @@ class LossFunctionCUDABase {
 // rho(s) = s
 class TrivialLossCUDA : public LossFunctionCUDABase {
  public:
+  // rho'' <= 0 everywhere: the evaluation kernel skips the Corrector's alpha branch
+  // (corrector.cc:105-110 takes it only for rho'' > 0) and never needs rho[2].
+  static constexpr bool kNonPositiveCurvature = true;
   HOST_DEVICE void Evaluate(double s, double rho[3]) const {
     rho[0] = s;
     rho[1] = 1.0;
@@ -34,6 +37,9 @@ class TrivialLossCUDA : public LossFunctionCUDABase {
 // rho(s) = s for s <= a^2, 2 a sqrt(s) - a^2 beyond.
 class HuberLossCUDA : public LossFunctionCUDABase {
  public:
+  // rho'' <= 0 everywhere: the evaluation kernel skips the Corrector's alpha branch
+  // (corrector.cc:105-110 takes it only for rho'' > 0) and never needs rho[2].
+  static constexpr bool kNonPositiveCurvature = true;
   HOST_DEVICE explicit HuberLossCUDA(double a) : a_(a), b_(a * a) {}
   HOST_DEVICE void Evaluate(double s, double rho[3]) const {
     if (s > b_) {
@@ -58,6 +64,9 @@ class HuberLossCUDA : public LossFunctionCUDABase {
 // rho(s) = a^2 log(1 + s / a^2)
 class CauchyLossCUDA : public LossFunctionCUDABase {
  public:
+  // rho'' <= 0 everywhere: the evaluation kernel skips the Corrector's alpha branch
+  // (corrector.cc:105-110 takes it only for rho'' > 0) and never needs rho[2].
+  static constexpr bool kNonPositiveCurvature = true;
   HOST_DEVICE explicit CauchyLossCUDA(double a) : b_(a * a), c_(1 / b_) {}
   HOST_DEVICE void Evaluate(double s, double rho[3]) const {
     const double sum = 1.0 + s * c_;
