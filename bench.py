@@ -305,15 +305,18 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the
-                     # ncu --set full capture in profiles/r1_v6_ncu_summary.txt (L, 1 GPU)
-                     "traffic": 7.592e9 if (args.workload == "L" and args.scale == 1.0
+                     # ncu --set full capture in profiles/r1_v8_ncu_summary.txt (L, 1 GPU)
+                     "traffic": 7.595e9 if (args.workload == "L" and args.scale == 1.0
                                             and world == 1) else None,
-                     "kernel": "EvaluateKernel<true, SnavelyReprojectionError, HuberLossCUDA, 2, 9, 3>",
+                     "kernel": "EvaluateKernel<plain all-outputs, SnavelyReprojectionError, HuberLossCUDA, 2, 9, 3>",
                      "algorithmic_bytes_per_block": ALG_BYTES_PER_RB,
                      "blocks_per_launch": local_rb, "launch_ms": ker_ms, "peak_source": peak_src,
                      "fp64": {"achieved_tflops": ALG_FLOPS_PER_RB * local_rb / (ker_ms * 1e-3) / 1e12,
                               "algorithmic_flops_per_block": ALG_FLOPS_PER_RB,
-                              "nominal_peak_tflops": 37.2}},
+                              "nominal_peak_tflops": 37.2,
+                              # scripts/fp64_peak.cu on a B200 of this pool
+                              "measured_peak_tflops": 33.78,
+                              "peak_source": "profiles/r1_fp64_peak.json"}},
         "setup_s": setup_s, "cost": cost,
     }
     if world == 1 and not args.no_cpu_baseline:

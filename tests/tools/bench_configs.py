@@ -3,7 +3,7 @@ SubsetManifold(9,{0}) + CompressedRowSparseMatrix; 5: pose graph <6,7,7> with
 EigenQuaternion x R^3 manifold), with a parity check against the oracle on a prefix.
 Usage: bench_configs.py [scale]"""
 import sys, os, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import numpy as np
 import ceres_b200

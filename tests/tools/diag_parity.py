@@ -1,6 +1,6 @@
 """Diagnostic: error statistics of the CUDA path vs the oracle on one problem."""
 import sys, os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import numpy as np
 import ceres_b200
