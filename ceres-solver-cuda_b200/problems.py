@@ -200,6 +200,8 @@ def bal_problem(num_cameras, num_points, num_observations, seed=1, loss="huber",
     N(0, 0.5^2) px noise, 2% outliers with N(0, 20^2) so the Huber outlier branch runs.
     """
     assert num_observations >= 2 * num_points and num_cameras >= 2
+    # a point is seen at most once by a camera
+    assert num_observations <= num_points * num_cameras, "more observations than camera-point pairs"
     rng = np.random.default_rng(seed)
     nc, npts, nobs = num_cameras, num_points, num_observations
     # degrees: every point seen by >= 2 cameras

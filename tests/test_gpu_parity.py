@@ -389,3 +389,38 @@ def test_pose_graph_3d_error_term(fmt):
         d = np.concatenate([rng.normal(size=3), mq, S.ravel()])
         b.add_residual_block(P.POSE_GRAPH_3D, [ps[i], qs[i], ps[j], qs[j]], d)
     _check(b.build(), fmt)
+
+
+@pytest.mark.parametrize("nobs", [4, 31, 33, 127, 129, 385])
+def test_ragged_sizes(nobs):
+    """Block counts around the warp (32) and CTA (128) tile sizes: the tail of the last tile
+    is masked, not skipped or duplicated."""
+    spec = P.bal_problem(40, max(2, nobs // 3), nobs, seed=nobs)
+    assert spec.num_rb == nobs
+    _check(spec, fmt=0)
+    _check(spec, fmt=1)
+
+
+def test_every_parameter_block_constant():
+    """RemoveFixedBlocks leaves an empty program (program.cc:324-430): nothing to launch, the
+    cost is the fixed cost and the outputs are empty."""
+    spec = P.bal_problem(6, 10, 40, seed=9)
+    spec.pb_constant[:] = 1
+    op = O.OracleProblem(spec)
+    cp = B.CudaProblem(spec)
+    assert cp.num_effective_parameters == 0 and cp.num_residuals == 0
+    assert cp.num_residuals == op.num_residuals
+    ok, cost, r, g, j = cp.evaluate()
+    assert ok and cost == 0.0 and r.size == 0 and g.size == 0
+    assert abs(cp.fixed_cost - op.fixed_cost) <= RTOL_SUMS * op.fixed_cost
+
+
+def test_one_residual_block():
+    spec = P.bal_problem(2, 2, 4, seed=3)
+    keep = slice(0, 1)
+    one = P.ProblemSpec(pb_size=spec.pb_size, pb_values=spec.pb_values, rb_type=spec.rb_type[keep],
+                        rb_pb=spec.rb_pb[:2], fdata=spec.fdata[:2],
+                        rb_loss_kind=spec.rb_loss_kind[keep], rb_loss_a=spec.rb_loss_a[keep],
+                        rb_loss_b=spec.rb_loss_b[keep])
+    _check(one, fmt=0)
+    _check(one, fmt=1)
