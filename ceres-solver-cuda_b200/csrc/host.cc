@@ -6,6 +6,7 @@
 // reorder_program.cc:254-335, block_jacobian_writer.cc, compressed_row_jacobian_writer.cc,
 // program_evaluator_cuda.h:65-183, registered_cuda_evaluators.cc:123-280.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -13,6 +14,7 @@
 #include <numeric>
 
 #include "ceres/internal/evaluator.h"
+#include "ceres/internal/parallel_for.h"
 #include "ceres/internal/program.h"
 #include "ceres/internal/sparse_matrix.h"
 
@@ -356,24 +358,30 @@ void Program::ConstantParameterBlocksToStateVector(double* state) const {
     state += pb->size;
   }
 }
-bool Program::Plus(const double* state, const double* delta, double* state_plus_delta) const {
-  for (const ParameterBlock* pb : parameter_blocks_) {
-    const double* x = state + pb->state_offset;
-    const double* d = delta + pb->delta_offset;
-    double* out = state_plus_delta + pb->state_offset;
-    if (pb->manifold) {
-      if (!pb->manifold->Plus(x, d, out)) return false;
-    } else {
-      for (int i = 0; i < pb->size; ++i) out[i] = x[i] + d[i];
-    }
-    if (pb->lower_bounds || pb->upper_bounds) {  // parameter_block.h:255-276 projection
-      for (int i = 0; i < pb->size; ++i) {
-        if (pb->lower_bounds) out[i] = std::max(out[i], pb->lower_bounds[i]);
-        if (pb->upper_bounds) out[i] = std::min(out[i], pb->upper_bounds[i]);
+bool Program::Plus(const double* state, const double* delta, double* state_plus_delta,
+                   int num_threads) const {
+  std::atomic<bool> ok{true};
+  ParallelFor(num_threads, static_cast<int64_t>(parameter_blocks_.size()),
+              [&](int64_t begin, int64_t end, int) {
+    for (int64_t k = begin; k < end; ++k) {
+      const ParameterBlock* pb = parameter_blocks_[k];
+      const double* x = state + pb->state_offset;
+      const double* d = delta + pb->delta_offset;
+      double* out = state_plus_delta + pb->state_offset;
+      if (pb->manifold) {
+        if (!pb->manifold->Plus(x, d, out)) ok = false;
+      } else {
+        for (int i = 0; i < pb->size; ++i) out[i] = x[i] + d[i];
+      }
+      if (pb->lower_bounds || pb->upper_bounds) {  // parameter_block.h:255-276 projection
+        for (int i = 0; i < pb->size; ++i) {
+          if (pb->lower_bounds) out[i] = std::max(out[i], pb->lower_bounds[i]);
+          if (pb->upper_bounds) out[i] = std::min(out[i], pb->upper_bounds[i]);
+        }
       }
     }
-  }
-  return true;
+  });
+  return ok;
 }
 int Program::NumParameters() const {
   int n = 0;
@@ -779,7 +787,7 @@ class ProgramEvaluatorCUDA final : public Evaluator {
   }
 
   bool Plus(const double* state, const double* delta, double* state_plus_delta) const override {
-    return program_->Plus(state, delta, state_plus_delta);
+    return program_->Plus(state, delta, state_plus_delta, options_.num_threads);
   }
   int NumParameters() const override { return program_->NumParameters(); }
   int NumEffectiveParameters() const override { return program_->NumEffectiveParameters(); }

@@ -1,10 +1,13 @@
 // Minimal TRUST_REGION driver around the CUDA evaluator; see ceres/solver.h for scope.
 #include "ceres/solver.h"
 
+#include "ceres/internal/parallel_for.h"
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace ceres {
@@ -57,6 +60,32 @@ class PinnedVector {
   double* data_ = nullptr;
   size_t size_ = 0;
 };
+
+// Wall-clock buckets of the trust-region loop, printed when CB200_SOLVER_TIMING is set.
+struct Buckets {
+  double diagonal = 0, scaling = 0, step = 0, plus = 0, bookkeeping = 0;
+};
+
+// Element-wise pass over [0, n) on num_threads threads; f(i) must only touch index i.
+template <typename F>
+void ForEach(int num_threads, int64_t n, F&& f) {
+  internal::ParallelFor(num_threads, n, [&](int64_t begin, int64_t end, int) {
+    for (int64_t i = begin; i < end; ++i) f(i);
+  });
+}
+// Sum (or maximum) of f(i) over [0, n) with one partial per thread.
+template <typename F>
+double Reduce(int num_threads, int64_t n, bool maximum, F&& f) {
+  std::vector<double> partial(std::max(1, num_threads), 0.0);
+  internal::ParallelFor(num_threads, n, [&](int64_t begin, int64_t end, int t) {
+    double acc = 0.0;
+    for (int64_t i = begin; i < end; ++i) acc = maximum ? std::max(acc, f(i)) : acc + f(i);
+    partial[t] = acc;
+  });
+  double total = 0.0;
+  for (double p : partial) total = maximum ? std::max(total, p) : total + p;
+  return total;
+}
 
 // Solves (J'J + D^2) y = J'r with Jacobi-preconditioned conjugate gradients (CGNR);
 // stand-in for the reference's linear solvers.  Returns the iteration count.
@@ -249,6 +278,8 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
   const double minimizer_start = Seconds();
   const int n = program->NumParameters(), ne = program->NumEffectiveParameters();
   const int m = program->NumResiduals();
+  const int nt = std::max(1, options.num_threads);
+  Buckets buckets;
   PinnedVector x(n), x_plus(n), gradient(ne), scale(ne, 1.0), diagonal(ne), D2(ne), y(ne);
   std::vector<double> delta(ne);
   // only the host linear solver reads the residuals and the model on the host
@@ -269,7 +300,7 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
   summary->initial_cost = cost + fixed_cost;
   if (options.jacobi_scaling) {
     jacobian->SquaredColumnNorm(scale.data());
-    for (double& s : scale) s = 1.0 / (1.0 + std::sqrt(s));
+    ForEach(nt, ne, [&](int64_t i) { scale[i] = 1.0 / (1.0 + std::sqrt(scale[i])); });
     jacobian->ScaleColumns(scale.data());
   }
   double radius = options.initial_trust_region_radius, decrease_factor = 2.0;
@@ -285,12 +316,21 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
       summary->message = "Maximum solver time reached.";
       break;
     }
+    double mark = Seconds();
+    auto lap = [&](double* bucket) {
+      const double now = Seconds();
+      *bucket += now - mark;
+      mark = now;
+    };
     if (!reuse_diagonal) {
       jacobian->SquaredColumnNorm(diagonal.data());
-      for (double& d : diagonal)
-        d = std::min(std::max(d, options.min_lm_diagonal), options.max_lm_diagonal);
+      ForEach(nt, ne, [&](int64_t i) {
+        diagonal[i] =
+            std::min(std::max(diagonal[i], options.min_lm_diagonal), options.max_lm_diagonal);
+      });
     }
-    for (int i = 0; i < ne; ++i) D2[i] = diagonal[i] / radius;
+    ForEach(nt, ne, [&](int64_t i) { D2[i] = diagonal[i] / radius; });
+    lap(&buckets.diagonal);
     const double ls_start = Seconds();
     int ls_iterations = 0;
     double model_cost_change = 0.0, step_norm = 0.0, x_norm = 0.0;
@@ -316,7 +356,7 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
       linear_solver_ok = cg.termination != 2;
       // step = -y: model cost change = (J y).r - |J y|^2 / 2
       model_cost_change = cg.jy_dot_b - 0.5 * cg.jy_squared_norm;
-      for (int i = 0; i < ne; ++i) y[i] = -y[i];
+      ForEach(nt, ne, [&](int64_t i) { y[i] = -y[i]; });
     } else {
       ls_iterations = SolveNormalEquations(*jacobian, D2.data(), residuals.data(),
                                            options.max_linear_solver_iterations,
@@ -328,29 +368,37 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
       for (int i = 0; i < m; ++i) model_cost_change -= model[i] * (residuals[i] + 0.5 * model[i]);
     }
     summary->linear_solver_time_in_seconds += Seconds() - ls_start;
-    for (int i = 0; i < ne; ++i) { delta[i] = y[i] * scale[i]; step_norm += delta[i] * delta[i]; }
-    for (int i = 0; i < n; ++i) x_norm += x[i] * x[i];
+    mark = Seconds();
+    ForEach(nt, ne, [&](int64_t i) { delta[i] = y[i] * scale[i]; });
+    step_norm = Reduce(nt, ne, false, [&](int64_t i) { return delta[i] * delta[i]; });
+    x_norm = Reduce(nt, n, false, [&](int64_t i) { return x[i] * x[i]; });
     step_norm = std::sqrt(step_norm);
     IterationSummary is;
     is.iteration = it;
     is.linear_solver_iterations = ls_iterations;
     is.step_norm = step_norm;
     double new_cost = 0.0;
-    bool ok = linear_solver_ok && model_cost_change > 0.0 && evaluator->Plus(x.data(), delta.data(), x_plus.data()) &&
-              evaluator->Evaluate(x_plus.data(), &new_cost, nullptr, nullptr, nullptr);
+    lap(&buckets.step);
+    bool ok = linear_solver_ok && model_cost_change > 0.0 &&
+              evaluator->Plus(x.data(), delta.data(), x_plus.data());
+    lap(&buckets.plus);
+    ok = ok && evaluator->Evaluate(x_plus.data(), &new_cost, nullptr, nullptr, nullptr);
+    mark = Seconds();
     const double relative_decrease = ok ? (cost - new_cost) / model_cost_change : -1.0;
     is.relative_decrease = relative_decrease;
     if (ok && relative_decrease > options.min_relative_decrease) {
       is.step_is_successful = true;
       is.cost_change = cost - new_cost;
-      x = x_plus;
+      ForEach(nt, n, [&](int64_t i) { x[i] = x_plus[i]; });
       if (!evaluator->Evaluate(x.data(), &cost, residuals_out, gradient.data(),
                                jacobian.get())) {
         summary->termination_type = FAILURE;
         summary->message = "Residual and Jacobian evaluation failed.";
         break;
       }
+      mark = Seconds();
       if (options.jacobi_scaling) jacobian->ScaleColumns(scale.data());
+      lap(&buckets.scaling);
       radius = std::min(options.max_trust_region_radius,
                         radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * relative_decrease - 1.0, 3)));
       decrease_factor = 2.0;
@@ -362,8 +410,10 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
       reuse_diagonal = true;
       ++summary->num_unsuccessful_steps;
     }
-    double gmax = 0.0;
-    for (double g : gradient) gmax = std::max(gmax, std::fabs(g));
+    mark = Seconds();
+    const double gmax =
+        Reduce(nt, ne, true, [&](int64_t i) { return std::fabs(gradient[i]); });
+    lap(&buckets.bookkeeping);
     is.cost = cost + fixed_cost;
     is.gradient_max_norm = gmax;
     is.trust_region_radius = radius;
@@ -405,6 +455,12 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
     }
   }
   summary->minimizer_time_in_seconds = Seconds() - minimizer_start;
+  if (std::getenv("CB200_SOLVER_TIMING"))
+    std::fprintf(stderr,
+                 "solver buckets (s): LM diagonal %.3f, Jacobi scaling %.3f, step vectors %.3f, "
+                 "Plus %.3f, gradient norm %.3f\n",
+                 buckets.diagonal, buckets.scaling, buckets.step, buckets.plus,
+                 buckets.bookkeeping);
   summary->total_time_in_seconds = Seconds() - start;
 }
 

@@ -12,9 +12,11 @@
 // then 9 doubles per camera and 3 per point, one per line.
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ceres/problem_cuda.h"
@@ -138,6 +140,9 @@ int main(int argc, char** argv) {
   ceres::Solver::Options options;
   options.max_num_iterations = iters ? std::atoi(iters) : 20;
   options.minimizer_progress_to_stdout = true;
+  const char* threads = Flag(argc, argv, "--num_threads");
+  options.num_threads = threads ? std::atoi(threads)
+                                : static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
   options.linear_solver_type = ceres::ITERATIVE_SCHUR;
   if (ls && !std::strcmp(ls, "cgnr")) options.linear_solver_type = ceres::CGNR;
   if (ls && !std::strcmp(ls, "cgnr_cuda")) {

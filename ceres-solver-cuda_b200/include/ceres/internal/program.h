@@ -158,7 +158,9 @@ class Program {
   void ParameterBlocksToStateVector(double* state) const;
   void StateVectorToParameterBlocks(const double* state) const;  // writes user state
   void ConstantParameterBlocksToStateVector(double* state) const;
-  bool Plus(const double* state, const double* delta, double* state_plus_delta) const;
+  // program.cc:121-150 (a ParallelFor over the parameter blocks)
+  bool Plus(const double* state, const double* delta, double* state_plus_delta,
+            int num_threads = 1) const;
 
   int NumParameterBlocks() const { return static_cast<int>(parameter_blocks_.size()); }
   int NumResidualBlocks() const { return static_cast<int>(residual_blocks_.size()); }
