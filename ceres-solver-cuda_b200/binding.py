@@ -107,6 +107,11 @@ def driver():
         L.drv_plus.argtypes = [C.c_void_p] * 4
         L.drv_dense_jacobian.argtypes = [C.c_void_p, C.c_void_p]
         L.drv_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.drv_problem_evaluate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                           C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.drv_problem_evaluate_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.drv_evaluate_residual_block.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.drv_jacobian_multiply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.drv_jacobian_squared_column_norm.argtypes = [C.c_void_p, C.c_void_p]
         L.drv_jacobian_scale_columns.argtypes = [C.c_void_p, C.c_void_p]
@@ -288,6 +293,60 @@ class CudaProblem:
         if rc < 0:
             raise RuntimeError(f"evaluate_device failed ({rc})")
         return rc == 0, float(cost[0])
+
+    # ---- Problem::Evaluate / Problem::EvaluateResidualBlock (the user-level entry points)
+    def problem_evaluate(self, parameter_blocks=None, residual_blocks=None,
+                         apply_loss_function=True, device=0):
+        """Problem::Evaluate(options, &cost, &residuals, &gradient, &jacobian) at the user
+        state.  Returns (ok, cost, residuals, gradient, (rows, cols, values), (num_rows,
+        num_cols))."""
+        pb = None if parameter_blocks is None else np.ascontiguousarray(parameter_blocks, np.int32)
+        rb = None if residual_blocks is None else np.ascontiguousarray(residual_blocks, np.int32)
+        cost, dims = np.zeros(1), np.zeros(5, dtype=np.int64)
+        ok = driver().drv_problem_evaluate(
+            self.h, int(apply_loss_function), 0 if pb is None else pb.size, _p(pb),
+            0 if rb is None else rb.size, _p(rb), int(device), _p(cost), _p(dims))
+        r, g = np.zeros(dims[0]), np.zeros(dims[1])
+        rows, cols = np.zeros(dims[2] + 1, np.int32), np.zeros(dims[4], np.int32)
+        vals = np.zeros(dims[4])
+        if ok:
+            for which, arr in enumerate((r, g, rows, cols, vals)):
+                if arr.size:
+                    driver().drv_problem_evaluate_get(self.h, which, _p(arr))
+        return bool(ok), float(cost[0]), r, g, (rows, cols, vals), (int(dims[2]), int(dims[3]))
+
+    def evaluate_residual_block(self, rb, apply_loss_function=True, jacobians=True):
+        """Problem::EvaluateResidualBlock on the host.  Returns (ok, cost, residuals, list of
+        per-argument Jacobians (None for constant blocks), parameter block ids)."""
+        from . import problems as P
+        spec = self.spec
+        kres, sizes, _ = P.COST_TYPES[int(spec.rb_type[rb])]
+        cost, res = np.zeros(1), np.zeros(kres)
+        jac = np.zeros(kres * sum(sizes))
+        ids = np.zeros(len(sizes), np.int32)
+        ok = driver().drv_evaluate_residual_block(self.h, int(rb), kres, int(apply_loss_function),
+                                                  int(jacobians), _p(cost), _p(res), _p(jac), _p(ids))
+        out, cursor = [], 0
+        for j, pb in enumerate(ids):
+            if not jacobians or spec.pb_constant[pb]:
+                out.append(None)
+                continue
+            tangent = self.tangent_size(int(pb))
+            out.append(jac[cursor:cursor + kres * tangent].reshape(kres, tangent).copy())
+            cursor += kres * tangent
+        return bool(ok), float(cost[0]), res, out, ids
+
+    def tangent_size(self, pb):
+        from . import problems as P
+        spec = self.spec
+        size, kind, param = int(spec.pb_size[pb]), int(spec.pb_manifold_kind[pb]), \
+            int(spec.pb_manifold_param[pb])
+        if kind in (P.MANIFOLD_SUBSET, P.MANIFOLD_OPAQUE_SUBSET):
+            return size - bin(param).count("1")
+        if kind in (P.MANIFOLD_QUATERNION, P.MANIFOLD_EIGEN_QUATERNION,
+                    P.MANIFOLD_QUATERNION_X_EUCLIDEAN, P.MANIFOLD_EIGEN_QUATERNION_X_EUCLIDEAN):
+            return size - 1
+        return size
 
     # ---- linear algebra on the Jacobian the last evaluation left in HBM
     def _la_check(self, rc):

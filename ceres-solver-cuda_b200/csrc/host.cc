@@ -17,6 +17,7 @@
 #include "ceres/internal/parallel_for.h"
 #include "ceres/internal/program.h"
 #include "ceres/internal/sparse_matrix.h"
+#include "ceres/problem.h"
 
 namespace ceres {
 namespace internal {
@@ -195,16 +196,61 @@ bool ProblemImpl::EvaluateResidualBlockOnHost(int32_t id, bool apply_loss_functi
   const ResidualTypeStore& t = types_[ref.type];
   const int nb = t.desc.num_parameter_blocks, kres = t.desc.num_residuals;
   const double* params[CB200_MAX_PARAMETER_BLOCKS];
-  for (int j = 0; j < nb; ++j)
-    params[j] = pbs_[t.parameter_blocks[static_cast<size_t>(ref.local) * nb + j]]->user_state;
+  const ParameterBlock* blocks[CB200_MAX_PARAMETER_BLOCKS];
+  for (int j = 0; j < nb; ++j) {
+    blocks[j] = pbs_[t.parameter_blocks[static_cast<size_t>(ref.local) * nb + j]].get();
+    params[j] = blocks[j]->user_state;
+    if (jacobians && jacobians[j] && blocks[j]->IsConstant()) {
+      // problem_impl.cc:777-782
+      std::fprintf(stderr, "Jacobian requested for parameter block : %d. But the parameter block "
+                           "is marked constant.\n", j);
+      return false;
+    }
+  }
   std::vector<double> scratch(kres);
   double* r = residuals ? residuals : scratch.data();
   const void* functor = t.functors.data() + static_cast<size_t>(ref.local) * t.desc.functor_size;
-  if (!t.host_functor(functor, params, r, jacobians)) return false;
+  // ambient Jacobians of the requested blocks (residual_block.cc:86-98)
+  std::vector<double> ambient_storage;
+  double* ambient[CB200_MAX_PARAMETER_BLOCKS] = {};
+  if (jacobians) {
+    size_t total = 0;
+    for (int j = 0; j < nb; ++j)
+      if (jacobians[j]) total += static_cast<size_t>(kres) * blocks[j]->size;
+    ambient_storage.assign(total, 0.0);
+    size_t cursor = 0;
+    for (int j = 0; j < nb; ++j)
+      if (jacobians[j]) {
+        ambient[j] = ambient_storage.data() + cursor;
+        cursor += static_cast<size_t>(kres) * blocks[j]->size;
+      }
+  }
+  if (!t.host_functor(functor, params, r, jacobians ? ambient : nullptr)) return false;
   double s = 0.0;
   for (int i = 0; i < kres; ++i) {
     if (!std::isfinite(r[i]) || r[i] == 1e302) return false;
     s += r[i] * r[i];
+  }
+  // J <- J * PlusJacobian (residual_block.cc:137-155)
+  if (jacobians) {
+    for (int j = 0; j < nb; ++j) {
+      if (!jacobians[j]) continue;
+      const int size = blocks[j]->size, tangent = blocks[j]->TangentSize();
+      for (size_t i = 0; i < static_cast<size_t>(kres) * size; ++i)
+        if (!std::isfinite(ambient[j][i])) return false;
+      if (blocks[j]->manifold) {
+        std::vector<double> plus(static_cast<size_t>(size) * tangent);
+        if (!blocks[j]->manifold->PlusJacobian(params[j], plus.data())) return false;
+        for (int row = 0; row < kres; ++row)
+          for (int c = 0; c < tangent; ++c) {
+            double acc = 0.0;
+            for (int k = 0; k < size; ++k) acc += ambient[j][row * size + k] * plus[k * tangent + c];
+            jacobians[j][row * tangent + c] = acc;
+          }
+      } else {
+        std::memcpy(jacobians[j], ambient[j], sizeof(double) * kres * size);
+      }
+    }
   }
   if (!apply_loss_function) {
     *cost = 0.5 * s;
@@ -214,7 +260,67 @@ bool ProblemImpl::EvaluateResidualBlockOnHost(int32_t id, bool apply_loss_functi
   t.host_loss(t.loss_table.data() + static_cast<size_t>(t.loss_index[ref.local]) * t.desc.loss_size,
               s, rho);
   *cost = 0.5 * rho[0];
+  if (!residuals && !jacobians) return true;
+  // Corrector (corrector.cc:88-160)
+  const double sqrt_rho1 = std::sqrt(rho[1]);
+  double residual_scaling = sqrt_rho1, alpha_sq_norm = 0.0;
+  if (!(s == 0.0 || rho[2] <= 0.0)) {
+    const double D = 1.0 + 2.0 * s * rho[2] / rho[1];
+    const double alpha = 1.0 - std::sqrt(D);
+    residual_scaling = sqrt_rho1 / (1.0 - alpha);
+    alpha_sq_norm = alpha / s;
+  }
+  if (jacobians) {
+    for (int j = 0; j < nb; ++j) {
+      if (!jacobians[j]) continue;
+      const int tangent = blocks[j]->TangentSize();
+      for (int c = 0; c < tangent; ++c) {
+        if (alpha_sq_norm == 0.0) {
+          for (int row = 0; row < kres; ++row) jacobians[j][row * tangent + c] *= sqrt_rho1;
+          continue;
+        }
+        double r_transpose_j = 0.0;
+        for (int row = 0; row < kres; ++row) r_transpose_j += jacobians[j][row * tangent + c] * r[row];
+        for (int row = 0; row < kres; ++row)
+          jacobians[j][row * tangent + c] =
+              sqrt_rho1 * (jacobians[j][row * tangent + c] - alpha_sq_norm * r[row] * r_transpose_j);
+      }
+    }
+  }
+  if (residuals)
+    for (int i = 0; i < kres; ++i) residuals[i] *= residual_scaling;
   return true;
+}
+
+void ProblemImpl::GetParameterBlocksForResidualBlock(int32_t id, std::vector<double*>* out) const {
+  const ResidualBlockRef ref = rbs_[id];
+  const ResidualTypeStore& t = types_[ref.type];
+  const int nb = t.desc.num_parameter_blocks;
+  out->clear();
+  for (int j = 0; j < nb; ++j)
+    out->push_back(pbs_[t.parameter_blocks[static_cast<size_t>(ref.local) * nb + j]]->user_state);
+}
+
+void ProblemImpl::GetResidualBlocksForParameterBlock(const double* values,
+                                                     std::vector<int32_t>* out) const {
+  out->clear();
+  const ParameterBlock* pb = FindParameterBlock(values);
+  if (!pb) return;
+  for (int32_t id = 0; id < static_cast<int32_t>(rbs_.size()); ++id) {
+    const ResidualBlockRef ref = rbs_[id];
+    const ResidualTypeStore& t = types_[ref.type];
+    const int nb = t.desc.num_parameter_blocks;
+    for (int j = 0; j < nb; ++j)
+      if (t.parameter_blocks[static_cast<size_t>(ref.local) * nb + j] == pb->id) {
+        out->push_back(id);
+        break;
+      }
+  }
+}
+
+const CostFunction* ProblemImpl::CostFunctionOf(int32_t id) const {
+  const ResidualBlockRef ref = rbs_[id];
+  return types_[ref.type].cost_functions[ref.local];
 }
 
 // ---------------------------------------------------------------------- Program
@@ -222,6 +328,30 @@ Program::Program(ProblemImpl* problem) : problem_(problem) {
   for (const auto& pb : problem->parameter_blocks()) parameter_blocks_.push_back(pb.get());
   residual_blocks_.resize(problem->residual_blocks().size());
   std::iota(residual_blocks_.begin(), residual_blocks_.end(), 0);
+}
+
+Program::Program(ProblemImpl* problem, std::vector<ParameterBlock*> parameter_blocks,
+                 std::vector<int32_t> residual_blocks)
+    : problem_(problem),
+      parameter_blocks_(std::move(parameter_blocks)),
+      residual_blocks_(std::move(residual_blocks)) {
+  std::vector<char> listed(problem->parameter_blocks().size(), 0), seen(listed.size(), 0);
+  for (const ParameterBlock* pb : parameter_blocks_) listed[pb->id] = 1;
+  const auto& rbs = problem->residual_blocks();
+  const auto& types = problem->types();
+  for (int32_t id : residual_blocks_) {
+    const ResidualBlockRef ref = rbs[id];
+    const ResidualTypeStore& t = types[ref.type];
+    const int nb = t.desc.num_parameter_blocks;
+    for (int j = 0; j < nb; ++j) {
+      const int pid = t.parameter_blocks[static_cast<size_t>(ref.local) * nb + j];
+      if (!listed[pid] && !seen[pid]) {
+        seen[pid] = 1;
+        constant_parameter_blocks_.push_back(problem->parameter_blocks()[pid].get());
+      }
+    }
+  }
+  SetParameterOffsetsAndIndex();
 }
 
 void Program::SetParameterOffsetsAndIndex() {
@@ -423,7 +553,9 @@ inline int CollectActive(const Program& program, int32_t id, ActiveBlock* out) {
     const ParameterBlock* pb =
         problem->parameter_blocks()[t.parameter_blocks[static_cast<size_t>(ref.local) * nb + j]]
             .get();
-    if (program.IsActive(pb)) {
+    // a constant block inside the program keeps its columns but gets no cells
+    // (block_jacobian_writer.cc:100-103, compressed_row_jacobian_writer.cc:104-107)
+    if (program.IsActive(pb) && !pb->IsConstant()) {
       out[n] = ActiveBlock{pb->index, n, pb->TangentSize()};
       ++n;
     }
@@ -629,7 +761,15 @@ class ProgramEvaluatorCUDA final : public Evaluator {
     // engine block id of every problem parameter block
     std::vector<int32_t> engine_id(problem->parameter_blocks().size(), -1);
     int plus_pool = 0;
+    // Constant blocks that are still part of the program (Problem::Evaluate does not reduce
+    // it): they keep their state and gradient slots but are evaluated like the removed ones,
+    // from their own (user) state and without derivatives (program.cc:80-88).
+    std::vector<const ParameterBlock*> constant_in_program;
     for (const ParameterBlock* pb : active) {
+      if (pb->IsConstant()) {
+        constant_in_program.push_back(pb);
+        continue;
+      }
       cb200_parameter_block b;
       b.size = pb->size;
       b.tangent_size = pb->TangentSize();
@@ -666,15 +806,39 @@ class ProgramEvaluatorCUDA final : public Evaluator {
       engine_id[pb->id] = static_cast<int32_t>(blocks.size());
       blocks.push_back(b);
     }
+    int constant_parameters = program_->NumConstantParameters();
+    for (const ParameterBlock* pb : constant_in_program) {
+      cb200_parameter_block b;
+      b.size = pb->size;
+      b.tangent_size = pb->TangentSize();
+      b.state_offset = constant_parameters;
+      b.delta_offset = -1;
+      b.plus_jacobian_offset = -1;
+      b.manifold_kind = CB200_MANIFOLD_NONE;
+      b.manifold_param = 0;
+      constant_parameters += pb->size;
+      engine_id[pb->id] = static_cast<int32_t>(blocks.size());
+      blocks.push_back(b);
+    }
     plus_pool_ = plus_pool;
     if (plus_pool > 0)
       plus_jacobians_ = static_cast<double*>(cb200_host_alloc(sizeof(double) * plus_pool));
-    std::vector<double> constant_state(program_->NumConstantParameters() + 1);
+    std::vector<double> constant_state(constant_parameters + 1);
     program_->ConstantParameterBlocksToStateVector(constant_state.data());
+    {
+      double* cursor = constant_state.data() + program_->NumConstantParameters();
+      for (const ParameterBlock* pb : constant_in_program) {
+        std::memcpy(cursor, pb->user_state, sizeof(double) * pb->size);
+        cursor += pb->size;
+      }
+    }
+    const int32_t num_engine_active =
+        static_cast<int32_t>(active.size() - constant_in_program.size());
     rc = cb200_engine_set_parameter_blocks(
-        engine_, static_cast<int32_t>(active.size()), static_cast<int32_t>(constant.size()),
-        blocks.data(), program_->NumParameters(), program_->NumEffectiveParameters(),
-        constant_state.data(), program_->NumConstantParameters(), plus_pool);
+        engine_, num_engine_active,
+        static_cast<int32_t>(constant.size() + constant_in_program.size()), blocks.data(),
+        program_->NumParameters(), program_->NumEffectiveParameters(), constant_state.data(),
+        constant_parameters, plus_pool);
     if (rc != CB200_OK) return Fail(error);
 
     // Bucket the program's residual blocks by type, keeping their program POSITION.
@@ -853,4 +1017,88 @@ std::unique_ptr<Evaluator> Evaluator::Create(const Evaluator::Options& options, 
 }
 
 }  // namespace internal
+
+// problem_impl.cc:599-760, on the CUDA evaluator.
+bool Problem::Evaluate(const EvaluateOptions& options, double* cost, std::vector<double>* residuals,
+                       std::vector<double>* gradient, CRSMatrix* jacobian) {
+  if (!cost && !residuals && !gradient && !jacobian) return true;
+  internal::ProblemImpl* impl = impl_.get();
+  std::vector<int32_t> rbs;
+  if (options.residual_blocks.empty()) {
+    rbs.resize(impl->NumResidualBlocks());
+    std::iota(rbs.begin(), rbs.end(), 0);
+  } else {
+    for (ResidualBlockId id : options.residual_blocks) rbs.push_back(internal::ProblemImpl::IdOf(id));
+  }
+  std::vector<internal::ParameterBlock*> pbs;
+  std::vector<internal::ParameterBlock*> held;  // excluded blocks held constant for the call
+  if (options.parameter_blocks.empty()) {
+    for (const auto& pb : impl->parameter_blocks()) pbs.push_back(pb.get());
+  } else {
+    std::vector<char> included(impl->parameter_blocks().size(), 0);
+    for (double* values : options.parameter_blocks) {
+      internal::ParameterBlock* pb = impl->FindParameterBlock(values);
+      if (!pb) {
+        std::fprintf(stderr, "No known parameter block for Problem::Evaluate::Options."
+                             "parameter_blocks = %p\n", static_cast<void*>(values));
+        std::abort();  // the reference LOG(FATAL)s (problem_impl.cc:638-642)
+      }
+      pbs.push_back(pb);
+      included[pb->id] = 1;
+    }
+    for (const auto& pb : impl->parameter_blocks())
+      if (!included[pb->id] && !pb->IsConstant()) {
+        held.push_back(pb.get());
+        pb->is_set_constant = true;
+      }
+  }
+  bool status = false;
+  {
+    internal::Program program(impl, pbs, rbs);
+    internal::RegisteredCUDAEvaluators registry(impl);
+    internal::Evaluator::Options eo;
+    eo.linear_solver_type = CGNR;  // with CUDA_SPARSE: "use a compressed-row Jacobian"
+    eo.sparse_linear_algebra_library_type = CUDA_SPARSE;
+    eo.num_threads = options.num_threads;
+    eo.use_cuda = true;
+    eo.registered_cuda_evaluators = &registry;
+    eo.device = options.cuda_device;
+    eo.num_eliminate_blocks = 0;
+    std::string error;
+    std::unique_ptr<internal::Evaluator> evaluator =
+        internal::Evaluator::Create(eo, &program, &error);
+    if (!evaluator) {
+      std::fprintf(stderr, "Problem::Evaluate: %s\n", error.c_str());
+    } else {
+      if (residuals) residuals->assign(evaluator->NumResiduals(), 0.0);
+      if (gradient) gradient->assign(evaluator->NumEffectiveParameters(), 0.0);
+      std::unique_ptr<internal::SparseMatrix> tmp_jacobian;
+      if (jacobian) tmp_jacobian = evaluator->CreateJacobian();
+      std::vector<double> parameters(program.NumParameters() + 1);
+      program.ParameterBlocksToStateVector(parameters.data());
+      double tmp_cost = 0.0;
+      internal::Evaluator::EvaluateOptions evaluate_options;
+      evaluate_options.apply_loss_function = options.apply_loss_function;
+      status = evaluator->Evaluate(evaluate_options, parameters.data(), &tmp_cost,
+                                   residuals && !residuals->empty() ? residuals->data() : nullptr,
+                                   gradient && !gradient->empty() ? gradient->data() : nullptr,
+                                   tmp_jacobian.get());
+      if (status) {
+        if (cost) *cost = tmp_cost;
+        if (jacobian) {
+          // CompressedRowSparseMatrix::ToCRSMatrix
+          auto* crs = static_cast<internal::CompressedRowSparseMatrix*>(tmp_jacobian.get());
+          jacobian->num_rows = crs->num_rows();
+          jacobian->num_cols = crs->num_cols();
+          jacobian->rows.assign(crs->rows(), crs->rows() + crs->num_rows() + 1);
+          jacobian->cols.assign(crs->cols(), crs->cols() + crs->num_nonzeros());
+          jacobian->values.assign(crs->values(), crs->values() + crs->num_nonzeros());
+        }
+      }
+    }
+  }
+  for (internal::ParameterBlock* pb : held) pb->is_set_constant = false;
+  return status;
+}
+
 }  // namespace ceres

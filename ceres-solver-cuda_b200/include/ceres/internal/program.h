@@ -124,9 +124,15 @@ class ProblemImpl {
     return reinterpret_cast<ResidualBlock*>(static_cast<intptr_t>(id) + 1);
   }
 
-  // Evaluates one residual block on the host (used for fixed costs).
+  // Evaluates one residual block on the host at the user state (fixed costs of the
+  // reduced program, Problem::EvaluateResidualBlock): residual_block.cc:68-204 with the
+  // manifold projection and the loss correction; jacobians[j] (may be null) is
+  // num_residuals x tangent size of argument j.
   bool EvaluateResidualBlockOnHost(int32_t id, bool apply_loss_function, double* cost,
                                    double* residuals, double** jacobians) const;
+  void GetParameterBlocksForResidualBlock(int32_t id, std::vector<double*>* out) const;
+  void GetResidualBlocksForParameterBlock(const double* values, std::vector<int32_t>* out) const;
+  const CostFunction* CostFunctionOf(int32_t id) const;
 
  private:
   ProblemOptions options_;
@@ -143,6 +149,10 @@ class ProblemImpl {
 class Program {
  public:
   explicit Program(ProblemImpl* problem);
+  // Explicit block lists (Problem::Evaluate); parameter blocks that residual blocks use
+  // but that are not listed go to constant_parameter_blocks().
+  Program(ProblemImpl* problem, std::vector<ParameterBlock*> parameter_blocks,
+          std::vector<int32_t> residual_blocks);
 
   // Program::CreateReducedProgram (program.cc:306-322): drops constant parameter
   // blocks and residual blocks that depend only on them (their cost goes to

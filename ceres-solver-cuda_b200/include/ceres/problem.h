@@ -8,6 +8,7 @@
 #include <memory>
 #include <vector>
 
+#include "ceres/crs_matrix.h"
 #include "ceres/internal/program.h"
 #include "ceres/manifold.h"
 #include "ceres/types.h"
@@ -68,6 +69,62 @@ class Problem {
     parameter_blocks->clear();
     for (const auto& pb : impl_->parameter_blocks()) parameter_blocks->push_back(pb->user_state);
   }
+  // ---- queries (include/ceres/problem.h:385-420)
+  void GetResidualBlocks(std::vector<ResidualBlockId>* residual_blocks) const {
+    residual_blocks->clear();
+    for (int i = 0; i < impl_->NumResidualBlocks(); ++i)
+      residual_blocks->push_back(internal::ProblemImpl::HandleOf(i));
+  }
+  void GetParameterBlocksForResidualBlock(ResidualBlockId residual_block,
+                                          std::vector<double*>* parameter_blocks) const {
+    impl_->GetParameterBlocksForResidualBlock(internal::ProblemImpl::IdOf(residual_block),
+                                              parameter_blocks);
+  }
+  // Null for residual blocks added in bulk (ProblemCUDA::AddResidualBlocks).
+  const CostFunction* GetCostFunctionForResidualBlock(ResidualBlockId residual_block) const {
+    return impl_->CostFunctionOf(internal::ProblemImpl::IdOf(residual_block));
+  }
+  void GetResidualBlocksForParameterBlock(const double* values,
+                                          std::vector<ResidualBlockId>* residual_blocks) const {
+    std::vector<int32_t> ids;
+    impl_->GetResidualBlocksForParameterBlock(values, &ids);
+    residual_blocks->clear();
+    for (int32_t id : ids) residual_blocks->push_back(internal::ProblemImpl::HandleOf(id));
+  }
+
+  // include/ceres/problem.h:426-470
+  struct EvaluateOptions {
+    // Columns of the gradient / Jacobian, in this order; empty = every parameter block in
+    // the order they were added.  Blocks left out are held constant for the call.
+    std::vector<double*> parameter_blocks;
+    // Rows; empty = every residual block in the order they were added.
+    std::vector<ResidualBlockId> residual_blocks;
+    bool apply_loss_function = true;
+    int num_threads = 1;
+    int cuda_device = 0;  // extension: the device that evaluates
+  };
+  // Evaluates the problem at the current values of the user's parameter blocks
+  // (internal/ceres/problem_impl.cc:599-760) — here on the CUDA evaluator, with a
+  // CompressedRowSparseMatrix Jacobian like the reference.  Any output may be null.
+  // Constant parameter blocks keep their columns (all zero), as in the reference.
+  bool Evaluate(const EvaluateOptions& options, double* cost, std::vector<double>* residuals,
+                std::vector<double>* gradient, CRSMatrix* jacobian);
+
+  // One residual block on the host, at the current user state (problem_impl.cc:762-810):
+  // residuals and Jacobians with the manifolds and (optionally) the loss function applied;
+  // jacobians[i] is num_residuals x tangent size, row-major, and may be null.
+  bool EvaluateResidualBlock(ResidualBlockId residual_block, bool apply_loss_function,
+                             double* cost, double* residuals, double** jacobians) const {
+    return impl_->EvaluateResidualBlockOnHost(internal::ProblemImpl::IdOf(residual_block),
+                                              apply_loss_function, cost, residuals, jacobians);
+  }
+  bool EvaluateResidualBlockAssumingParametersUnchanged(ResidualBlockId residual_block,
+                                                        bool apply_loss_function, double* cost,
+                                                        double* residuals,
+                                                        double** jacobians) const {
+    return EvaluateResidualBlock(residual_block, apply_loss_function, cost, residuals, jacobians);
+  }
+
   const Options& options() const { return impl_->options(); }
   internal::ProblemImpl* mutable_impl() { return impl_.get(); }
 

@@ -153,6 +153,39 @@ class ProblemCUDA {
   void GetParameterBlocks(std::vector<double*>* parameter_blocks) const {
     problem_->GetParameterBlocks(parameter_blocks);
   }
+  void GetResidualBlocks(std::vector<ResidualBlockId>* residual_blocks) const {
+    problem_->GetResidualBlocks(residual_blocks);
+  }
+  void GetParameterBlocksForResidualBlock(ResidualBlockId residual_block,
+                                          std::vector<double*>* parameter_blocks) const {
+    problem_->GetParameterBlocksForResidualBlock(residual_block, parameter_blocks);
+  }
+  const CostFunction* GetCostFunctionForResidualBlock(ResidualBlockId residual_block) const {
+    return problem_->GetCostFunctionForResidualBlock(residual_block);
+  }
+  void GetResidualBlocksForParameterBlock(const double* values,
+                                          std::vector<ResidualBlockId>* residual_blocks) const {
+    problem_->GetResidualBlocksForParameterBlock(values, residual_blocks);
+  }
+  // problem_cuda.h:364-396.  Evaluate runs on the CUDA evaluator (the reference forwards to
+  // the CPU one); EvaluateResidualBlock is a host evaluation of one block.
+  bool Evaluate(const Problem::EvaluateOptions& evaluate_options, double* cost,
+                std::vector<double>* residuals, std::vector<double>* gradient,
+                CRSMatrix* jacobian) {
+    return problem_->Evaluate(evaluate_options, cost, residuals, gradient, jacobian);
+  }
+  bool EvaluateResidualBlock(ResidualBlockId residual_block_id, bool apply_loss_function,
+                             double* cost, double* residuals, double** jacobians) const {
+    return problem_->EvaluateResidualBlock(residual_block_id, apply_loss_function, cost,
+                                           residuals, jacobians);
+  }
+  bool EvaluateResidualBlockAssumingParametersUnchanged(ResidualBlockId residual_block_id,
+                                                        bool apply_loss_function, double* cost,
+                                                        double* residuals,
+                                                        double** jacobians) const {
+    return problem_->EvaluateResidualBlock(residual_block_id, apply_loss_function, cost,
+                                           residuals, jacobians);
+  }
   const Problem::Options& options() const { return problem_->options(); }
 
   Problem* mutable_problem() { return problem_.get(); }

@@ -32,6 +32,9 @@ struct DriverProblem {
   ceres::internal::JacobianLayout layout;  // layout-only builds (no device)
   double fixed_cost = 0.0;
   std::string error;
+  // results of the last drv_problem_evaluate
+  std::vector<double> pe_residuals, pe_gradient;
+  ceres::CRSMatrix pe_jacobian;
   DriverProblem() : problem(MakeOptions()) {}
   static ceres::Problem::Options MakeOptions() {
     ceres::Problem::Options o;

@@ -259,6 +259,68 @@ int drv_evaluate_device(void* h, int apply_loss_function, int want_residuals, in
                                       want_residuals, want_gradient, want_jacobian, cost);
 }
 
+// Problem::Evaluate through ProblemCUDA's wrapped Problem.  parameter_blocks / residual_blocks
+// are ids in creation order (NULL = all).  dims: [num_residuals, num_gradient, num_rows,
+// num_cols, num_nonzeros]; the arrays are then fetched with drv_problem_evaluate_get.
+int drv_problem_evaluate(void* h, int apply_loss_function, int num_pb, const int* pb_ids,
+                         int num_rb, const int* rb_ids, int device, double* cost, int64_t* dims) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  ceres::Problem::EvaluateOptions options;
+  options.apply_loss_function = apply_loss_function != 0;
+  options.cuda_device = device;
+  for (int i = 0; i < num_pb; ++i) options.parameter_blocks.push_back(dp->pb(pb_ids[i]));
+  std::vector<ceres::ResidualBlockId> all;
+  dp->problem.GetResidualBlocks(&all);
+  for (int i = 0; i < num_rb; ++i) options.residual_blocks.push_back(all[rb_ids[i]]);
+  const bool ok =
+      dp->problem.Evaluate(options, cost, &dp->pe_residuals, &dp->pe_gradient, &dp->pe_jacobian);
+  dims[0] = static_cast<int64_t>(dp->pe_residuals.size());
+  dims[1] = static_cast<int64_t>(dp->pe_gradient.size());
+  dims[2] = dp->pe_jacobian.num_rows;
+  dims[3] = dp->pe_jacobian.num_cols;
+  dims[4] = static_cast<int64_t>(dp->pe_jacobian.values.size());
+  return ok ? 1 : 0;
+}
+// which: 0 residuals, 1 gradient, 2 rows (int32), 3 cols (int32), 4 values
+void drv_problem_evaluate_get(void* h, int which, void* dst) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  switch (which) {
+    case 0: std::memcpy(dst, dp->pe_residuals.data(), dp->pe_residuals.size() * 8); break;
+    case 1: std::memcpy(dst, dp->pe_gradient.data(), dp->pe_gradient.size() * 8); break;
+    case 2: std::memcpy(dst, dp->pe_jacobian.rows.data(), dp->pe_jacobian.rows.size() * 4); break;
+    case 3: std::memcpy(dst, dp->pe_jacobian.cols.data(), dp->pe_jacobian.cols.size() * 4); break;
+    default: std::memcpy(dst, dp->pe_jacobian.values.data(), dp->pe_jacobian.values.size() * 8);
+  }
+}
+
+// Problem::EvaluateResidualBlock (host).  jacobians: the blocks of the non-constant
+// arguments, each num_residuals x tangent, concatenated in argument order; want_jacobians
+// = 0 skips them.  Also exercises the query functions: parameter block ids of the residual
+// block are written to pb_ids_out.
+int drv_evaluate_residual_block(void* h, int rb, int num_residuals, int apply_loss_function,
+                                int want_jacobians, double* cost, double* residuals,
+                                double* jacobians, int* pb_ids_out) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  ceres::Problem* problem = dp->problem.mutable_problem();
+  std::vector<ceres::ResidualBlockId> all;
+  problem->GetResidualBlocks(&all);
+  std::vector<double*> blocks;
+  problem->GetParameterBlocksForResidualBlock(all[rb], &blocks);
+  std::vector<double*> ptrs(blocks.size(), nullptr);
+  double* cursor = jacobians;
+  for (size_t j = 0; j < blocks.size(); ++j) {
+    for (size_t k = 0; k < dp->pb_offset.size(); ++k)
+      if (dp->pb(static_cast<int>(k)) == blocks[j]) pb_ids_out[j] = static_cast<int>(k);
+    if (!want_jacobians || problem->IsParameterBlockConstant(blocks[j])) continue;
+    ptrs[j] = cursor;
+    cursor += num_residuals * problem->ParameterBlockTangentSize(blocks[j]);
+  }
+  return problem->EvaluateResidualBlock(all[rb], apply_loss_function != 0, cost, residuals,
+                                        want_jacobians ? ptrs.data() : nullptr)
+             ? 1
+             : 0;
+}
+
 // Linear algebra on the Jacobian the last evaluation left on the device (C ABI pass-through).
 static int LaResult(DriverProblem* dp, int rc) {
   if (rc != CB200_OK) dp->error = cb200_engine_last_error(dp->evaluator->engine());
