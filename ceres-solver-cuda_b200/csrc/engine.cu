@@ -342,6 +342,115 @@ __global__ void __launch_bounds__(256) JacobianNormalKernel(const JacobianWalk w
   }
 }
 
+// Same operation with the values staged through shared memory.  In the block-sparse layout
+// the cells of a warp's 32 consecutive residual blocks are one contiguous run per argument
+// (block_jacobian_writer.cc:62-150), so the warp copies the run as it lies in memory with
+// 16-byte cp.async (two cache lines per instruction instead of 32) and every thread then
+// reads its own cell from shared memory, for both passes.  Arguments whose run is not
+// contiguous / aligned (constant blocks, the ragged last tile) are read from global memory
+// as in the kernel above.
+constexpr int kNormalThreads = 128;
+__device__ __forceinline__ void CopyAsync16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                   static_cast<unsigned>(__cvta_generic_to_shared(smem))),
+               "l"(gmem)
+               : "memory");
+}
+__global__ void __launch_bounds__(kNormalThreads) JacobianNormalStagedKernel(
+    const JacobianWalk w, const double* __restrict__ x, double* __restrict__ y,
+    int cell_doubles_per_block) {
+  extern __shared__ double2 normal_smem[];
+  constexpr int kChunk = 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* const stage = reinterpret_cast<double*>(normal_smem) + warp * 32 * cell_doubles_per_block;
+  for (int i0 = (blockIdx.x * (kNormalThreads / 32) + warp) * 32; i0 < w.n;
+       i0 += gridDim.x * kNormalThreads) {
+    const bool full = i0 + 32 <= w.n;
+    const bool valid = i0 + lane < w.n;
+    const int i = valid ? i0 + lane : w.n - 1;
+    // ---- stage the contiguous runs
+    unsigned staged = 0u;
+    int offset = 0;  // doubles, per warp
+    for (int j = 0; j < w.nb; ++j) {
+      const size_t at = static_cast<size_t>(j) * w.n + i;
+      const int jp = w.jpos[at];
+      const int tan = w.plain ? w.sizes[j] : w.pb_table[8 * w.pb[at] + 2];
+      const int jp0 = __shfl_sync(0xffffffffu, jp, 0);
+      const int tan0 = __shfl_sync(0xffffffffu, tan, 0);
+      const int cs = w.kres * tan0;
+      const bool ok = full && jp0 >= 0 && (jp0 & 1) == 0 && tan == tan0 && jp == jp0 + lane * cs &&
+                      tan0 <= w.sizes[j];
+      if (__all_sync(0xffffffffu, ok)) {
+        const double2* src = reinterpret_cast<const double2*>(w.values + jp0);
+        double2* dst = reinterpret_cast<double2*>(stage + offset);
+        for (int k = lane; k < 16 * cs; k += 32) CopyAsync16(dst + k, src + k);
+        staged |= 1u << j;
+      }
+      offset += 32 * w.kres * w.sizes[j];
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+
+    double wr[kNormalRows];
+#pragma unroll
+    for (int r = 0; r < kNormalRows; ++r) wr[r] = 0.0;
+    if (valid) {
+      offset = 0;
+      for (int j = 0; j < w.nb; ++j) {
+        const size_t at = static_cast<size_t>(j) * w.n + i;
+        const int jp = w.jpos[at];
+        const int tan = w.plain ? w.sizes[j] : w.pb_table[8 * w.pb[at] + 2];
+        const double* v =
+            ((staged >> j) & 1u) ? stage + offset + lane * w.kres * tan : w.values + jp;
+        offset += 32 * w.kres * w.sizes[j];
+        if (jp < 0) continue;
+        const double* __restrict__ xs = x + w.doff[at];
+        for (int c0 = 0; c0 < tan; c0 += kChunk) {
+          double b[kChunk];
+#pragma unroll
+          for (int k = 0; k < kChunk; ++k) b[k] = c0 + k < tan ? xs[c0 + k] : 0.0;
+#pragma unroll
+          for (int r = 0; r < kNormalRows; ++r) {
+            if (r < w.kres) {
+#pragma unroll
+              for (int k = 0; k < kChunk; ++k)
+                wr[r] = fma(c0 + k < tan ? v[r * tan + c0 + k] : 0.0, b[k], wr[r]);
+            }
+          }
+        }
+      }
+      offset = 0;
+      for (int j = 0; j < w.nb; ++j) {
+        const size_t at = static_cast<size_t>(j) * w.n + i;
+        const int jp = w.jpos[at];
+        const int tan = w.plain ? w.sizes[j] : w.pb_table[8 * w.pb[at] + 2];
+        const double* v =
+            ((staged >> j) & 1u) ? stage + offset + lane * w.kres * tan : w.values + jp;
+        offset += 32 * w.kres * w.sizes[j];
+        if (jp < 0) continue;
+        const int col = w.doff[at];
+        for (int c0 = 0; c0 < tan; c0 += kChunk) {
+          double acc[kChunk];
+#pragma unroll
+          for (int k = 0; k < kChunk; ++k) acc[k] = 0.0;
+#pragma unroll
+          for (int r = 0; r < kNormalRows; ++r) {
+            if (r < w.kres) {
+#pragma unroll
+              for (int k = 0; k < kChunk; ++k)
+                acc[k] = fma(c0 + k < tan ? v[r * tan + c0 + k] : 0.0, wr[r], acc[k]);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < kChunk; ++k)
+            if (c0 + k < tan) RedAddF64(y + col + c0 + k, acc[k]);
+        }
+      }
+    }
+    __syncwarp();  // the next tile overwrites the staging area
+  }
+}
+
 // Conjugate-gradient vector kernels.  S is a small array of device scalars:
 enum { kSRho = 0, kSLastRho, kSPq, kSRnorm2, kSXbr, kSJyB, kSJy2, kSCount };
 
@@ -1128,7 +1237,23 @@ static int RunJacobianWalk(cb200_engine* e, int op, const double* x, double* y) 
       case kOpRight: JacobianWalkKernel<kOpRight><<<grid, 256, 0, s>>>(w, x, y); break;
       case kOpLeft: JacobianWalkKernel<kOpLeft><<<grid, 256, 0, s>>>(w, x, y); break;
       case kOpColumnNorm: JacobianWalkKernel<kOpColumnNorm><<<grid, 256, 0, s>>>(w, x, y); break;
-      case kOpNormal: JacobianNormalKernel<<<grid, 256, 0, s>>>(w, x, y); break;
+      case kOpNormal: {
+        int cell_doubles = 0;
+        for (int j = 0; j < w.nb; ++j) cell_doubles += w.kres * w.sizes[j];
+        const size_t smem =
+            static_cast<size_t>(kNormalThreads / 32) * 32 * cell_doubles * sizeof(double);
+        if (!w.crs && smem <= 96 * 1024) {
+          if (smem > 48 * 1024)
+            CB200_CUDA(e, cudaFuncSetAttribute(JacobianNormalStagedKernel,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(smem)));
+          const int sgrid = std::min((t->n_local + kNormalThreads - 1) / kNormalThreads, 148 * 16);
+          JacobianNormalStagedKernel<<<sgrid, kNormalThreads, smem, s>>>(w, x, y, cell_doubles);
+        } else {
+          JacobianNormalKernel<<<grid, 256, 0, s>>>(w, x, y);
+        }
+        break;
+      }
       default: JacobianWalkKernel<kOpScale><<<grid, 256, 0, s>>>(w, x, y); break;
     }
   }
