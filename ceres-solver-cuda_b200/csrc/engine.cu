@@ -47,6 +47,7 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, /* ncclUniqueId by value */ Uid, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   int (*CommDestroy)(void*) = nullptr;
@@ -75,6 +76,9 @@ NcclApi* GetNccl() {
       api.Broadcast =
           reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(
               dlsym(api.handle, "ncclBroadcast"));
+      api.AllGather =
+          reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(
+              dlsym(api.handle, "ncclAllGather"));
       api.GroupStart = reinterpret_cast<int (*)()>(dlsym(api.handle, "ncclGroupStart"));
       api.GroupEnd = reinterpret_cast<int (*)()>(dlsym(api.handle, "ncclGroupEnd"));
       api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(api.handle, "ncclCommDestroy"));
@@ -152,6 +156,27 @@ __global__ void ReduceCostKernel(const double* __restrict__ partials, int n, dou
     __syncthreads();
   }
   if (threadIdx.x == 0) *out = sm[0];
+}
+
+// Gradient exchange, second half: every rank's exclusive range arrived in `staging`
+// (rank r at [r * chunk, r * chunk + length[r])) and goes to its place in the gradient.
+constexpr int kMaxGatherRanks = 64;
+struct GatherPlan {
+  int64_t begin[kMaxGatherRanks];
+  int32_t length[kMaxGatherRanks];
+  int32_t world, self;
+  int64_t chunk;
+};
+__global__ void __launch_bounds__(256) GatherScatterKernel(const GatherPlan plan,
+                                                           const double* __restrict__ staging,
+                                                           double* __restrict__ gradient) {
+  const int64_t total = plan.chunk * plan.world;
+  for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < total;
+       k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(k / plan.chunk);
+    const int64_t i = k - r * plan.chunk;
+    if (r != plan.self && i < plan.length[r]) gradient[plan.begin[r] + i] = staging[k];
+  }
 }
 
 // ---- linear algebra on the device-resident Jacobian.
@@ -585,6 +610,10 @@ struct cb200_engine {
   int64_t local_jacobian_values = 0;
   // Gradient exchange plan (empty = one all-reduce over [gradient | cost]).
   std::vector<GradientInterval> exchange;
+  // ... and its all-gather form: one exclusive range per rank, padded to gather_chunk
+  GatherPlan gather{};
+  bool gather_ok = false;
+  DeviceBuffer<double> d_gather;
 
   std::vector<ResidualType*> types;
 
@@ -677,6 +706,7 @@ void cb200_engine_destroy(cb200_engine* e) {
   for (auto& b : e->la_col) b.Free();
   e->la_row.Free(); e->la_scalars.Free();
   if (e->h_la_scalars) cudaFreeHost(e->h_la_scalars);
+  e->d_gather.Free();
   e->d_state.Free(); e->d_plus.Free(); e->d_residuals.Free(); e->d_jacobian.Free();
   e->d_gradcost.Free(); e->d_cost_partials.Free(); e->d_pb_table.Free(); e->d_status.Free();
   if (e->h_scalars) cudaFreeHost(e->h_scalars);
@@ -830,6 +860,31 @@ int cb200_engine_finalize(cb200_engine* e) {
     int64_t covered = 0;
     for (const auto& g : plan) covered += g.length;
     if (plan.size() <= 96 && covered == e->num_effective) e->exchange.swap(plan);
+    // All-gather form: usable when every rank owns at most one exclusive range and those
+    // ranges are most of the vector (bundle adjustment after the Schur ordering).
+    e->gather_ok = false;
+    if (!e->exchange.empty() && e->world <= kMaxGatherRanks) {
+      GatherPlan gp{};
+      gp.world = e->world;
+      gp.self = e->rank;
+      std::vector<int> count(e->world, 0);
+      int64_t exclusive = 0, chunk = 0;
+      for (const GradientInterval& iv : e->exchange) {
+        if (iv.owner < 0) continue;
+        ++count[iv.owner];
+        gp.begin[iv.owner] = iv.begin;
+        gp.length[iv.owner] = static_cast<int32_t>(iv.length);
+        exclusive += iv.length;
+        chunk = std::max(chunk, iv.length);
+      }
+      bool one_each = true;
+      for (int c : count) one_each = one_each && c <= 1;
+      gp.chunk = chunk;
+      if (one_each && chunk > 0 && 2 * exclusive >= e->num_effective) {
+        e->gather = gp;
+        e->gather_ok = true;
+      }
+    }
   }
 
   // Pass 1: per type, pick this rank's blocks and find what part of the values
@@ -986,7 +1041,11 @@ int cb200_engine_finalize(cb200_engine* e) {
   CB200_CUDA(e, e->d_plus.Resize(static_cast<size_t>(e->plus_pool) + 1));
   CB200_CUDA(e, e->d_residuals.Resize(static_cast<size_t>(e->res_end - e->res_begin) + 1));
   CB200_CUDA(e, e->d_jacobian.Resize(static_cast<size_t>(e->local_jacobian_values) + 2));
-  CB200_CUDA(e, e->d_gradcost.Resize(static_cast<size_t>(e->num_effective) + 2));
+  // (+ gather_chunk: the all-gather reads a full chunk starting at this rank's range)
+  CB200_CUDA(e, e->d_gradcost.Resize(static_cast<size_t>(e->num_effective) + 2 +
+                                     (e->gather_ok ? e->gather.chunk : 0)));
+  if (e->gather_ok)
+    CB200_CUDA(e, e->d_gather.Resize(static_cast<size_t>(e->gather.chunk) * e->world));
   CB200_CUDA(e, e->d_cost_partials.Resize(static_cast<size_t>(e->total_cost_partials) + 1));
   CB200_CUDA(e, e->d_status.Resize(1));
   CB200_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -1079,32 +1138,40 @@ static int EvaluateOnDevice(cb200_engine* e, uint32_t flags, bool want_r, bool w
     if (!want_g) {
       // cost-only evaluation: one double
       r = n->AllReduce(cost_slot, cost_slot, 1, kNcclFloat64, kNcclSum, e->comm, s);
-    } else if (e->exchange.empty() || !n->Broadcast || !n->GroupStart || !n->GroupEnd ||
-               !getenv("CB200_GRADIENT_EXCHANGE_PLAN")) {
-      // One all-reduce over [gradient | cost].  Measured on 8 x B200 (BAL L, 108 MB): 0.34 ms,
-      // against 0.62 ms for the exchange plan below (seven broadcasts + one small
-      // all-reduce in a group); at 4 GPUs the two are equal.  NVSwitch reduces in the switch,
-      // so the all-reduce already moves each byte once per rank: the plan stays opt-in.
+    } else if (!e->gather_ok || !n->AllGather || !n->GroupStart || !n->GroupEnd ||
+               !getenv("CB200_GRADIENT_GATHER")) {
+      // One all-reduce over [gradient | cost]: the default.  The all-gather form below is
+      // correct (scripts/check_multigpu.py) but measured no faster: BAL L, 108 MB, device
+      // time per evaluation 1.25 ms (all-reduce) vs 1.33 ms (gather) on 2 GPUs and 0.62 vs
+      // 0.63 ms on 8 - NCCL's all-reduce over NVSwitch already moves each byte once per rank.
+      // It is kept behind CB200_GRADIENT_GATHER for fabrics without in-switch reduction.
       r = n->AllReduce(g, g, static_cast<size_t>(e->num_effective) + 1, kNcclFloat64, kNcclSum,
                        e->comm, s);
     } else {
-      // Exchange plan: entries owned by one rank are broadcast from it, shared entries
-      // (the cameras of a BAL problem, boundary points) are all-reduced; the cost rides
-      // with the last shared interval when it is adjacent, else on its own.
+      // After a Schur ordering all but a handful of gradient entries are touched by one rank
+      // only.  Those need distribution, not reduction: one all-gather of every rank's
+      // exclusive range (padded to a common chunk) moves 1/world of the vector per rank
+      // instead of all of it, and a copy kernel puts the ranges in place; the shared entries
+      // (the cameras of a BAL problem, boundary points) and the cost are all-reduced.  (A
+      // group of per-rank broadcasts does the same job but measured no faster than the plain
+      // all-reduce on 4 GPUs and slower on 8.)
       n->GroupStart();
       bool cost_done = false;
       for (const GradientInterval& iv : e->exchange) {
+        if (iv.owner >= 0) continue;
         size_t len = static_cast<size_t>(iv.length);
-        if (iv.owner >= 0) {
-          r |= n->Broadcast(g + iv.begin, g + iv.begin, len, kNcclFloat64, iv.owner, e->comm, s);
-        } else {
-          if (iv.begin + iv.length == e->num_effective) { ++len; cost_done = true; }
-          r |= n->AllReduce(g + iv.begin, g + iv.begin, len, kNcclFloat64, kNcclSum, e->comm, s);
-        }
+        if (iv.begin + iv.length == e->num_effective) { ++len; cost_done = true; }
+        r |= n->AllReduce(g + iv.begin, g + iv.begin, len, kNcclFloat64, kNcclSum, e->comm, s);
       }
       if (!cost_done)
         r |= n->AllReduce(cost_slot, cost_slot, 1, kNcclFloat64, kNcclSum, e->comm, s);
+      r |= n->AllGather(g + e->gather.begin[e->rank], e->d_gather.ptr,
+                        static_cast<size_t>(e->gather.chunk), kNcclFloat64, e->comm, s);
       r |= n->GroupEnd();
+      const int64_t total = e->gather.chunk * e->world;
+      const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16));
+      GatherScatterKernel<<<grid, 256, 0, s>>>(e->gather, e->d_gather.ptr, g);
+      ++launches;
     }
     if (r != 0) return e->Fail(CB200_ERROR_NCCL, "NCCL collective failed (%d)", r);
   }
