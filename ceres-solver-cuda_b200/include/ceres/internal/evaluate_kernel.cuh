@@ -222,6 +222,9 @@ __device__ __forceinline__ void CpAsyncWait() {
 #ifndef CB200_KERNEL_STAGE_GRADIENT
 #define CB200_KERNEL_STAGE_GRADIENT 1 // warp-staged, sector-coalesced gradient reductions
 #endif
+#ifndef CB200_KERNEL_STAGE_GRADIENT_MIN_SIZE
+#define CB200_KERNEL_STAGE_GRADIENT_MIN_SIZE 1  // smaller blocks add their sums directly
+#endif
 #ifndef CB200_KERNEL_STAGE_JACOBIAN
 #define CB200_KERNEL_STAGE_JACOBIAN 1 // warp-staged, fully coalesced Jacobian stores
 #endif
@@ -353,13 +356,13 @@ struct PassPlan {
   }
 };
 
-template <typename Functor, int kNumParameters, int kNumBlocks>
+template <typename Functor, int kNumParameters, int kNumBlocks, int kParameterPitch>
 struct PrefetchLayout {
   // doubles per thread for the parameters; the cooperative gather pads every block to an
   // odd pitch (at most one extra double per block) so both its writes and the owner
   // lane's reads are bank-conflict free
   static constexpr int kParamBytes =
-      (kNumParameters + (CB200_KERNEL_COOP_GATHER ? kNumBlocks : 0)) * 8;
+      (CB200_KERNEL_COOP_GATHER ? kParameterPitch : kNumParameters) * 8;
   // Per-block int tables that travel with the parameters: [delta offset or block id]
   // and [Jacobian position] per argument, residual position, CRS row stride, loss index.
   static constexpr int kIntSlots = 2 * kNumBlocks + 3;
@@ -381,7 +384,8 @@ __host__ __device__ constexpr int StagePitch(int n) { return n | 1; }
 template <typename Functor, int kRes, int... Ns>
 struct SmemPlan {
   using Dims = BlockDims<Ns...>;
-  using Layout = PrefetchLayout<Functor, Dims::kNumParameters, Dims::kNumBlocks>;
+  using Layout = PrefetchLayout<Functor, Dims::kNumParameters, Dims::kNumBlocks,
+                                Dims::PitchBefore(Dims::kNumBlocks)>;
   static constexpr int kPrefetchBytes = Layout::kFits ? Layout::kPrefetchBytes : 0;
   // per warp: every argument's cells side by side (Jacobian staging) ...
   static constexpr int kJacobianDoubles = 32 * kRes * Dims::kNumParameters;
@@ -441,7 +445,7 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
   const bool out_gradient = kAll || a.output_gradient;
   const bool apply_loss = kAll || a.apply_loss_function;
   const bool crs = kVariant != kVariantPlainAll && a.crs;
-  using Layout = PrefetchLayout<Functor, kNP, kNB>;
+  using Layout = PrefetchLayout<Functor, kNP, kNB, Dims::PitchBefore(kNB)>;
   constexpr bool kPrefetch = Layout::kFits;
   constexpr bool kStage = kJets && Smem::kStageJacobian;
 
@@ -901,7 +905,8 @@ __global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ...
             }
             const bool emit = head && valid && ok && active;
             const unsigned emit_mask = __ballot_sync(0xffffffffu, emit);
-            if (CB200_KERNEL_STAGE_GRADIENT && __popc(emit_mask) >= 12) {
+            if (CB200_KERNEL_STAGE_GRADIENT && kSize >= CB200_KERNEL_STAGE_GRADIENT_MIN_SIZE &&
+                __popc(emit_mask) >= 12) {
               // Most lanes own a distinct block (the cameras of a BAL warp): stage the
               // per-lane sums and let consecutive lanes add to consecutive addresses, so
               // one red instruction touches a few sectors instead of 32.
