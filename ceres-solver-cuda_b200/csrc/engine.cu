@@ -454,6 +454,8 @@ __global__ void __launch_bounds__(kNormalThreads) JacobianNormalStagedKernel(
         offset += 32 * w.kres * w.sizes[j];
         if (jp < 0) continue;
         const int col = w.doff[at];
+        const bool in_smem = (staged >> j) & 1u;
+        double* sums = stage + (offset - 32 * w.kres * w.sizes[j]) + lane * w.kres * tan;
         for (int c0 = 0; c0 < tan; c0 += kChunk) {
           double acc[kChunk];
 #pragma unroll
@@ -466,9 +468,41 @@ __global__ void __launch_bounds__(kNormalThreads) JacobianNormalStagedKernel(
                 acc[k] = fma(c0 + k < tan ? v[r * tan + c0 + k] : 0.0, wr[r], acc[k]);
             }
           }
+          if (in_smem) {
+            // columns c0.. of the cell are not read again: its first row takes their sums
+            // for the warp-wide scatter below
 #pragma unroll
-          for (int k = 0; k < kChunk; ++k)
-            if (c0 + k < tan) RedAddF64(y + col + c0 + k, acc[k]);
+            for (int k = 0; k < kChunk; ++k)
+              if (c0 + k < tan) sums[c0 + k] = acc[k];
+          } else {
+#pragma unroll
+            for (int k = 0; k < kChunk; ++k)
+              if (c0 + k < tan) RedAddF64(y + col + c0 + k, acc[k]);
+          }
+        }
+      }
+    }
+    // ---- staged arguments: the sums leave by runs, consecutive
+    // lanes adding to consecutive addresses of a parameter block (a red instruction then
+    // touches a few sectors instead of 32)
+    if (staged) {
+      __syncwarp();
+      int offset2 = 0;
+      for (int j = 0; j < w.nb; ++j) {
+        const size_t at = static_cast<size_t>(j) * w.n + i;
+        const int tan = w.plain ? w.sizes[j] : w.pb_table[8 * w.pb[at] + 2];
+        const int col = w.doff[at];
+        const int base = offset2;
+        offset2 += 32 * w.kres * w.sizes[j];
+        if (!((staged >> j) & 1u)) continue;  // warp-uniform, and so is tan when staged
+        const int cs = w.kres * tan;
+        const unsigned magic = tan == 1 ? 0u : 0xffffffffu / static_cast<unsigned>(tan) + 1u;
+        for (int k = 0; k < tan; ++k) {
+          const int e = k * 32 + lane;
+          const int owner = magic ? static_cast<int>(__umulhi(static_cast<unsigned>(e), magic)) : e;
+          const int c = e - owner * tan;
+          const int ocol = __shfl_sync(0xffffffffu, col, owner);
+          RedAddF64(y + ocol + c, stage[base + owner * cs + c]);
         }
       }
     }
