@@ -416,6 +416,9 @@ struct SmemPlan {
 #ifndef CB200_RESIDENT_CTAS_SMALL
 #define CB200_RESIDENT_CTAS_SMALL 3
 #endif
+#ifndef CB200_RESIDENT_CTAS_COST
+#define CB200_RESIDENT_CTAS_COST 5  // CTAs per SM wanted for the Jet-free variant
+#endif
 __host__ __device__ constexpr int ResidentCtas(int num_residuals, int num_parameters) {
   return (num_parameters <= 13 && num_residuals <= 3) ? CB200_RESIDENT_CTAS_SMALL : 2;
 }
@@ -429,8 +432,20 @@ __host__ __device__ constexpr int ResidentCtas(int num_residuals, int num_parame
 // in flight during the ~1500 instructions of the previous block instead of stalling the
 // warp (v1 of this kernel: long-scoreboard stalls 7.5 of 15 cycles per issue, FP64 pipe
 // 22% busy; profiles/r1_v1_ncu_summary.txt).
+// The Jet-free cost / residual kernel needs ~80 registers and only the prefetch buffers, so
+// more of its CTAs fit on an SM; it is latency bound (argument reduction of sincos, divisions),
+// and the extra warps hide that: BAL L cost-only 0.97 ms at 3 CTAs per SM.
+__host__ __device__ constexpr int VariantCtas(int variant, int resident, int cost_bytes) {
+  if (variant != kVariantCost) return resident;
+  const int by_smem = (200 * 1024) / (cost_bytes + 1024);
+  const int wanted = CB200_RESIDENT_CTAS_COST;
+  return by_smem < resident ? resident : (by_smem < wanted ? by_smem : wanted);
+}
+
 template <int kVariant, typename Functor, typename Loss, int kRes, int... Ns>
-__global__ void __launch_bounds__(kEvaluateThreads, ResidentCtas(kRes, (Ns + ... + 0)))
+__global__ void __launch_bounds__(
+    kEvaluateThreads, VariantCtas(kVariant, ResidentCtas(kRes, (Ns + ... + 0)),
+                                  SmemPlan<Functor, kRes, Ns...>::kCostBytes))
     EvaluateKernel(const cb200_launch_args a) {
   using Dims = BlockDims<Ns...>;
   using Plan = PassPlan<kRes, Ns...>;
@@ -1093,11 +1108,16 @@ int LaunchEvaluate(const cb200_launch_args* args, void* stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     persistent_ctas = (sms > 0 ? sms : 148) * ResidentCtas(kRes, (Ns + ... + 0));
   }
+  using Smem = SmemPlan<Functor, kRes, Ns...>;
+  const bool cost_only = !(args->output_jacobian || args->output_gradient);
+  constexpr int kJetCtas = ResidentCtas(kRes, (Ns + ... + 0));
+  const int wanted =
+      cost_only ? persistent_ctas / kJetCtas * VariantCtas(kVariantCost, kJetCtas, Smem::kCostBytes)
+                : persistent_ctas;
   const int needed = (args->n + kEvaluateThreads - 1) / kEvaluateThreads;
-  int grid = needed < persistent_ctas ? needed : persistent_ctas;
+  int grid = needed < wanted ? needed : wanted;
   if (grid > args->cost_partial_count) grid = args->cost_partial_count;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  using Smem = SmemPlan<Functor, kRes, Ns...>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(EvaluateKernel<kVariantCost, Functor, Loss, kRes, Ns...>,
@@ -1114,7 +1134,7 @@ int LaunchEvaluate(const cb200_launch_args* args, void* stream) {
 #endif
     configured = true;
   }
-  if (!(args->output_jacobian || args->output_gradient)) {
+  if (cost_only) {
     EvaluateKernel<kVariantCost, Functor, Loss, kRes, Ns...>
         <<<grid, kEvaluateThreads, Smem::kCostBytes, s>>>(*args);
 #if CB200_KERNEL_SPECIALISE_ALL_OUTPUTS
