@@ -9,6 +9,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -735,8 +736,12 @@ class ProgramEvaluatorCUDA final : public Evaluator {
  public:
   ProgramEvaluatorCUDA(const Evaluator::Options& options, Program* program, int jacobian_format)
       : options_(options), program_(program) {
+    const auto t0 = std::chrono::steady_clock::now();
     BuildJacobianLayout(*program, jacobian_format, std::max(0, options.num_eliminate_blocks),
                         &layout_);
+    if (std::getenv("CB200_SETUP_TIMING"))
+      std::fprintf(stderr, "setup: %-28s %.3f s\n", "BuildJacobianLayout",
+                   std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   }
   ~ProgramEvaluatorCUDA() override {
     if (engine_) cb200_engine_destroy(engine_);
@@ -745,6 +750,16 @@ class ProgramEvaluatorCUDA final : public Evaluator {
 
   // RegisteredCUDAEvaluators::Init (registered_cuda_evaluators.cc:226-280).
   bool Init(std::string* error) {
+    const bool timing = std::getenv("CB200_SETUP_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t0 = now();
+    auto lap = [&](const char* what) {
+      if (!timing) return;
+      const auto t1 = now();
+      std::fprintf(stderr, "setup: %-28s %.3f s\n", what,
+                   std::chrono::duration<double>(t1 - t0).count());
+      t0 = t1;
+    };
     int rc = cb200_engine_create(options_.device, &engine_);
     if (rc != CB200_OK) {
       *error = "cb200_engine_create failed: no usable CUDA device " +
@@ -841,6 +856,7 @@ class ProgramEvaluatorCUDA final : public Evaluator {
         constant_parameters, plus_pool);
     if (rc != CB200_OK) return Fail(error);
 
+    lap("parameter blocks");
     // Bucket the program's residual blocks by type, keeping their program POSITION.
     const auto& rbs = program_->residual_blocks();
     const auto& refs = problem->residual_blocks();
@@ -875,6 +891,7 @@ class ProgramEvaluatorCUDA final : public Evaluator {
                                             num_losses > 1 ? loss_index.data() : nullptr);
       if (rc != CB200_OK) return Fail(error);
     }
+    lap("residual blocks -> engine");
     rc = cb200_engine_set_layout(
         engine_, layout_.jacobian_format, static_cast<int32_t>(rbs.size()), layout_.num_residuals,
         layout_.residual_layout.data(), layout_.jacobian_per_residual_layout.data(),
@@ -884,7 +901,9 @@ class ProgramEvaluatorCUDA final : public Evaluator {
     if (rc != CB200_OK) return Fail(error);
     rc = cb200_engine_set_shard(engine_, options_.shard_rank, options_.shard_world_size);
     if (rc != CB200_OK) return Fail(error);
+    lap("set_layout");
     rc = cb200_engine_finalize(engine_);
+    lap("engine finalize");
     if (rc != CB200_OK) return Fail(error);
     if (options_.nccl_unique_id && options_.shard_world_size > 1) {
       rc = cb200_engine_comm_init(engine_, options_.nccl_unique_id, options_.shard_rank,
