@@ -1640,6 +1640,11 @@ void* cb200_host_alloc(uint64_t bytes) {
   const uint64_t total = ((bytes + kPage - 1) / kPage + 1) * kPage;
   void* p = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
   if (p == MAP_FAILED) return nullptr;
+#ifdef MADV_HUGEPAGE
+  // Large arrays (Jacobian values, residuals) are DMA targets: transparent huge pages cut
+  // the number of pages the driver has to lock and map (a hint; ignored when unavailable).
+  if (total >= (8u << 20)) madvise(p, total, MADV_HUGEPAGE);
+#endif
   auto* h = static_cast<AllocHeader*>(p);
   h->magic = kAllocMagic;
   h->total_bytes = total;
