@@ -16,20 +16,27 @@
 // CorrectJacobian (uses uncorrected r) -> CorrectResiduals -> gradient J^T r
 // (both corrected) -> scatter.
 //
-// Design (DESIGN.md has the numbers):
+// Design (DESIGN.md section 3 has the numbers and the measurements behind each choice):
 //  * one thread per residual block, Jets with compile-time sparsity masks
-//    (ceres/jet.h): ~500 FP64 instructions and < 128 registers for the BAL
-//    functor, no local-memory spills, no per-thread Jacobian scratch in HBM;
-//  * structure-of-arrays inputs, argument-major, so every per-block table is read
-//    with unit-stride loads; parameters are gathered through L1/L2 (a camera is
-//    72 B and hot, consecutive blocks share their point);
-//  * each Jacobian cell is written exactly once, straight to its final position in
-//    the BlockSparseMatrix / CompressedRowSparseMatrix values array: no memset of
-//    the values, no second copy;
+//    (ceres/jet.h): ~500 FP64 instructions and 160 registers for the BAL functor, no
+//    local-memory spills, no per-thread Jacobian scratch in HBM;
+//  * persistent CTAs with a three-stage software pipeline: state offsets two blocks
+//    ahead in registers, parameters / functor / per-block integer tables one block ahead
+//    through cp.async into shared memory (the parameter gather is warp-cooperative, so a
+//    copy instruction touches a few sectors instead of 32), compute from shared memory;
+//  * structure-of-arrays inputs, argument-major: every per-block table is read with
+//    unit-stride copies;
+//  * each Jacobian cell is written exactly once, straight to its final position in the
+//    BlockSparseMatrix / CompressedRowSparseMatrix values array (no memset, no second
+//    copy): a warp stages its 32 cells in shared memory in global layout and one TMA bulk
+//    store moves the run;
+//  * gradient: per-lane sums staged in shared memory and added with consecutive lanes on
+//    consecutive addresses (red.global.add.f64); long runs of one parameter block are
+//    pre-reduced with a segmented warp shuffle;
 //  * cost: warp shuffle + one partial per thread block, summed in a fixed order;
-//  * gradient: runs of blocks that share a parameter block (the points of a
-//    Schur-ordered BAL problem) are pre-reduced with a segmented warp shuffle;
-//    what is left goes out as fire-and-forget red.global.add.f64.
+//  * variants: Jet-free cost / residual kernel, plain, generic (manifolds, constant
+//    blocks), and all-outputs instantiations of the last two with the output flags as
+//    compile-time constants.
 #ifndef CERES_B200_INTERNAL_EVALUATE_KERNEL_CUH_
 #define CERES_B200_INTERNAL_EVALUATE_KERNEL_CUH_
 
