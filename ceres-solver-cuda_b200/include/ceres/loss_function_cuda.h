@@ -21,6 +21,21 @@ class LossFunctionCUDABase {
   virtual ~LossFunctionCUDABase() {}
 };
 
+namespace loss_internal {
+// rho <- (value, first derivative, second derivative)
+HOST_DEVICE inline void Set(double rho[3], double value, double d1, double d2) {
+  rho[0] = value;
+  rho[1] = d1;
+  rho[2] = d2;
+}
+// max(x, numeric_limits<double>::min()): rho' is kept strictly positive
+// (loss_function.cc:56,70).
+HOST_DEVICE inline double AtLeastTiny(double x) {
+  const double tiny = 2.2250738585072014e-308;
+  return x > tiny ? x : tiny;
+}
+}  // namespace loss_internal
+
 // rho(s) = s
 class TrivialLossCUDA : public LossFunctionCUDABase {
  public:
@@ -28,9 +43,7 @@ class TrivialLossCUDA : public LossFunctionCUDABase {
   // (corrector.cc:105-110 takes it only for rho'' > 0) and never needs rho[2].
   static constexpr bool kNonPositiveCurvature = true;
   HOST_DEVICE void Evaluate(double s, double rho[3]) const {
-    rho[0] = s;
-    rho[1] = 1.0;
-    rho[2] = 0.0;
+    loss_internal::Set(rho, s, 1.0, 0.0);
   }
 };
 
@@ -42,18 +55,13 @@ class HuberLossCUDA : public LossFunctionCUDABase {
   static constexpr bool kNonPositiveCurvature = true;
   HOST_DEVICE explicit HuberLossCUDA(double a) : a_(a), b_(a * a) {}
   HOST_DEVICE void Evaluate(double s, double rho[3]) const {
-    if (s > b_) {
-      const double r = sqrt(s);
-      rho[0] = 2.0 * a_ * r - b_;
-      const double d = a_ / r;
-      const double tiny = 2.2250738585072014e-308;  // numeric_limits<double>::min()
-      rho[1] = d > tiny ? d : tiny;
-      rho[2] = -rho[1] / (2.0 * s);
-    } else {
-      rho[0] = s;
-      rho[1] = 1.0;
-      rho[2] = 0.0;
+    if (!(s > b_)) {  // inlier region (and NaN, as in the reference): the identity
+      loss_internal::Set(rho, s, 1.0, 0.0);
+      return;
     }
+    const double root = sqrt(s);
+    const double slope = loss_internal::AtLeastTiny(a_ / root);
+    loss_internal::Set(rho, 2.0 * a_ * root - b_, slope, -slope / (2.0 * s));
   }
 
  private:
@@ -69,12 +77,10 @@ class CauchyLossCUDA : public LossFunctionCUDABase {
   static constexpr bool kNonPositiveCurvature = true;
   HOST_DEVICE explicit CauchyLossCUDA(double a) : b_(a * a), c_(1 / b_) {}
   HOST_DEVICE void Evaluate(double s, double rho[3]) const {
-    const double sum = 1.0 + s * c_;
-    const double inv = 1.0 / sum;
-    rho[0] = b_ * log(sum);
-    const double tiny = 2.2250738585072014e-308;
-    rho[1] = inv > tiny ? inv : tiny;
-    rho[2] = -c_ * (inv * inv);
+    const double one_plus = 1.0 + s * c_;
+    const double reciprocal = 1.0 / one_plus;
+    loss_internal::Set(rho, b_ * log(one_plus), loss_internal::AtLeastTiny(reciprocal),
+                       -c_ * (reciprocal * reciprocal));
   }
 
  private:
@@ -89,9 +95,7 @@ class ScaledLossCUDA : public LossFunctionCUDABase {
   HOST_DEVICE ScaledLossCUDA(const LossFunctionCUDA& rho, double a) : rho_(rho), a_(a) {}
   HOST_DEVICE void Evaluate(double s, double rho[3]) const {
     rho_.Evaluate(s, rho);
-    rho[0] *= a_;
-    rho[1] *= a_;
-    rho[2] *= a_;
+    loss_internal::Set(rho, rho[0] * a_, rho[1] * a_, rho[2] * a_);
   }
 
  private:
@@ -104,9 +108,7 @@ class ScaledLossCUDA<TrivialLossCUDA> : public LossFunctionCUDABase {
  public:
   HOST_DEVICE ScaledLossCUDA(const TrivialLossCUDA&, double a) : a_(a) {}
   HOST_DEVICE void Evaluate(double s, double rho[3]) const {
-    rho[0] = a_ * s;
-    rho[1] = a_;
-    rho[2] = 0.0;
+    loss_internal::Set(rho, a_ * s, a_, 0.0);
   }
 
  private:
