@@ -105,3 +105,18 @@ def test_problem_evaluate_cost_only_and_nothing():
     cp = B.CudaProblem(spec, with_device=False)
     ok, c, r, g, _, _ = cp.problem_evaluate()
     assert ok and abs(c - c_o) <= 1e-10 * c_o
+
+
+def test_problem_evaluate_fails_loudly_without_a_gpu():
+    """No CPU fallback behind Problem::Evaluate either: without a device it returns false
+    (and the blocks it held constant for the call are variable again)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    spec = P.bal_problem(5, 30, 120, seed=22)
+    cp = B.CudaProblem(spec, with_device=False)
+    ok, *_ = cp.problem_evaluate(parameter_blocks=np.arange(spec.meta["num_points"]))
+    assert not ok
+    # the cameras are not left constant: a Jacobian for one can still be requested
+    ok, c, res, jac, ids = cp.evaluate_residual_block(0)
+    assert ok and all(j is not None for j in jac)
