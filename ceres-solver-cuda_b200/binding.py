@@ -105,6 +105,7 @@ def driver():
         L.drv_timing.argtypes = [C.c_void_p, C.c_void_p]
         L.drv_shard_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.drv_plus.argtypes = [C.c_void_p] * 4
+        L.drv_plus_threads.argtypes = [C.c_void_p] * 4 + [C.c_int]
         L.drv_dense_jacobian.argtypes = [C.c_void_p, C.c_void_p]
         L.drv_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.drv_problem_evaluate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
@@ -396,8 +397,12 @@ class CudaProblem:
                 "residual_end": int(info[3]),
                 "segments": [tuple(int(x) for x in seg[3 * i:3 * i + 3]) for i in range(max(n, 0))]}
 
-    def plus(self, state, delta):
+    def plus(self, state, delta, num_threads=1):
         out = np.zeros(self.num_parameters)
+        if num_threads > 1:
+            driver().drv_plus_threads(self.h, _p(np.ascontiguousarray(state)),
+                                      _p(np.ascontiguousarray(delta)), _p(out), int(num_threads))
+            return out
         driver().drv_plus(self.h, _p(np.ascontiguousarray(state)), _p(np.ascontiguousarray(delta)),
                           _p(out))
         return out

@@ -372,6 +372,11 @@ int drv_shard_info(void* h, int32_t* info4, int64_t* segments, int max_segments)
 int drv_plus(void* h, const double* state, const double* delta, double* out) {
   return static_cast<DriverProblem*>(h)->program->Plus(state, delta, out) ? 1 : 0;
 }
+// Program::Plus on num_threads host threads (program.cc:121-150).
+int drv_plus_threads(void* h, const double* state, const double* delta, double* out,
+                     int num_threads) {
+  return static_cast<DriverProblem*>(h)->program->Plus(state, delta, out, num_threads) ? 1 : 0;
+}
 
 // ceres::Solve(options, ProblemCUDA*, summary) on the driver's problem.  ordering: group id
 // per parameter block (or NULL).  out: [initial_cost, final_cost, iterations,

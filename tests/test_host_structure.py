@@ -127,3 +127,18 @@ def test_plus_matches_oracle():
     x = op.initial_state()
     d = np.random.default_rng(2).normal(0, 0.1, op.num_effective_parameters)
     assert np.array_equal(op.plus(x, d), cp.plus(x, d))
+
+
+def test_plus_on_several_threads_is_identical():
+    """Program::Plus partitions the parameter blocks over the host threads
+    (program.cc:121-150); the result does not depend on the thread count."""
+    spec = P.pose_graph_problem(12000, 30000, seed=7)   # quaternion x R^3 manifolds
+    cp = B.CudaProblem(spec, with_device=False)
+    rng = np.random.default_rng(0)
+    state = cp.initial_state()
+    delta = rng.normal(0, 0.05, cp.num_effective_parameters)
+    one = cp.plus(state, delta)
+    many = cp.plus(state, delta, num_threads=8)
+    assert np.array_equal(one, many)
+    op = O.OracleProblem(spec)
+    assert np.max(np.abs(op.plus(state, delta) - one)) <= 1e-15 * np.max(np.abs(one))
