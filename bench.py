@@ -166,7 +166,7 @@ def run_reference(args):
     if rank != 0:
         return
     spec = make_spec(args)
-    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
+    steps, warmup = args.steps, args.warmup  # a step is a 6 M-block sample: ~0.6 s on 16 cores
     cpu = time_cpu(spec, args.cpu_sample_blocks, steps, warmup)
     line = {
         "impl": "reference", "metric": "residual blocks/s (residual+Jacobian+loss+gradient)",
