@@ -142,3 +142,69 @@ def test_plus_on_several_threads_is_identical():
     assert np.array_equal(one, many)
     op = O.OracleProblem(spec)
     assert np.max(np.abs(op.plus(state, delta) - one)) <= 1e-15 * np.max(np.abs(one))
+
+
+def random_mixed_problem(seed):
+    rng = np.random.default_rng(100 + seed)
+    b = P.ProblemBuilder()
+    by_size = {}
+    for size in (1, 2, 3, 4):
+        for _ in range(int(rng.integers(3, 9)) + (10 if size == 1 else 0)):
+            manifold = (P.MANIFOLD_NONE, 0)
+            if size >= 2 and rng.random() < 0.3:
+                mask = int(rng.integers(1, 2 ** size - 1))       # at least one free coordinate
+                manifold = (P.MANIFOLD_SUBSET, mask)
+            pb = b.add_parameter_block(rng.normal(size=size), manifold=manifold,
+                                       constant=bool(rng.random() < 0.25))
+            by_size.setdefault(size, []).append(pb)
+    kinds = [P.AFFINE_1_3_234, P.AFFINE_1_3_432, P.AFFINE_1_2_23, P.AFFINE_2_3_24, P.AFFINE_3_4_34,
+             P.BINARY_SCALAR, P.POINT_DISPLACEMENT, P.TEN_PARAMETER, P.PARAMETER_SENSITIVE]
+    for _ in range(int(rng.integers(20, 60))):
+        kind = kinds[int(rng.integers(len(kinds)))]
+        nres, sizes, flen = P.COST_TYPES[kind]
+        chosen, ok = [], True
+        for s in sizes:
+            free = [pb for pb in by_size[s] if pb not in chosen]
+            if not free:
+                ok = False
+                break
+            chosen.append(free[int(rng.integers(len(free)))])
+        if not ok:
+            continue
+        b.add_residual_block(kind, chosen, fdata=rng.normal(size=flen))
+    return b.build(num_eliminate_blocks=int(rng.integers(0, 6)))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_mixed_problems_structure(seed):
+    """Random problems mixing residual-block types with 1 to 10 arguments, constant blocks,
+    subset manifolds and unused blocks: program, offsets and both Jacobian layouts equal the
+    oracle's bit for bit, for the reduced program and for the unreduced one (whose constant
+    blocks keep their columns, as Problem::Evaluate needs)."""
+    spec = random_mixed_problem(seed)
+    for fmt in (0, 1):
+        for reduce in (True, False):
+            _compare_structure(spec, fmt, reduce=reduce)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(6))
+def test_random_mixed_problems_values(seed):
+    """The same random problems evaluated on the device, reduced and unreduced, both layouts."""
+    spec = random_mixed_problem(seed)
+    for fmt in (0, 1):
+        for reduce in (True, False):
+            op = O.OracleProblem(spec, jacobian_format=fmt, reduce=reduce)
+            cp = B.CudaProblem(spec, jacobian_format=fmt, reduce=reduce)
+            state = op.initial_state()
+            ok_o, c_o, r_o, g_o, j_o = op.evaluate(state)
+            ok, c, r, g, j = cp.evaluate(state)
+            assert ok == ok_o
+            if not ok_o:
+                continue
+            scale = lambda v: max(float(np.max(np.abs(v))) if v.size else 0.0, 1e-300)
+            assert abs(c - c_o) <= 1e-10 * max(abs(c_o), 1e-300)
+            assert np.max(np.abs(r - r_o), initial=0.0) <= 1e-12 * scale(r_o)
+            assert np.max(np.abs(g - g_o), initial=0.0) <= 1e-10 * scale(g_o)
+            n = op.num_jacobian_values
+            assert np.max(np.abs(j[:n] - j_o[:n]), initial=0.0) <= 1e-12 * scale(j_o[:n])
