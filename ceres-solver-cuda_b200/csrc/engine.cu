@@ -141,11 +141,20 @@ struct ResidualType {
   DeviceBuffer<char> d_functors, d_loss_table;
   DeviceBuffer<int32_t> d_loss_index, d_pb, d_soff, d_doff, d_jpos, d_jstride, d_respos;
   bool plain = true;
+  // Tables that turned out to be arithmetic progressions (cb200_launch_args::affine).
+  uint32_t affine = 0;
+  int32_t residual_base = 0, row_stride = 0;
+  int32_t jacobian_base[CB200_MAX_PARAMETER_BLOCKS] = {};
+  int32_t jacobian_step[CB200_MAX_PARAMETER_BLOCKS] = {};
 };
 
 // Sums the per-thread-block cost partials in a fixed order (one block, tree in
 // shared memory) and writes the total next to the gradient.
-__global__ void ReduceCostKernel(const double* __restrict__ partials, int n, double* out) {
+// out[1] = the evaluation status as a double, so that it travels through the same sum over
+// the ranks as the cost: every rank then returns the same verdict (a functor failing on one
+// rank fails the whole Evaluate, like the CPU evaluator's all-or-nothing contract).
+__global__ void ReduceCostKernel(const double* __restrict__ partials, int n, double* out,
+                                 const int32_t* __restrict__ status) {
   __shared__ double sm[256];
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) acc += partials[i];
@@ -155,7 +164,10 @@ __global__ void ReduceCostKernel(const double* __restrict__ partials, int n, dou
     if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *out = sm[0];
+  if (threadIdx.x == 0) {
+    out[0] = sm[0];
+    out[1] = *status ? 1.0 : 0.0;
+  }
 }
 
 // Gradient exchange, second half: every rank's exclusive range arrived in `staging`
@@ -525,11 +537,44 @@ __device__ __forceinline__ double BlockSum(double v) {
   return v;  // valid in thread 0
 }
 
+// Reproducible grid-wide sums: every thread block writes its partial sums, the last block to
+// arrive adds them in a fixed order.  The conjugate-gradient scalars are then bit-identical
+// run to run and, because every rank holds identical vectors, rank to rank: all ranks take
+// the same termination decision and issue the same number of collectives.
+struct ScalarReduce {
+  double* partials;    // [gridDim.x][3]
+  unsigned* arrivals;  // zero between kernels
+};
+template <int kCount>
+__device__ __forceinline__ void FinishScalars(const ScalarReduce red, const double (&v)[kCount],
+                                              double* S, const int (&slot)[kCount]) {
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < kCount; ++k) red.partials[blockIdx.x * 3 + k] = v[k];
+    __threadfence();
+    last = atomicAdd(red.arrivals, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < kCount; ++k) {
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+      acc += __ldcg(red.partials + b * 3 + k);
+    acc = BlockSum(acc);
+    if (threadIdx.x == 0) S[slot[k]] = acc;
+  }
+  if (threadIdx.x == 0) *red.arrivals = 0;
+}
+
 // minv = 1 / (colnorm + d2);  r = b;  z = minv r;  p = z;  x = 0;  rho = r.z;  rnorm2 = r.r
 __global__ void __launch_bounds__(256) CgInitKernel(int n, const double* __restrict__ colnorm,
                                                     const double* __restrict__ d2,
                                                     const double* __restrict__ b, double* minv,
-                                                    double* r, double* p, double* x, double* S) {
+                                                    double* r, double* p, double* x, double* S,
+                                                    const ScalarReduce red) {
   double rho = 0.0, rr = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double m = 1.0 / (colnorm[i] + (d2 ? d2[i] : 0.0));
@@ -541,23 +586,22 @@ __global__ void __launch_bounds__(256) CgInitKernel(int n, const double* __restr
     rho += ri * zi;
     rr += ri * ri;
   }
-  rho = BlockSum(rho);
-  rr = BlockSum(rr);
-  if (threadIdx.x == 0) {
-    atomicAdd(S + kSRho, rho);
-    atomicAdd(S + kSRnorm2, rr);
-  }
+  const double v[2] = {BlockSum(rho), BlockSum(rr)};
+  const int slot[2] = {kSRho, kSRnorm2};
+  FinishScalars<2>(red, v, S, slot);
 }
 
 // pq = p.(q + d2 p)
 __global__ void __launch_bounds__(256) CgDotKernel(int n, const double* __restrict__ p,
                                                    const double* __restrict__ q,
-                                                   const double* __restrict__ d2, double* S) {
+                                                   const double* __restrict__ d2, double* S,
+                                                   const ScalarReduce red) {
   double acc = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     acc += p[i] * (q[i] + (d2 ? d2[i] : 0.0) * p[i]);
-  acc = BlockSum(acc);
-  if (threadIdx.x == 0) atomicAdd(S + kSPq, acc);
+  const double v[1] = {BlockSum(acc)};
+  const int slot[1] = {kSPq};
+  FinishScalars<1>(red, v, S, slot);
 }
 
 // alpha = rho / pq;  x += alpha p;  r -= alpha (q + d2 p);  accumulates the next rho = r.(minv r),
@@ -567,7 +611,8 @@ __global__ void __launch_bounds__(256) CgUpdateKernel(int n, const double* __res
                                                       const double* __restrict__ d2,
                                                       const double* __restrict__ minv,
                                                       const double* __restrict__ b, double* x,
-                                                      double* r, const double* S, double* Snext) {
+                                                      double* r, const double* S, double* Snext,
+                                                      const ScalarReduce red) {
   const double alpha = S[kSRho] / S[kSPq];
   double rho = 0.0, rr = 0.0, xbr = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -580,14 +625,9 @@ __global__ void __launch_bounds__(256) CgUpdateKernel(int n, const double* __res
     rr += ri * ri;
     xbr += xi * (b[i] + ri);
   }
-  rho = BlockSum(rho);
-  rr = BlockSum(rr);
-  xbr = BlockSum(xbr);
-  if (threadIdx.x == 0) {
-    atomicAdd(Snext + kSRho, rho);
-    atomicAdd(Snext + kSRnorm2, rr);
-    atomicAdd(Snext + kSXbr, xbr);
-  }
+  const double v[3] = {BlockSum(rho), BlockSum(rr), BlockSum(xbr)};
+  const int slot[3] = {kSRho, kSRnorm2, kSXbr};
+  FinishScalars<3>(red, v, Snext, slot);
 }
 
 // p = minv r + (rho_next / rho) p
@@ -602,18 +642,16 @@ __global__ void __launch_bounds__(256) CgDirectionKernel(int n, const double* __
 
 // jy.b and |jy|^2 over this rank's residuals
 __global__ void __launch_bounds__(256) CgModelKernel(int n, const double* __restrict__ jy,
-                                                     const double* __restrict__ b, double* S) {
+                                                     const double* __restrict__ b, double* S,
+                                                     const ScalarReduce red) {
   double d = 0.0, s = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     d += jy[i] * b[i];
     s += jy[i] * jy[i];
   }
-  d = BlockSum(d);
-  s = BlockSum(s);
-  if (threadIdx.x == 0) {
-    atomicAdd(S + kSJyB, d);
-    atomicAdd(S + kSJy2, s);
-  }
+  const double v[2] = {BlockSum(d), BlockSum(s)};
+  const int slot[2] = {kSJyB, kSJy2};
+  FinishScalars<2>(red, v, S, slot);
 }
 
 }  // namespace
@@ -664,6 +702,8 @@ struct cb200_engine {
   DeviceBuffer<double> la_col[8];   // x-like: num_effective + 1 each
   DeviceBuffer<double> la_row;      // residual-like: this rank's residuals
   DeviceBuffer<double> la_scalars;  // 3 x kSCount
+  DeviceBuffer<double> la_partials; // per-thread-block partial sums of the scalar reductions
+  DeviceBuffer<unsigned> la_arrivals;
   double* h_la_scalars = nullptr;   // pinned, 3 x kSCount
 
   void* comm = nullptr;
@@ -738,7 +778,7 @@ void cb200_engine_destroy(cb200_engine* e) {
     delete t;
   }
   for (auto& b : e->la_col) b.Free();
-  e->la_row.Free(); e->la_scalars.Free();
+  e->la_row.Free(); e->la_scalars.Free(); e->la_partials.Free(); e->la_arrivals.Free();
   if (e->h_la_scalars) cudaFreeHost(e->h_la_scalars);
   e->d_gather.Free();
   e->d_state.Free(); e->d_plus.Free(); e->d_residuals.Free(); e->d_jacobian.Free();
@@ -1006,8 +1046,8 @@ int cb200_engine_finalize(cb200_engine* e) {
     t->n_local = n;
     const int tpb = t->desc.threads_per_block > 0 ? t->desc.threads_per_block : 128;
     // Cost partials reserved for the launch: the thunk's (persistent) grid is clamped to
-    // this, so the fixed-order reduction reads at most 1024 values per type.
-    t->grid = std::min((n + tpb - 1) / tpb, 1024);
+    // this, so the fixed-order reduction reads at most 2048 values per type.
+    t->grid = std::min((n + tpb - 1) / tpb, 2048);
     t->cost_partial_offset = e->total_cost_partials;
     e->total_cost_partials += t->grid;
     if (n == 0) continue;
@@ -1044,6 +1084,31 @@ int cb200_engine_finalize(cb200_engine* e) {
         ++a;
       }
     }
+    // Arithmetic progressions: a type laid out in program order (bundle adjustment after
+    // the Schur ordering, a pose graph's residuals) needs no position tables at all.
+    {
+      bool res_affine = true, jac_affine = true, delta_is_state = true;
+      for (int32_t i = 0; i < n && res_affine; ++i)
+        res_affine = respos[i] == respos[0] + static_cast<int64_t>(i) * kres;
+      for (int j = 0; j < nb; ++j) {
+        const int32_t* jp = jpos.data() + static_cast<size_t>(j) * n;
+        const int64_t step = n > 1 ? static_cast<int64_t>(jp[1]) - jp[0] : 0;
+        t->jacobian_base[j] = jp[0];
+        t->jacobian_step[j] = static_cast<int32_t>(step);
+        for (int32_t i = 0; i < n && jac_affine; ++i)
+          jac_affine = jp[i] >= 0 && jp[i] == jp[0] + step * i;
+        const int32_t* so = soff.data() + static_cast<size_t>(j) * n;
+        const int32_t* dof = doff.data() + static_cast<size_t>(j) * n;
+        for (int32_t i = 0; i < n && delta_is_state; ++i) delta_is_state = so[i] == dof[i];
+      }
+      for (int32_t i = 0; i < n && jac_affine; ++i) jac_affine = jstride[i] == jstride[0];
+      t->residual_base = respos[0];
+      t->row_stride = jstride[0];
+      t->affine = (res_affine ? CB200_AFFINE_RESIDUAL : 0u) |
+                  (jac_affine ? CB200_AFFINE_JACOBIAN : 0u) |
+                  (delta_is_state ? CB200_AFFINE_DELTA_IS_STATE : 0u);
+      if (getenv("CB200_NO_AFFINE")) t->affine = 0;  // A/B switch: always read the tables
+    }
     if (e->planning) continue;
     CB200_CUDA(e, t->d_pb.Upload(pb, e->stream));
     CB200_CUDA(e, t->d_soff.Upload(soff, e->stream));
@@ -1066,8 +1131,10 @@ int cb200_engine_finalize(cb200_engine* e) {
     return CB200_OK;
   }
   CB200_CUDA(e, e->d_pb_table.Upload(table, e->stream));
+  // (+4: the kernels gather parameter blocks in aligned 16-byte pieces and may read up to
+  // two doubles past the last block)
   CB200_CUDA(e, e->d_state.Resize(static_cast<size_t>(e->num_parameters) +
-                                  e->num_constant_parameters + 1));
+                                  e->num_constant_parameters + 4));
   if (e->num_constant_parameters > 0)
     CB200_CUDA(e, cudaMemcpyAsync(e->d_state.ptr + e->num_parameters, e->constant_state.data(),
                                   e->constant_state.size() * sizeof(double),
@@ -1152,6 +1219,11 @@ static int EvaluateOnDevice(cb200_engine* e, uint32_t flags, bool want_r, bool w
     a.gradient = e->d_gradcost.ptr;
     a.cost_partials = e->d_cost_partials.ptr + t->cost_partial_offset;
     a.status = e->d_status.ptr;
+    a.affine = t->affine;
+    a.residual_base = t->residual_base;
+    a.row_stride = t->row_stride;
+    std::memcpy(a.jacobian_base, t->jacobian_base, sizeof(a.jacobian_base));
+    std::memcpy(a.jacobian_step, t->jacobian_step, sizeof(a.jacobian_step));
     const int err = t->desc.launch(&a, s);
     if (err != 0)
       return e->Fail(CB200_ERROR_CUDA, "kernel launch: %s",
@@ -1159,19 +1231,18 @@ static int EvaluateOnDevice(cb200_engine* e, uint32_t flags, bool want_r, bool w
     ++launches;
   }
   CB200_CUDA(e, cudaEventRecord(e->ev[2], s));
-  if (e->total_cost_partials > 0) {
-    ReduceCostKernel<<<1, 256, 0, s>>>(e->d_cost_partials.ptr, e->total_cost_partials,
-                                       e->d_gradcost.ptr + e->num_effective);
-    ++launches;
-  }
+  // [gradient | cost | failed]: the last two slots are written here
+  ReduceCostKernel<<<1, 256, 0, s>>>(e->d_cost_partials.ptr, e->total_cost_partials,
+                                     e->d_gradcost.ptr + e->num_effective, e->d_status.ptr);
+  ++launches;
   if (e->comm && e->world > 1) {
     NcclApi* n = GetNccl();
     double* g = e->d_gradcost.ptr;
     double* cost_slot = g + e->num_effective;
     int r = 0;
     if (!want_g) {
-      // cost-only evaluation: one double
-      r = n->AllReduce(cost_slot, cost_slot, 1, kNcclFloat64, kNcclSum, e->comm, s);
+      // cost-only evaluation: [cost | failed]
+      r = n->AllReduce(cost_slot, cost_slot, 2, kNcclFloat64, kNcclSum, e->comm, s);
     } else if (!e->gather_ok || !n->AllGather || !n->GroupStart || !n->GroupEnd ||
                !getenv("CB200_GRADIENT_GATHER")) {
       // One all-reduce over [gradient | cost]: the default.  The all-gather form below is
@@ -1179,7 +1250,7 @@ static int EvaluateOnDevice(cb200_engine* e, uint32_t flags, bool want_r, bool w
       // time per evaluation 1.25 ms (all-reduce) vs 1.33 ms (gather) on 2 GPUs and 0.62 vs
       // 0.63 ms on 8 - NCCL's all-reduce over NVSwitch already moves each byte once per rank.
       // It is kept behind CB200_GRADIENT_GATHER for fabrics without in-switch reduction.
-      r = n->AllReduce(g, g, static_cast<size_t>(e->num_effective) + 1, kNcclFloat64, kNcclSum,
+      r = n->AllReduce(g, g, static_cast<size_t>(e->num_effective) + 2, kNcclFloat64, kNcclSum,
                        e->comm, s);
     } else {
       // After a Schur ordering all but a handful of gradient entries are touched by one rank
@@ -1194,11 +1265,11 @@ static int EvaluateOnDevice(cb200_engine* e, uint32_t flags, bool want_r, bool w
       for (const GradientInterval& iv : e->exchange) {
         if (iv.owner >= 0) continue;
         size_t len = static_cast<size_t>(iv.length);
-        if (iv.begin + iv.length == e->num_effective) { ++len; cost_done = true; }
+        if (iv.begin + iv.length == e->num_effective) { len += 2; cost_done = true; }
         r |= n->AllReduce(g + iv.begin, g + iv.begin, len, kNcclFloat64, kNcclSum, e->comm, s);
       }
       if (!cost_done)
-        r |= n->AllReduce(cost_slot, cost_slot, 1, kNcclFloat64, kNcclSum, e->comm, s);
+        r |= n->AllReduce(cost_slot, cost_slot, 2, kNcclFloat64, kNcclSum, e->comm, s);
       r |= n->AllGather(g + e->gather.begin[e->rank], e->d_gather.ptr,
                         static_cast<size_t>(e->gather.chunk), kNcclFloat64, e->comm, s);
       r |= n->GroupEnd();
@@ -1245,9 +1316,7 @@ int cb200_engine_evaluate(cb200_engine* e, const double* state, const double* pl
                                   jacobian_values != nullptr || keep_j);
   if (rc != CB200_OK) return rc;
   CB200_CUDA(e, cudaMemcpyAsync(e->h_scalars, e->d_gradcost.ptr + e->num_effective,
-                                sizeof(double), cudaMemcpyDeviceToHost, s));
-  CB200_CUDA(e, cudaMemcpyAsync(e->h_scalars + 1, e->d_status.ptr, sizeof(int32_t),
-                                cudaMemcpyDeviceToHost, s));
+                                2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (!(flags & CB200_SKIP_HOST_COPY)) {
     if (residuals && !keep_r && e->res_end > e->res_begin)
       CB200_CUDA(e, cudaMemcpyAsync(residuals + e->res_begin, e->d_residuals.ptr,
@@ -1266,9 +1335,7 @@ int cb200_engine_evaluate(cb200_engine* e, const double* state, const double* pl
   CB200_CUDA(e, cudaStreamSynchronize(s));  // the only host synchronisation
   FinishTiming(e);
   *cost = e->h_scalars[0];
-  int32_t status;
-  std::memcpy(&status, e->h_scalars + 1, sizeof(status));
-  return status ? CB200_EVALUATION_FAILED : CB200_OK;
+  return e->h_scalars[1] != 0.0 ? CB200_EVALUATION_FAILED : CB200_OK;
 }
 
 int cb200_engine_evaluate_device(cb200_engine* e, const double* state_device,
@@ -1292,16 +1359,12 @@ int cb200_engine_evaluate_device(cb200_engine* e, const double* state_device,
                                   want_jacobian != 0);
   if (rc != CB200_OK) return rc;
   CB200_CUDA(e, cudaMemcpyAsync(e->h_scalars, e->d_gradcost.ptr + e->num_effective,
-                                sizeof(double), cudaMemcpyDeviceToHost, s));
-  CB200_CUDA(e, cudaMemcpyAsync(e->h_scalars + 1, e->d_status.ptr, sizeof(int32_t),
-                                cudaMemcpyDeviceToHost, s));
+                                2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CB200_CUDA(e, cudaEventRecord(e->ev[4], s));
   CB200_CUDA(e, cudaStreamSynchronize(s));
   FinishTiming(e);
   *cost = e->h_scalars[0];
-  int32_t status;
-  std::memcpy(&status, e->h_scalars + 1, sizeof(status));
-  return status ? CB200_EVALUATION_FAILED : CB200_OK;
+  return e->h_scalars[1] != 0.0 ? CB200_EVALUATION_FAILED : CB200_OK;
 }
 
 void* cb200_engine_device_ptr(cb200_engine* e, int which) {
@@ -1374,6 +1437,7 @@ static int SumOverRanks(cb200_engine* e, double* v, size_t count) {
   return CB200_OK;
 }
 
+constexpr int kMaxVectorGrid = 148 * 8;
 static int PrepareLinearAlgebra(cb200_engine* e, bool need_residuals) {
   if (!e) return CB200_ERROR_INVALID_ARGUMENT;
   if (!e->finalized) return e->Fail(CB200_ERROR_NOT_FINALIZED, "not finalized");
@@ -1388,6 +1452,11 @@ static int PrepareLinearAlgebra(cb200_engine* e, bool need_residuals) {
   for (auto& b : e->la_col) CB200_CUDA(e, b.Resize(static_cast<size_t>(e->num_effective) + 1));
   CB200_CUDA(e, e->la_row.Resize(static_cast<size_t>(e->res_end - e->res_begin) + 1));
   CB200_CUDA(e, e->la_scalars.Resize(3 * kSCount));
+  CB200_CUDA(e, e->la_partials.Resize(3 * kMaxVectorGrid));
+  if (!e->la_arrivals.ptr) {
+    CB200_CUDA(e, e->la_arrivals.Resize(1));
+    CB200_CUDA(e, cudaMemsetAsync(e->la_arrivals.ptr, 0, sizeof(unsigned), e->stream));
+  }
   if (!e->h_la_scalars)
     CB200_CUDA(e, cudaHostAlloc(reinterpret_cast<void**>(&e->h_la_scalars),
                                 3 * kSCount * sizeof(double), cudaHostAllocDefault));
@@ -1463,8 +1532,9 @@ int cb200_engine_cgnr_solve(cb200_engine* e, const double* d_squared,
   double* w = e->la_row.ptr;
   const double* residuals = e->d_residuals.ptr;
   double* S = e->la_scalars.ptr;  // three rotating sets of scalars
-  const int vgrid = std::max(1, std::min((ne + 255) / 256, 148 * 8));
-  const int rgrid = std::max(1, std::min((m + 255) / 256, 148 * 8));
+  const int vgrid = std::max(1, std::min((ne + 255) / 256, kMaxVectorGrid));
+  const int rgrid = std::max(1, std::min((m + 255) / 256, kMaxVectorGrid));
+  const ScalarReduce red{e->la_partials.ptr, e->la_arrivals.ptr};
   std::memset(summary, 0, sizeof(*summary));
   bool one_pass = true;
   for (const ResidualType* t : e->types)
@@ -1480,7 +1550,7 @@ int cb200_engine_cgnr_solve(cb200_engine* e, const double* d_squared,
   if ((rc = SumOverRanks(e, b, ne)) != CB200_OK) return rc;
   if ((rc = SumOverRanks(e, colnorm, ne)) != CB200_OK) return rc;
   CB200_CUDA(e, cudaMemsetAsync(S, 0, 3 * kSCount * sizeof(double), s));
-  CgInitKernel<<<vgrid, 256, 0, s>>>(ne, colnorm, d2, b, minv, r, p, x, S);
+  CgInitKernel<<<vgrid, 256, 0, s>>>(ne, colnorm, d2, b, minv, r, p, x, S, red);
   CB200_CUDA(e, cudaMemcpyAsync(e->h_la_scalars, S, kSCount * sizeof(double),
                                 cudaMemcpyDeviceToHost, s));
   CB200_CUDA(e, cudaStreamSynchronize(s));
@@ -1506,9 +1576,9 @@ int cb200_engine_cgnr_solve(cb200_engine* e, const double* d_squared,
         if ((rc = RunJacobianWalk(e, kOpLeft, w, q)) != CB200_OK) return rc;
       }
       if ((rc = SumOverRanks(e, q, ne)) != CB200_OK) return rc;
-      CgDotKernel<<<vgrid, 256, 0, s>>>(ne, p, q, d2, Sc);
+      CgDotKernel<<<vgrid, 256, 0, s>>>(ne, p, q, d2, Sc, red);
       CB200_CUDA(e, cudaMemsetAsync(Sn, 0, kSCount * sizeof(double), s));
-      CgUpdateKernel<<<vgrid, 256, 0, s>>>(ne, p, q, d2, minv, b, x, r, Sc, Sn);
+      CgUpdateKernel<<<vgrid, 256, 0, s>>>(ne, p, q, d2, minv, b, x, r, Sc, Sn, red);
       CgDirectionKernel<<<vgrid, 256, 0, s>>>(ne, r, minv, p, Sc, Sn);
       CB200_CUDA(e, cudaMemcpyAsync(e->h_la_scalars, S, 3 * kSCount * sizeof(double),
                                     cudaMemcpyDeviceToHost, s));
@@ -1538,7 +1608,7 @@ int cb200_engine_cgnr_solve(cb200_engine* e, const double* d_squared,
   double* Sm = S + ((cur + 2) % 3) * kSCount;
   CB200_CUDA(e, cudaMemsetAsync(Sm, 0, kSCount * sizeof(double), s));
   if ((rc = RunJacobianWalk(e, kOpRight, x, w)) != CB200_OK) return rc;
-  CgModelKernel<<<rgrid, 256, 0, s>>>(m, w, residuals, Sm);
+  CgModelKernel<<<rgrid, 256, 0, s>>>(m, w, residuals, Sm, red);
   if (e->comm && e->world > 1) {
     NcclApi* n = GetNccl();
     if (n->AllReduce(Sm + kSJyB, Sm + kSJyB, 2, kNcclFloat64, kNcclSum, e->comm, s) != 0)

@@ -89,15 +89,29 @@ void ProblemImpl::SetManifold(double* values, Manifold* manifold) {
   if (manifold != nullptr) manifolds_to_delete_.push_back(manifold);
 }
 
+// The reference LOG(FATAL)s with this message when the block is unknown
+// (problem_impl.cc:455-515).
+ParameterBlock* ProblemImpl::FindParameterBlockOrDie(const double* values, const char* what) const {
+  ParameterBlock* pb = FindParameterBlock(values);
+  if (pb == nullptr) {
+    std::fprintf(stderr,
+                 "Parameter block not found: %p. You must add the parameter block to the "
+                 "problem before %s.\n",
+                 static_cast<const void*>(values), what);
+    std::abort();
+  }
+  return pb;
+}
+
 void ProblemImpl::SetParameterBlockConstant(const double* values) {
-  FindParameterBlock(values)->is_set_constant = true;
+  FindParameterBlockOrDie(values, "it can be set constant")->is_set_constant = true;
 }
 void ProblemImpl::SetParameterBlockVariable(double* values) {
-  FindParameterBlock(values)->is_set_constant = false;
+  FindParameterBlockOrDie(values, "it can be set varying")->is_set_constant = false;
 }
 
 void ProblemImpl::SetParameterLowerBound(double* values, int index, double bound) {
-  ParameterBlock* pb = FindParameterBlock(values);
+  ParameterBlock* pb = FindParameterBlockOrDie(values, "you can set a lower bound on one of its components");
   if (!pb->lower_bounds) {
     pb->lower_bounds.reset(new double[pb->size]);
     std::fill_n(pb->lower_bounds.get(), pb->size, -std::numeric_limits<double>::max());
@@ -105,7 +119,7 @@ void ProblemImpl::SetParameterLowerBound(double* values, int index, double bound
   pb->lower_bounds[index] = bound;
 }
 void ProblemImpl::SetParameterUpperBound(double* values, int index, double bound) {
-  ParameterBlock* pb = FindParameterBlock(values);
+  ParameterBlock* pb = FindParameterBlockOrDie(values, "you can set an upper bound on one of its components");
   if (!pb->upper_bounds) {
     pb->upper_bounds.reset(new double[pb->size]);
     std::fill_n(pb->upper_bounds.get(), pb->size, std::numeric_limits<double>::max());
@@ -113,11 +127,11 @@ void ProblemImpl::SetParameterUpperBound(double* values, int index, double bound
   pb->upper_bounds[index] = bound;
 }
 double ProblemImpl::GetParameterLowerBound(const double* values, int index) const {
-  const ParameterBlock* pb = FindParameterBlock(values);
+  const ParameterBlock* pb = FindParameterBlockOrDie(values, "you can get its lower bound");
   return pb->lower_bounds ? pb->lower_bounds[index] : -std::numeric_limits<double>::max();
 }
 double ProblemImpl::GetParameterUpperBound(const double* values, int index) const {
-  const ParameterBlock* pb = FindParameterBlock(values);
+  const ParameterBlock* pb = FindParameterBlockOrDie(values, "you can get its upper bound");
   return pb->upper_bounds ? pb->upper_bounds[index] : std::numeric_limits<double>::max();
 }
 
@@ -156,8 +170,12 @@ ResidualBlock* ProblemImpl::AddResidualBlock(int type, CostFunction* cost_functi
   // and the reference then copies one loss object per block to the device
   // (autodiff_residual_block_cuda_evaluator.h:96-133).  Loss functors are plain data
   // evaluated by value on the device, so equal bytes mean the same loss.
+  // (Same pointer as the last block is only a shortcut when its bytes still match what was
+  // captured: a stack loss may have been modified, a freed one reallocated at the address.)
   int loss_id = -1;
-  if (!t.loss_objects.empty() && t.loss_objects.back() == loss) {
+  if (!t.loss_objects.empty() && t.loss_objects.back() == loss &&
+      std::memcmp(loss, t.loss_table.data() + (t.loss_objects.size() - 1) * t.desc.loss_size,
+                  t.desc.loss_size) == 0) {
     loss_id = static_cast<int>(t.loss_objects.size()) - 1;
   } else {
     const std::string bytes(static_cast<const char*>(loss), t.desc.loss_size);

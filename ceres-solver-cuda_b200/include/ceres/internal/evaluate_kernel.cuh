@@ -52,7 +52,10 @@
 namespace ceres {
 namespace internal {
 
-constexpr int kEvaluateThreads = 128;
+#ifndef CB200_EVALUATE_THREADS
+#define CB200_EVALUATE_THREADS 128
+#endif
+constexpr int kEvaluateThreads = CB200_EVALUATE_THREADS;
 // internal/ceres/array_utils.h: the value autodiff leaves in outputs a functor
 // did not write; evaluations containing it are invalid.
 constexpr double kImpossibleValue = 1e302;
@@ -81,6 +84,17 @@ struct BlockDims {
     for (int i = 0; i < kNumBlocks; ++i) m = Size(i) > m ? Size(i) : m;
     return m;
   }
+  // 16-byte chunks of the aligned window that contains block j whether its first double
+  // sits at an even or an odd offset of the state vector.
+  __host__ __device__ static constexpr int WindowChunks(int j) { return Size(j) / 2 + 1; }
+  __host__ __device__ static constexpr int ChunksBefore(int j) {
+    int o = 0;
+    for (int i = 0; i < j; ++i) o += WindowChunks(i);
+    return o;
+  }
+  // chunks per thread; odd, so that the 16-byte copies of 8 consecutive threads (one
+  // shared-memory wavefront) fall into distinct banks
+  __host__ __device__ static constexpr int RowChunks() { return ChunksBefore(kNumBlocks) | 1; }
 };
 
 template <typename Dims, typename Functor, typename T, std::size_t... Is>
@@ -112,6 +126,27 @@ __device__ __forceinline__ void WarpSegmentedSum(int run_end, double (&v)[kCount
     }
   }
 }
+
+__device__ __forceinline__ int VolatileLaneId() {
+  int lane;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+  return lane;
+}
+
+// (row, column) of element 32 * round + lane in a row-major [32][kSize] array.
+template <int kSize>
+struct RoundIndex {
+  int row, c;
+  __device__ __forceinline__ explicit RoundIndex(int lane) : row(lane / kSize), c(lane % kSize) {}
+  __device__ __forceinline__ void Next() {
+    row += 32 / kSize;
+    c += 32 % kSize;
+    if (c >= kSize) {
+      c -= kSize;
+      ++row;
+    }
+  }
+};
 
 __device__ __forceinline__ void RedAdd(double* address, double value) {
   // No return value wanted: red.global.add.f64 instead of an atom round trip.
@@ -214,9 +249,6 @@ __device__ __forceinline__ void CpAsyncWait() {
 
 // Tuning switches (compile-time; scripts/kbench.cu builds the kernel with several
 // settings to measure each on the GPU).
-#ifndef CB200_KERNEL_INTS_IN_SMEM
-#define CB200_KERNEL_INTS_IN_SMEM 1   // per-block int tables ride the cp.async pipeline
-#endif
 #ifndef CB200_KERNEL_FMA_CHECK
 #define CB200_KERNEL_FMA_CHECK 1      // finite check: 1 = FMA chain (FP64 pipe), 0 = integer max
 #endif
@@ -224,7 +256,7 @@ __device__ __forceinline__ void CpAsyncWait() {
 #define CB200_KERNEL_FMA_CHECK_CHAINS 1
 #endif
 #ifndef CB200_KERNEL_SPECIALISE_ALL_OUTPUTS
-#define CB200_KERNEL_SPECIALISE_ALL_OUTPUTS 1  // extra instantiation for the all-outputs call
+#define CB200_KERNEL_SPECIALISE_ALL_OUTPUTS 1  // extra instantiations for the all-outputs call
 #endif
 #ifndef CB200_KERNEL_STAGE_GRADIENT
 #define CB200_KERNEL_STAGE_GRADIENT 1 // warp-staged, sector-coalesced gradient reductions
@@ -235,11 +267,23 @@ __device__ __forceinline__ void CpAsyncWait() {
 #ifndef CB200_KERNEL_STAGE_JACOBIAN
 #define CB200_KERNEL_STAGE_JACOBIAN 1 // warp-staged, fully coalesced Jacobian stores
 #endif
-#ifndef CB200_KERNEL_COOP_GATHER
-#define CB200_KERNEL_COOP_GATHER 1    // warp-cooperative, sector-coalesced parameter gather
-#endif
 #ifndef CB200_KERNEL_BULK_STORE
 #define CB200_KERNEL_BULK_STORE 1     // staged cells leave through TMA bulk copies (UBLKCP)
+#endif
+#ifndef CB200_KERNEL_GATHER
+// How a warp's 32 residual blocks fetch their parameter blocks into shared memory:
+// 0 = warp-cooperative, 8-byte copies, consecutive lanes on consecutive doubles of a block;
+// 1 = every thread copies its own blocks, 16-byte pieces of the aligned window;
+// 2 = warp-cooperative, 16-byte pieces of the aligned windows.
+#define CB200_KERNEL_GATHER 2
+#endif
+#ifndef CB200_KERNEL_EARLY_PREFETCH
+// 1: parameters and functor are double-buffered and the copies for block k+1 are issued
+// before block k is computed; 0: single-buffered, issued after block k's last functor call.
+#define CB200_KERNEL_EARLY_PREFETCH 1
+#endif
+#ifndef CB200_KERNEL_SEGMENTED_GRADIENT
+#define CB200_KERNEL_SEGMENTED_GRADIENT 1  // warp-shuffle pre-reduction of long same-block runs
 #endif
 
 // ---- TMA bulk store shared -> global (cp.async.bulk): one instruction moves a
@@ -264,13 +308,6 @@ __device__ __forceinline__ void BulkWaitAll() {
 }
 
 __host__ __device__ constexpr int MaxInt(int a, int b) { return a > b ? a : b; }
-// Doubles of per-warp output staging: every argument's dense cells side by side.
-// Argument j stages into its own region [32 * kRes * Offset(j), +32 * kRes * Size(j));
-// padded (odd-pitch) staging may spill 32 doubles past its region, hence the slack.
-__host__ __device__ constexpr int WarpStageDoubles(int num_residuals, int max_block,
-                                                   int num_parameters) {
-  return 32 * num_residuals * num_parameters + 32 + 0 * max_block;
-}
 
 // Accumulates evidence of a non-finite value; Bad() is true iff one was seen.
 struct FiniteCheck {
@@ -320,6 +357,12 @@ constexpr int kVariantGeneric = 2;  // Jets; per-block manifold projection / con
 // constants, which removes their (uniform) branches and lets the compiler schedule across.
 constexpr int kVariantPlainAll = 3;
 constexpr int kVariantGenericAll = 4;  // kVariantGeneric with all outputs (either value layout)
+// The two all-outputs variants are instantiated twice: reading the per-block integer tables
+// (any program), and `kAffine`, for types whose tables are arithmetic progressions
+// (cb200_launch_args::affine: one residual-block type laid out in program order, e.g. bundle
+// adjustment): positions are computed from the block index, nothing is fetched, the
+// contiguity of a warp's Jacobian cells is known without a vote, and 16-20 bytes per block
+// of index traffic disappear.
 
 // ---- derivative passes.  Wide problems (pose graphs: 14 derivative lanes x 6 residuals
 // = 90 live doubles of output alone) are differentiated in several passes, each seeding
@@ -363,116 +406,144 @@ struct PassPlan {
   }
 };
 
-template <typename Functor, int kNumParameters, int kNumBlocks, int kParameterPitch>
-struct PrefetchLayout {
-  // doubles per thread for the parameters; the cooperative gather pads every block to an
-  // odd pitch (at most one extra double per block) so both its writes and the owner
-  // lane's reads are bank-conflict free
+__host__ __device__ constexpr int StagePitch(int n) { return n | 1; }
+
+// CTAs per SM the Jet kernels are compiled for.  Measured on B200 for the BAL functor
+// (scripts/kbench.cu, profiles/r2_kbench_variants.txt): 3 CTAs x 128 threads (162 registers)
+// 1.98 ms; 4 x 128 (128 registers, no spills) 2.08; 2 x 128 (242 registers) 2.36; 5 x 96 2.16;
+// 3 x 160 2.19; 7 x 64 2.19 - more warps cost the compiler the registers it uses to overlap
+// independent Jet lanes, fewer warps cost latency hiding.  Wide problems get 2 CTAs.
+#ifndef CB200_RESIDENT_CTAS_SMALL
+#define CB200_RESIDENT_CTAS_SMALL 3
+#endif
+#ifndef CB200_RESIDENT_CTAS_COST
+#define CB200_RESIDENT_CTAS_COST 6  // CTAs per SM wanted for the Jet-free variant
+#endif
+#ifndef CB200_RESIDENT_CTAS_TABLES
+#define CB200_RESIDENT_CTAS_TABLES 3  // variants that stage the int tables need more shared memory
+#endif
+__host__ __device__ constexpr int ResidentCtas(int num_residuals, int num_parameters,
+                                               bool int_tables = false) {
+  return (num_parameters <= 13 && num_residuals <= 3)
+             ? (int_tables ? CB200_RESIDENT_CTAS_TABLES : CB200_RESIDENT_CTAS_SMALL)
+             : 2;
+}
+// Dynamic shared memory a CTA may use so that `ctas` of them fit on an SM (228 KB per SM,
+// 1 KB reserved per CTA, at most 227 KB for one CTA).
+__host__ __device__ constexpr int SmemBudget(int ctas) {
+  const int share = 228 * 1024 / ctas - 1024;
+  return share < 227 * 1024 ? share : 227 * 1024;
+}
+
+// Shared memory plan of a kernel instantiation.  Per CTA:
+//   [parameters: one row of 16-byte windows per thread][functor slot per thread]
+//   [per-block integer tables, two stages — absent when kInts is false]
+//   [per warp: Jacobian staging | gradient staging]
+// Parameters and functor are single-buffered: the copies for the next residual block are
+// issued after the last functor call of the current one, into the rows just consumed.
+template <typename Functor, bool kInts, int kRes, int... Ns>
+struct SmemPlan {
+  using Dims = BlockDims<Ns...>;
+  static constexpr int kNB = Dims::kNumBlocks;
+  // bytes per thread of one parameter stage
   static constexpr int kParamBytes =
-      (CB200_KERNEL_COOP_GATHER ? kParameterPitch : kNumParameters) * 8;
-  // Per-block int tables that travel with the parameters: [delta offset or block id]
-  // and [Jacobian position] per argument, residual position, CRS row stride, loss index.
-  static constexpr int kIntSlots = 2 * kNumBlocks + 3;
-  static constexpr int kSlotDelta = 0, kSlotJpos = kNumBlocks, kSlotResidual = 2 * kNumBlocks,
-                       kSlotRowStride = 2 * kNumBlocks + 1, kSlotLoss = 2 * kNumBlocks + 2;
+      CB200_KERNEL_GATHER == 0 ? Dims::PitchBefore(kNB) * 8
+                               : (CB200_KERNEL_GATHER == 1 ? Dims::RowChunks() * 16
+                                                           : Dims::ChunksBefore(kNB) * 16);
+  static constexpr int kStages = CB200_KERNEL_EARLY_PREFETCH ? 2 : 1;
   static constexpr bool kFunctorInSmem =
       (sizeof(Functor) % 4 == 0) && (alignof(Functor) <= 16) && (sizeof(Functor) <= 128);
   static constexpr int kFunctorBytes = kFunctorInSmem ? static_cast<int>(sizeof(Functor)) : 0;
   // Functor slots are padded to 16 bytes so every slot is 16-byte aligned.
   static constexpr int kFunctorSlot = (kFunctorBytes + 15) / 16 * 16;
-  static constexpr int kStageBytes = (kParamBytes + kIntSlots * 4 + kFunctorSlot) * kEvaluateThreads;
-  static constexpr int kPrefetchBytes = 2 * kStageBytes;
-  static constexpr bool kFits = kPrefetchBytes <= 96 * 1024;
-};
+  // Per-block int tables that travel with the parameters: [delta offset or block id]
+  // and [Jacobian position] per argument, residual position, CRS row stride, loss index.
+  static constexpr int kIntSlots = 2 * kNB + 3;
+  static constexpr int kSlotDelta = 0, kSlotJpos = kNB, kSlotResidual = 2 * kNB,
+                       kSlotRowStride = 2 * kNB + 1, kSlotLoss = 2 * kNB + 2;
+  static constexpr int kIntStageBytes = kInts ? kIntSlots * 4 * kEvaluateThreads : 0;
 
-__host__ __device__ constexpr int StagePitch(int n) { return n | 1; }
+  static constexpr int kParamOffset = 0;
+  static constexpr int kParamStageBytes = kParamBytes * kEvaluateThreads;
+  static constexpr int kFunctorOffset = kStages * kParamStageBytes;
+  static constexpr int kFunctorStageBytes = kFunctorSlot * kEvaluateThreads;
+  static constexpr int kIntOffset = kFunctorOffset + kStages * kFunctorStageBytes;
+  static constexpr int kPrefetchRaw = kIntOffset + 2 * kIntStageBytes;
+  static constexpr bool kFits = kPrefetchRaw <= 96 * 1024;
+  static constexpr int kPrefetchBytes = kFits ? kPrefetchRaw : 0;
 
-// Shared memory plan of a kernel instantiation.
-template <typename Functor, int kRes, int... Ns>
-struct SmemPlan {
-  using Dims = BlockDims<Ns...>;
-  using Layout = PrefetchLayout<Functor, Dims::kNumParameters, Dims::kNumBlocks,
-                                Dims::PitchBefore(Dims::kNumBlocks)>;
-  static constexpr int kPrefetchBytes = Layout::kFits ? Layout::kPrefetchBytes : 0;
+  static constexpr int kCtas = ResidentCtas(kRes, Dims::kNumParameters, kInts);
   // per warp: every argument's cells side by side (Jacobian staging) ...
   static constexpr int kJacobianDoubles = 32 * kRes * Dims::kNumParameters;
-  // ... and one padded row per lane for the staged gradient reductions
-  // the staged gradient reductions reuse the Jacobian staging buffer: with a single
-  // derivative pass every gradient is out before the first cell is staged.
-  // (plus, per lane, the destination offset and the live-column mask: 2 x 32 ints)
+  // ... and one padded row per lane for the staged gradient reductions (plus, per lane,
+  // the destination offset and the live-column mask: 2 x 32 ints).  With a single
+  // derivative pass every gradient is out before the first cell is staged, so the
+  // gradient staging reuses the Jacobian staging buffer.
   static constexpr int kGradientStage = 32 * StagePitch(Dims::MaxSize()) + 32;
   static constexpr bool kGradientAliasesJacobian =
-      PassPlan<kRes, Ns...>::kNumPasses == 1 &&
-      kGradientStage <= kJacobianDoubles;
+      PassPlan<kRes, Ns...>::kNumPasses == 1 && kGradientStage <= kJacobianDoubles;
   static constexpr int kGradientDoubles = kGradientAliasesJacobian ? 0 : kGradientStage;
   static constexpr int kWarps = kEvaluateThreads / 32;
   static constexpr bool kStageJacobian =
       CB200_KERNEL_STAGE_JACOBIAN &&
-      (kPrefetchBytes + kWarps * (kJacobianDoubles + kGradientDoubles) * 8 <= 72 * 1024);
+      (kPrefetchBytes + kWarps * (kJacobianDoubles + kGradientDoubles) * 8 <= SmemBudget(kCtas));
   static constexpr int kGradientOffset =
       (kStageJacobian && !kGradientAliasesJacobian) ? kJacobianDoubles : 0;
   static constexpr int kWarpDoubles =
       kStageJacobian ? kJacobianDoubles + kGradientDoubles : kGradientStage;
   static constexpr int kJetBytes = kPrefetchBytes + kWarps * kWarpDoubles * 8;
-  static constexpr int kCostBytes = kPrefetchBytes > 0 ? kPrefetchBytes : 16;
+  static constexpr int kCostBytes = kPrefetchBytes > 0 ? kPrefetchBytes : 64;
 };
 
-// CTAs per SM the kernel is compiled for.  Measured on B200 for the BAL functor
-// (scripts/kbench.cu): 3 CTAs x 128 threads (168 registers, no spills, 71 KB shared each)
-// equal or beat 4 (128 registers, spills) and 5; wide problems get 2 CTAs (255 registers).
-#ifndef CB200_RESIDENT_CTAS_SMALL
-#define CB200_RESIDENT_CTAS_SMALL 3
-#endif
-#ifndef CB200_RESIDENT_CTAS_COST
-#define CB200_RESIDENT_CTAS_COST 5  // CTAs per SM wanted for the Jet-free variant
-#endif
-__host__ __device__ constexpr int ResidentCtas(int num_residuals, int num_parameters) {
-  return (num_parameters <= 13 && num_residuals <= 3) ? CB200_RESIDENT_CTAS_SMALL : 2;
-}
-
-// One thread evaluates one residual block at a time and walks the type's blocks with a
-// grid stride (persistent CTAs).  Software pipeline per thread:
-//   iteration k:  [state offsets of block k+2 -> registers]
-//                 [cp.async parameters + functor + int tables of block k+1 -> shared]
-//                 [wait for stage k&1] compute block k from shared memory
-// so the two dependent global loads (offset, then the gathered parameters) of a block are
-// in flight during the ~1500 instructions of the previous block instead of stalling the
-// warp (v1 of this kernel: long-scoreboard stalls 7.5 of 15 cycles per issue, FP64 pipe
-// 22% busy; profiles/r1_v1_ncu_summary.txt).
 // The Jet-free cost / residual kernel needs ~80 registers and only the prefetch buffers, so
-// more of its CTAs fit on an SM; it is latency bound (argument reduction of sincos, divisions),
-// and the extra warps hide that: BAL L cost-only 0.97 ms at 3 CTAs per SM.
+// more of its CTAs fit on an SM; it is latency bound (argument reduction of sincos,
+// divisions), and the extra warps hide that.
 __host__ __device__ constexpr int VariantCtas(int variant, int resident, int cost_bytes) {
   if (variant != kVariantCost) return resident;
-  const int by_smem = (200 * 1024) / (cost_bytes + 1024);
+  const int by_smem = (227 * 1024) / (cost_bytes + 1024);
   const int wanted = CB200_RESIDENT_CTAS_COST;
   return by_smem < resident ? resident : (by_smem < wanted ? by_smem : wanted);
 }
 
-template <int kVariant, typename Functor, typename Loss, int kRes, int... Ns>
+// One thread evaluates one residual block at a time and walks the type's blocks with a
+// grid stride (persistent CTAs).  Software pipeline per thread:
+//   iteration k:  [state offsets of block k+1 -> registers]
+//                 [wait for block k's copies] functor of block k from shared memory
+//                 [cp.async parameters + functor (+ int tables) of block k+1 -> shared]
+//                 epilogue of block k (loss, gradient, scatter)
+// so the two dependent global loads (offset, then the gathered parameters) of a block are
+// in flight during the functor and the epilogue of the previous block instead of stalling
+// the warp (v1 of this kernel: long-scoreboard stalls 7.5 of 15 cycles per issue, FP64 pipe
+// 22% busy; profiles/r1_v1_ncu_summary.txt).  a.state must be 16-byte aligned and followed
+// by at least two doubles of slack (the engine's state buffer is).
+template <int kVariant, bool kAffine, typename Functor, typename Loss, int kRes, int... Ns>
 __global__ void __launch_bounds__(
-    kEvaluateThreads, VariantCtas(kVariant, ResidentCtas(kRes, (Ns + ... + 0)),
-                                  SmemPlan<Functor, kRes, Ns...>::kCostBytes))
+    kEvaluateThreads,
+    VariantCtas(kVariant,
+                ResidentCtas(kRes, (Ns + ... + 0), kVariant != kVariantCost && !kAffine),
+                SmemPlan<Functor, false, kRes, Ns...>::kCostBytes))
     EvaluateKernel(const cb200_launch_args a) {
   using Dims = BlockDims<Ns...>;
   using Plan = PassPlan<kRes, Ns...>;
-  using Smem = SmemPlan<Functor, kRes, Ns...>;
   constexpr int kNB = Dims::kNumBlocks;
   constexpr int kNP = Dims::kNumParameters;
   constexpr bool kJets = kVariant != kVariantCost;
   constexpr bool kGeneric = kVariant == kVariantGeneric || kVariant == kVariantGenericAll;
   constexpr bool kAll = kVariant == kVariantPlainAll || kVariant == kVariantGenericAll;
+  static_assert(!kAffine || kAll, "affine tables are for the all-outputs variants");
+  // The int tables ride the cp.async pipeline except where positions are computed (affine)
+  // and in the Jet-free variant (it needs one or two of them: read directly).
+  constexpr bool kInts = kJets && !kAffine;
+  using Smem = SmemPlan<Functor, kInts, kRes, Ns...>;
   const bool out_residuals = kAll || a.output_residuals;
   const bool out_jacobian = kAll || a.output_jacobian;
   const bool out_gradient = kAll || a.output_gradient;
   const bool apply_loss = kAll || a.apply_loss_function;
   const bool crs = kVariant != kVariantPlainAll && a.crs;
-  using Layout = PrefetchLayout<Functor, kNP, kNB, Dims::PitchBefore(kNB)>;
-  constexpr bool kPrefetch = Layout::kFits;
+  constexpr bool kPrefetch = Smem::kFits;
   constexpr bool kStage = kJets && Smem::kStageJacobian;
 
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ double warp_cost[kEvaluateThreads / 32];
   double* const wbuf = reinterpret_cast<double*>(smem + Smem::kPrefetchBytes) +
                        (threadIdx.x >> 5) * Smem::kWarpDoubles;
   double* const jbuf = wbuf;                                              // Jacobian staging
@@ -488,34 +559,71 @@ __global__ void __launch_bounds__(
   const int cta_first = blockIdx.x * kEvaluateThreads;
   const int iterations = cta_first < n ? (n - cta_first + stride - 1) / stride : 0;
 
-  constexpr int kPitchSum = Dims::PitchBefore(kNB);  // cooperative gather: odd pitches
   auto clamp = [&](int rb) { return rb < n ? rb : n - 1; };
+  constexpr int kStages = Smem::kStages;
+  // parameter stage: per-thread rows (gather 1) or one region per warp (gathers 0, 2)
   auto stage_params = [&](int stage) {
-    return reinterpret_cast<double*>(smem + stage * Layout::kStageBytes);
-  };
-  auto stage_ints = [&](int stage) {
-    return reinterpret_cast<int*>(smem + stage * Layout::kStageBytes +
-                                  Layout::kParamBytes * kEvaluateThreads);
+    double* base = reinterpret_cast<double*>(smem + Smem::kParamOffset +
+                                             (kStages > 1 ? stage : 0) * Smem::kParamStageBytes);
+    return CB200_KERNEL_GATHER == 1 ? base + tid * (Smem::kParamBytes / 8)
+                                    : base + (tid >> 5) * 32 * (Smem::kParamBytes / 8);
   };
   auto stage_functor = [&](int stage) {
-    return smem + stage * Layout::kStageBytes +
-           (Layout::kParamBytes + Layout::kIntSlots * 4) * kEvaluateThreads +
-           tid * Layout::kFunctorSlot;
+    return smem + Smem::kFunctorOffset + (kStages > 1 ? stage : 0) * Smem::kFunctorStageBytes +
+           tid * Smem::kFunctorSlot;
+  };
+  auto stage_ints = [&](int stage) {
+    return reinterpret_cast<int*>(smem + Smem::kIntOffset + stage * Smem::kIntStageBytes) + tid;
   };
   auto load_offsets = [&](int rb, int (&soff)[kNB]) {
     const int r = clamp(rb);
 #pragma unroll
     for (int j = 0; j < kNB; ++j) soff[j] = __ldg(a.state_offset + static_cast<size_t>(j) * n + r);
   };
+  // bit j: block j starts at an odd double of the state vector
+  auto parity_of = [&](const int (&soff)[kNB]) {
+    unsigned p = 0;
+#pragma unroll
+    for (int j = 0; j < kNB; ++j) p |= static_cast<unsigned>(soff[j] & 1) << j;
+    return p;
+  };
+  // Issues the copies of residual block rb: its parameter blocks (into this thread's row),
+  // its functor, and — table variants — its integers into int stage `stage`.
   auto prefetch = [&](int stage, int rb, const int (&soff)[kNB]) {
     if constexpr (kPrefetch) {
       double* dst = stage_params(stage);
-      if constexpr (CB200_KERNEL_COOP_GATHER) {
+      if constexpr (CB200_KERNEL_GATHER == 1) {
+        // Every thread copies its own blocks in 16-byte pieces: the aligned window
+        // [start & ~1, ...) of Size/2 + 1 pieces holds the block for either parity of its
+        // start.  The owner reads from (start & 1) on.
+#pragma unroll
+        for (int j = 0; j < kNB; ++j) {
+          const double* __restrict__ src = a.state + (soff[j] & ~1);
+#pragma unroll
+          for (int c = 0; c < Dims::WindowChunks(j); ++c)
+            CpAsync16(dst + 2 * (Dims::ChunksBefore(j) + c), src + 2 * c);
+        }
+      } else if constexpr (CB200_KERNEL_GATHER == 2) {
+        // The warp copies the 32 windows of argument j as one stream of 32 * W 16-byte
+        // pieces (W = Size/2 + 1): consecutive lanes fetch consecutive pieces of a window,
+        // so a copy instruction touches a handful of cache lines instead of 32, and its
+        // 512 bytes land contiguously in shared memory ([argument][lane][W pieces]).
+#pragma unroll
+        for (int j = 0; j < kNB; ++j) {
+          const int kW = Dims::WindowChunks(j);  // constant after unrolling
+#pragma unroll
+          for (int it = 0; it < kW; ++it) {
+            const int e = it * 32 + lane;
+            const int owner = e / kW;
+            const int c = e - owner * kW;
+            const int so = __shfl_sync(0xffffffffu, soff[j], owner);
+            CpAsync16(dst + 2 * (32 * Dims::ChunksBefore(j) + e), a.state + ((so & ~1) + 2 * c));
+          }
+        }
+      } else {
         // The warp copies its 32 blocks of argument j as one stream of 32 * Size(j)
-        // doubles: consecutive lanes fetch consecutive doubles of a block, so a copy
-        // instruction touches ~Size(j)*8*32/32 sectors instead of 32 (one per lane).
-        // Shared layout per warp: [argument][lane][pitch], pitch odd.
-        double* wdst = dst + (tid >> 5) * 32 * kPitchSum;
+        // doubles: consecutive lanes fetch consecutive doubles of a block.  Shared layout
+        // per warp: [argument][lane][pitch], pitch odd (conflict free for the owner).
 #pragma unroll
         for (int j = 0; j < kNB; ++j) {
           const int kS = Dims::Size(j);  // constants after unrolling
@@ -526,59 +634,49 @@ __global__ void __launch_bounds__(
             const int owner = e / kS;
             const int i = e - owner * kS;
             const int so = __shfl_sync(0xffffffffu, soff[j], owner);
-            CpAsync8(wdst + 32 * Dims::PitchBefore(j) + (kP == kS ? e : owner * kP + i),
+            CpAsync8(dst + 32 * Dims::PitchBefore(j) + (kP == kS ? e : owner * kP + i),
                      a.state + (so + i));
           }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < kNB; ++j) {
-          const double* __restrict__ src = a.state + soff[j];
-#pragma unroll
-          for (int i = 0; i < Dims::Size(j); ++i)
-            CpAsync8(dst + (Dims::Offset(j) + i) * kEvaluateThreads + tid, src + i);
         }
       }
       // The int tables of the block (consumed in the epilogue, from shared memory, so
       // no register is held across the functor).
-      if constexpr (CB200_KERNEL_INTS_IN_SMEM) {
+      if constexpr (kInts) {
         const int r = clamp(rb);
-        int* idst = stage_ints(stage) + tid;
-        if constexpr (kJets) {
+        int* idst = stage_ints(stage);
 #pragma unroll
-          for (int j = 0; j < kNB; ++j) {
-            const int32_t* tab = kGeneric ? a.parameter_block : a.delta_offset;
-            CpAsync4(idst + (Layout::kSlotDelta + j) * kEvaluateThreads,
-                     tab + static_cast<size_t>(j) * n + r);
-            if (out_jacobian)
-              CpAsync4(idst + (Layout::kSlotJpos + j) * kEvaluateThreads,
-                       a.jacobian_pos + static_cast<size_t>(j) * n + r);
-          }
-          if (crs && out_jacobian)
-            CpAsync4(idst + Layout::kSlotRowStride * kEvaluateThreads, a.jacobian_row_stride + r);
+        for (int j = 0; j < kNB; ++j) {
+          const int32_t* tab = kGeneric ? a.parameter_block : a.delta_offset;
+          CpAsync4(idst + (Smem::kSlotDelta + j) * kEvaluateThreads,
+                   tab + static_cast<size_t>(j) * n + r);
+          if (out_jacobian)
+            CpAsync4(idst + (Smem::kSlotJpos + j) * kEvaluateThreads,
+                     a.jacobian_pos + static_cast<size_t>(j) * n + r);
         }
+        if (crs && out_jacobian)
+          CpAsync4(idst + Smem::kSlotRowStride * kEvaluateThreads, a.jacobian_row_stride + r);
         if (out_residuals)
-          CpAsync4(idst + Layout::kSlotResidual * kEvaluateThreads, a.residual_pos + r);
+          CpAsync4(idst + Smem::kSlotResidual * kEvaluateThreads, a.residual_pos + r);
         if (a.loss_index)
-          CpAsync4(idst + Layout::kSlotLoss * kEvaluateThreads, a.loss_index + r);
+          CpAsync4(idst + Smem::kSlotLoss * kEvaluateThreads, a.loss_index + r);
       }
-      if constexpr (Layout::kFunctorInSmem) {
+      if constexpr (Smem::kFunctorInSmem) {
         const unsigned char* src = static_cast<const unsigned char*>(a.functors) +
                                    static_cast<size_t>(clamp(rb)) * sizeof(Functor);
-        unsigned char* fdst = stage_functor(stage);
+        unsigned char* my_functor = stage_functor(stage);
         if constexpr (sizeof(Functor) % 16 == 0) {
 #pragma unroll
-          for (int b = 0; b < static_cast<int>(sizeof(Functor)); b += 16) CpAsync16(fdst + b, src + b);
+          for (int b = 0; b < static_cast<int>(sizeof(Functor)); b += 16) CpAsync16(my_functor + b, src + b);
         } else if constexpr (sizeof(Functor) % 8 == 0) {
 #pragma unroll
-          for (int b = 0; b < static_cast<int>(sizeof(Functor)); b += 8) CpAsync8(fdst + b, src + b);
+          for (int b = 0; b < static_cast<int>(sizeof(Functor)); b += 8) CpAsync8(my_functor + b, src + b);
         } else {
 #pragma unroll
-          for (int b = 0; b < static_cast<int>(sizeof(Functor)); b += 4) CpAsync4(fdst + b, src + b);
+          for (int b = 0; b < static_cast<int>(sizeof(Functor)); b += 4) CpAsync4(my_functor + b, src + b);
         }
       }
+      CpAsyncCommit();
     }
-    CpAsyncCommit();
   };
 
   double cost_sum = 0.0;
@@ -589,6 +687,7 @@ __global__ void __launch_bounds__(
   int soff_cur[kNB];    // state offsets of the block being computed (fallback path)
   load_offsets(first, soff_cur);
   prefetch(0, first, soff_cur);
+  unsigned parity_cur = parity_of(soff_cur);
   load_offsets(first + stride, soff_next);
 
   for (int k = 0; k < iterations; ++k) {
@@ -596,22 +695,39 @@ __global__ void __launch_bounds__(
     const bool valid = rb < n;
     const int tt = clamp(rb);
     const int stage = k & 1;
+    // first residual block of this warp: affine positions of a whole warp derive from it
+    const int warp_rb = rb - lane;
+    const bool warp_valid = warp_rb + 31 < n;
 
-    // Issue the next block's copies, then fetch the offsets of the one after.
+    // The offsets of the next block arrive while this one is computed; its copies are
+    // issued after the last functor call below.
     int soff_issue[kNB];
 #pragma unroll
     for (int j = 0; j < kNB; ++j) soff_issue[j] = soff_next[j];
-    prefetch(stage ^ 1, rb + stride, soff_issue);
+    const unsigned parity_issue = parity_of(soff_issue);
     load_offsets(rb + 2 * stride, soff_next);
+    bool issued = false;
+    auto issue_next = [&]() {
+      if (!issued) {
+        // (cooperative gathers overwrite rows other lanes read: the warp must be past them)
+        if constexpr (kPrefetch && kStages == 1 && CB200_KERNEL_GATHER != 1) __syncwarp();
+        prefetch(stage ^ 1, rb + stride, soff_issue);
+      }
+      issued = true;
+    };
+    if constexpr (kStages > 1) issue_next();
 
-    CpAsyncWait<1>();  // this thread's copies for `stage` have landed
-    if constexpr (kPrefetch && CB200_KERNEL_COOP_GATHER) __syncwarp();  // ... and its warp's
+    if constexpr (kPrefetch) {
+      // this thread's copies for block k have landed ...
+      if constexpr (kStages > 1) CpAsyncWait<1>(); else CpAsyncWait<0>();
+      if constexpr (CB200_KERNEL_GATHER != 1) __syncwarp();  // ... and its warp's
+    }
 
-    // Per-block int tables: from the prefetched stage (or straight from global memory
-    // when the parameters do not fit in shared memory).
-    const int* sints = stage_ints(stage) + tid;
+    // Per-block int tables: from the prefetched stage, computed (affine), or straight
+    // from global memory (Jet-free variant; parameters too large for shared memory).
+    const int* sints = stage_ints(stage);
     auto table = [&](int slot, const int32_t* global_table, size_t index) -> int {
-      if constexpr (kPrefetch && CB200_KERNEL_INTS_IN_SMEM) {
+      if constexpr (kPrefetch && kInts) {
         return sints[slot * kEvaluateThreads];
       } else {
         return __ldg(global_table + index);
@@ -625,7 +741,8 @@ __global__ void __launch_bounds__(
       for (int j = 0; j < kNB; ++j) {
         const size_t at = static_cast<size_t>(j) * n + tt;
         if constexpr (kGeneric) {
-          const int id = table(Layout::kSlotDelta + j, a.parameter_block, at);
+          const int id = kAffine ? __ldg(a.parameter_block + at)
+                                 : table(Smem::kSlotDelta + j, a.parameter_block, at);
           const int4* rec = reinterpret_cast<const int4*>(a.parameter_block_table) + 2 * id;
           const int4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
           delta_off[j] = r0.y;
@@ -635,38 +752,51 @@ __global__ void __launch_bounds__(
           plus_off[j] = r1.y;
           key[j] = id;
         } else {
-          delta_off[j] = table(Layout::kSlotDelta + j, a.delta_offset, at);
+          // affine plain types have delta offset == state offset (cb200_launch_args::affine)
+          delta_off[j] = kAffine ? 0 : table(Smem::kSlotDelta + j, a.delta_offset, at);
           tangent[j] = Dims::Size(j);
           kind[j] = CB200_MANIFOLD_NONE;
           mparam[j] = 0;
           plus_off[j] = -1;
           key[j] = delta_off[j];
         }
-        jpos[j] = out_jacobian ? table(Layout::kSlotJpos + j, a.jacobian_pos, at) : 0;
+        if constexpr (kAffine) {
+          jpos[j] = a.jacobian_base[j] + tt * a.jacobian_step[j];
+        } else {
+          jpos[j] = out_jacobian ? table(Smem::kSlotJpos + j, a.jacobian_pos, at) : 0;
+        }
       }
     }
-    const int respos = out_residuals ? table(Layout::kSlotResidual, a.residual_pos, tt) : 0;
+    int respos = 0;
+    if (out_residuals)
+      respos = kAffine ? a.residual_base + tt * kRes : table(Smem::kSlotResidual, a.residual_pos, tt);
     int row_stride_crs = 0;
     if constexpr (kJets) {
       if (crs && out_jacobian)
-        row_stride_crs = table(Layout::kSlotRowStride, a.jacobian_row_stride, tt);
+        row_stride_crs =
+            kAffine ? a.row_stride : table(Smem::kSlotRowStride, a.jacobian_row_stride, tt);
     }
     const Loss* __restrict__ losses = static_cast<const Loss*>(a.loss_table);
-    const Loss& loss = losses[a.loss_index ? table(Layout::kSlotLoss, a.loss_index, tt) : 0];
+    int loss_at = 0;
+    if (a.loss_index)
+      loss_at = kAffine ? __ldg(a.loss_index + tt) : table(Smem::kSlotLoss, a.loss_index, tt);
+    const Loss& loss = losses[loss_at];
 
     const double* sp = stage_params(stage);
     auto param = [&](int j, int i) -> double {
-      if constexpr (kPrefetch && CB200_KERNEL_COOP_GATHER) {
-        return sp[(tid >> 5) * 32 * kPitchSum + 32 * Dims::PitchBefore(j) +
-                  lane * (Dims::Size(j) | 1) + i];
+      if constexpr (kPrefetch && CB200_KERNEL_GATHER == 1) {
+        return sp[2 * Dims::ChunksBefore(j) + ((parity_cur >> j) & 1) + i];
+      } else if constexpr (kPrefetch && CB200_KERNEL_GATHER == 2) {
+        return sp[2 * (32 * Dims::ChunksBefore(j) + lane * Dims::WindowChunks(j)) +
+                  ((parity_cur >> j) & 1) + i];
       } else if constexpr (kPrefetch) {
-        return sp[(Dims::Offset(j) + i) * kEvaluateThreads + tid];
+        return sp[32 * Dims::PitchBefore(j) + lane * (Dims::Size(j) | 1) + i];
       } else {
         return __ldg(a.state + soff_cur[j] + i);
       }
     };
     const Functor* functor_ptr;
-    if constexpr (kPrefetch && Layout::kFunctorInSmem) {
+    if constexpr (kPrefetch && Smem::kFunctorInSmem) {
       functor_ptr = reinterpret_cast<const Functor*>(stage_functor(stage));
     } else {
       functor_ptr = static_cast<const Functor*>(a.functors) + tt;
@@ -689,6 +819,7 @@ __global__ void __launch_bounds__(
 #pragma unroll
       for (int r = 0; r < kRes; ++r) res[r] = kNaN;  // unwritten outputs stay invalid
       ok = CallFunctor<Dims>(functor, xval, res, std::make_index_sequence<kNB>{});
+      issue_next();
       FiniteCheck check;
 #pragma unroll
       for (int r = 0; r < kRes; ++r) check.Add(res[r]);
@@ -731,12 +862,21 @@ __global__ void __launch_bounds__(
           if (!crs) {
 #pragma unroll
             for (int j = 0; j < kNB; ++j) {
-              const int t0 = __shfl_sync(0xffffffffu, tangent[j], 0);
-              const int base = __shfl_sync(0xffffffffu, jpos[j], 0);
-              const bool mine = valid && delta_off[j] >= 0 && tangent[j] == t0 &&
-                                jpos[j] == base + lane * kRes * t0;
-              bulk_arg[j] = __all_sync(0xffffffffu, mine) && ((base & 1) == 0);
-              bulk_base[j] = base;
+              if constexpr (kAffine && !kGeneric) {
+                // positions are an arithmetic progression: contiguity is a property of
+                // the type, only the evenness of the warp's first cell varies
+                const int base = a.jacobian_base[j] + warp_rb * a.jacobian_step[j];
+                bulk_arg[j] = warp_valid && a.jacobian_step[j] == kRes * Dims::Size(j) &&
+                              ((base & 1) == 0);
+                bulk_base[j] = base;
+              } else {
+                const int t0 = __shfl_sync(0xffffffffu, tangent[j], 0);
+                const int base = __shfl_sync(0xffffffffu, jpos[j], 0);
+                const bool mine = valid && delta_off[j] >= 0 && tangent[j] == t0 &&
+                                  jpos[j] == base + lane * kRes * t0;
+                bulk_arg[j] = __all_sync(0xffffffffu, mine) && ((base & 1) == 0);
+                bulk_base[j] = base;
+              }
             }
           } else {
             int lo = 0x7fffffff;
@@ -779,6 +919,9 @@ __global__ void __launch_bounds__(
 #pragma unroll
         for (int r = 0; r < kRes; ++r) out[r] = JetT::Filled(kNaN, kNaN);
         ok = CallFunctor<Dims>(functor, x, out, std::make_index_sequence<kNB>{}) && ok;
+        // Parameters and functor of this block are consumed (the last pass re-reads
+        // neither): their rows take the next block's copies.
+        if constexpr (p == Plan::kNumPasses - 1) issue_next();
 
         FiniteCheck check;
 #pragma unroll
@@ -839,17 +982,17 @@ __global__ void __launch_bounds__(
           if constexpr (j >= kFirst && j < kEnd) {
             constexpr int kSize = Dims::Size(j);
             constexpr int kLane0 = Plan::Lane(j, 0);
-            constexpr unsigned kAll = kSize >= 32 ? 0xffffffffu : ((1u << kSize) - 1u);
+            constexpr unsigned kAllLive = kSize >= 32 ? 0xffffffffu : ((1u << kSize) - 1u);
             const bool active = kGeneric ? delta_off[j] >= 0 : true;
             double B[kRes][kSize];
 #pragma unroll
             for (int r = 0; r < kRes; ++r)
 #pragma unroll
               for (int c = 0; c < kSize; ++c) B[r][c] = out[r].v[kLane0 + c];
-            unsigned lv = kAll;
+            unsigned lv = kAllLive;
             if constexpr (kGeneric) {
               if (kind[j] == CB200_MANIFOLD_SUBSET) {
-                lv = kAll & ~static_cast<unsigned>(mparam[j]);  // column selection
+                lv = kAllLive & ~static_cast<unsigned>(mparam[j]);  // column selection
               } else if (kind[j] == CB200_MANIFOLD_QUATERNION_TAIL ||
                          kind[j] == CB200_MANIFOLD_EIGEN_QUATERNION_TAIL) {
                 if constexpr (kSize >= 4) {
@@ -873,7 +1016,7 @@ __global__ void __launch_bounds__(
 #pragma unroll
                     for (int c = 3; c + 1 < kSize; ++c) B[r][c] = B[r][c + 1];
                   }
-                  lv = kAll >> 1;
+                  lv = kAllLive >> 1;
                 }
               } else if (kind[j] == CB200_MANIFOLD_GENERIC && active) {
                 BlockEpilogue<kRes, kSize>::MultiplyPlusJacobian(
@@ -896,9 +1039,13 @@ __global__ void __launch_bounds__(
           if constexpr (j >= kFirst && j < kEnd) {
             constexpr int kSize = Dims::Size(j);
             constexpr int kLane0 = Plan::Lane(j, 0);
-            constexpr unsigned kAll = kSize >= 32 ? 0xffffffffu : ((1u << kSize) - 1u);
+            constexpr unsigned kAllLive = kSize >= 32 ? 0xffffffffu : ((1u << kSize) - 1u);
             const bool active = kGeneric ? delta_off[j] >= 0 : true;
-            const unsigned lv = kGeneric ? live[j] : kAll;
+            const unsigned lv = kGeneric ? live[j] : kAllLive;
+            // affine plain types: the gradient offset is the state offset, still in the
+            // registers that fetched this block's parameters
+            const int doff = (kAffine && !kGeneric) ? soff_cur[j] : delta_off[j];
+            const int run_key = (kAffine && !kGeneric) ? doff : key[j];
             double g[kSize];
 #pragma unroll
             for (int c = 0; c < kSize; ++c) {
@@ -912,18 +1059,21 @@ __global__ void __launch_bounds__(
             // to memory.  Short runs (the 3-10 observations of a BAL point) go out
             // directly: lanes of one red instruction that hit the same sector share one
             // L2 request, which is cheaper than 5 shuffle steps per value.
-            const int k_ = (valid && active) ? key[j] : -1 - lane;
-            const int prev_key = __shfl_up_sync(0xffffffffu, k_, 1);
-            bool head = (lane == 0) || (prev_key != k_);
-            const unsigned heads = __ballot_sync(0xffffffffu, head);
-            if (__popc(heads) <= 4) {
+            bool head = true;
+            if constexpr (CB200_KERNEL_SEGMENTED_GRADIENT) {
+              const int k_ = (valid && active) ? run_key : -1 - lane;
+              const int prev_key = __shfl_up_sync(0xffffffffu, k_, 1);
+              head = (lane == 0) || (prev_key != k_);
+              const unsigned heads = __ballot_sync(0xffffffffu, head);
+              if (__popc(heads) <= 4) {
 #pragma unroll
-              for (int c = 0; c < kSize; ++c) g[c] = (valid && ok && active) ? g[c] : 0.0;
-              const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
-              const int run_end = above ? __ffs(above) - 1 : 32;
-              WarpSegmentedSum<kSize>(run_end, g, lane);
-            } else {
-              head = true;  // every lane adds its own contribution
+                for (int c = 0; c < kSize; ++c) g[c] = (valid && ok && active) ? g[c] : 0.0;
+                const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+                const int run_end = above ? __ffs(above) - 1 : 32;
+                WarpSegmentedSum<kSize>(run_end, g, lane);
+              } else {
+                head = true;  // every lane adds its own contribution
+              }
             }
             const bool emit = head && valid && ok && active;
             const unsigned emit_mask = __ballot_sync(0xffffffffu, emit);
@@ -937,9 +1087,8 @@ __global__ void __launch_bounds__(
               for (int c = 0; c < kSize; ++c) gbuf[lane * kPitch + c] = g[c];
               // destination of every lane's sums (or -1) and, with manifolds, its live
               // columns: the reduction rounds read them back by row, so a round is two
-              // shared loads, an address and one predicated red (v7 fetched them with
-              // shuffles inside a divergent branch: 19 instructions a round, now 9)
-              obuf[lane] = emit ? delta_off[j] : -1;
+              // shared loads, an address and one predicated red
+              obuf[lane] = emit ? doff : -1;
               if constexpr (kGeneric) obuf[32 + lane] = static_cast<int>(lv);
               __syncwarp();
               if (!kGeneric && emit_mask == 0xffffffffu) {
@@ -970,7 +1119,7 @@ __global__ void __launch_bounds__(
               }
               __syncwarp();
             } else if (emit) {
-              double* __restrict__ dst = a.gradient + delta_off[j];
+              double* __restrict__ dst = a.gradient + doff;
 #pragma unroll
               for (int c = 0; c < kSize; ++c)
                 if (!kGeneric || ((lv >> c) & 1u))
@@ -984,9 +1133,9 @@ __global__ void __launch_bounds__(
           if constexpr (j >= kFirst && j < kEnd) {
             constexpr int kSize = Dims::Size(j);
             constexpr int kLane0 = Plan::Lane(j, 0);
-            constexpr unsigned kAll = kSize >= 32 ? 0xffffffffu : ((1u << kSize) - 1u);
+            constexpr unsigned kAllLive = kSize >= 32 ? 0xffffffffu : ((1u << kSize) - 1u);
             const bool active = kGeneric ? delta_off[j] >= 0 : true;
-            const unsigned lv = kGeneric ? live[j] : kAll;
+            const unsigned lv = kGeneric ? live[j] : kAllLive;
             auto dcol = [&](int c) -> int { return kGeneric ? __popc(lv & ((1u << c) - 1u)) : c; };
             auto is_live = [&](int c) -> bool { return kGeneric ? ((lv >> c) & 1u) : true; };
             const int tan = kGeneric ? tangent[j] : kSize;
@@ -1007,14 +1156,6 @@ __global__ void __launch_bounds__(
 #pragma unroll
                   for (int c = 0; c < kSize; ++c)
                     if (is_live(c)) cell[r * row_stride + dcol(c)] = out[r].v[kLane0 + c];
-              }
-              if (bulk_arg[j]) {
-                FenceProxyAsyncShared();
-                __syncwarp();
-                if (lane == 0)
-                  BulkStore(a.jacobian_values + bulk_base[j],
-                            jbuf + 32 * kRes * Dims::Offset(j), 32 * kRes * tan * 8);
-                bulk_issued = true;
               }
             } else if (valid && active) {
               double* __restrict__ dst = a.jacobian_values + jpos[j];
@@ -1039,7 +1180,29 @@ __global__ void __launch_bounds__(
         if (out_jacobian || out_gradient) {
           ForEachBlock(prepare, std::make_index_sequence<kNB>{});
           if (out_gradient) ForEachBlock(gradient, std::make_index_sequence<kNB>{});
-          if (out_jacobian) ForEachBlock(scatter, std::make_index_sequence<kNB>{});
+          if (out_jacobian) {
+            ForEachBlock(scatter, std::make_index_sequence<kNB>{});
+            if constexpr (kStage) {
+              // One proxy fence for all the cells staged in this pass, then one bulk store
+              // per argument (the fence costs ~2 % of the kernel each time it runs).
+              bool any = false;
+#pragma unroll
+              for (int j = kFirst; j < kEnd; ++j) any = any || bulk_arg[j];
+              if (any) {
+                FenceProxyAsyncShared();
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                  for (int j = kFirst; j < kEnd; ++j)
+                    if (bulk_arg[j])
+                      BulkStore(a.jacobian_values + bulk_base[j],
+                                jbuf + 32 * kRes * Dims::Offset(j),
+                                32 * kRes * (kGeneric ? tangent[j] : Dims::Size(j)) * 8);
+                }
+                bulk_issued = true;
+              }
+            }
+          }
         }
       };
       ForEachBlock(pass, std::make_index_sequence<Plan::kNumPasses>{});
@@ -1077,12 +1240,11 @@ __global__ void __launch_bounds__(
         }
       }
     }
-    if constexpr (!kPrefetch) {
-      // Fallback (parameters too large for shared memory): next block's offsets.
-      load_offsets(rb + stride, soff_cur);
-    }
+#pragma unroll
+    for (int j = 0; j < kNB; ++j) soff_cur[j] = soff_issue[j];
+    parity_cur = parity_issue;
   }
-  CpAsyncWait<0>();
+  if constexpr (kPrefetch) CpAsyncWait<0>();
   if (bulk_pending && lane == 0) BulkWaitAll();
 
   if (!all_ok) *a.status = 1;
@@ -1092,6 +1254,8 @@ __global__ void __launch_bounds__(
   double c = cost_sum;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
+  __syncthreads();  // every warp is done with the prefetch buffers: reuse their first bytes
+  double* const warp_cost = reinterpret_cast<double*>(smem);
   if (lane == 0) warp_cost[tid >> 5] = c;
   __syncthreads();
   if (tid == 0) {
@@ -1104,64 +1268,66 @@ __global__ void __launch_bounds__(
   }
 }
 
-// The launch thunk whose address goes through the C ABI.
-template <typename Functor, typename Loss, int kRes, int... Ns>
-int LaunchEvaluate(const cb200_launch_args* args, void* stream) {
-  if (args->n <= 0) return 0;
-  static int persistent_ctas = 0;
-  if (persistent_ctas == 0) {
-    int device = 0, sms = 0;
-    cudaGetDevice(&device);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    persistent_ctas = (sms > 0 ? sms : 148) * ResidentCtas(kRes, (Ns + ... + 0));
-  }
-  using Smem = SmemPlan<Functor, kRes, Ns...>;
-  const bool cost_only = !(args->output_jacobian || args->output_gradient);
-  constexpr int kJetCtas = ResidentCtas(kRes, (Ns + ... + 0));
-  const int wanted =
-      cost_only ? persistent_ctas / kJetCtas * VariantCtas(kVariantCost, kJetCtas, Smem::kCostBytes)
-                : persistent_ctas;
+// The launch thunk whose address goes through the C ABI.  Nothing is cached per process:
+// the opt-in to large dynamic shared memory is a per-device function attribute and an
+// application may run engines on several devices (Solver::Options::cuda_device), so it is
+// set for the kernel being launched on the current device every time (~1 us).
+template <typename Kernel>
+int LaunchVariant(Kernel kernel, int wanted_ctas_per_sm, int smem_bytes,
+                  const cb200_launch_args* args, cudaStream_t s) {
+  int device = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const int wanted = (sms > 0 ? sms : 148) * wanted_ctas_per_sm;
   const int needed = (args->n + kEvaluateThreads - 1) / kEvaluateThreads;
   int grid = needed < wanted ? needed : wanted;
   if (grid > args->cost_partial_count) grid = args->cost_partial_count;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(EvaluateKernel<kVariantCost, Functor, Loss, kRes, Ns...>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kCostBytes);
-    cudaFuncSetAttribute(EvaluateKernel<kVariantPlain, Functor, Loss, kRes, Ns...>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kJetBytes);
-    cudaFuncSetAttribute(EvaluateKernel<kVariantGeneric, Functor, Loss, kRes, Ns...>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kJetBytes);
-#if CB200_KERNEL_SPECIALISE_ALL_OUTPUTS
-    cudaFuncSetAttribute(EvaluateKernel<kVariantPlainAll, Functor, Loss, kRes, Ns...>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kJetBytes);
-    cudaFuncSetAttribute(EvaluateKernel<kVariantGenericAll, Functor, Loss, kRes, Ns...>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kJetBytes);
-#endif
-    configured = true;
-  }
-  if (cost_only) {
-    EvaluateKernel<kVariantCost, Functor, Loss, kRes, Ns...>
-        <<<grid, kEvaluateThreads, Smem::kCostBytes, s>>>(*args);
-#if CB200_KERNEL_SPECIALISE_ALL_OUTPUTS
-  } else if (args->plain && args->output_residuals && args->output_jacobian &&
-             args->output_gradient && args->apply_loss_function && !args->crs) {
-    EvaluateKernel<kVariantPlainAll, Functor, Loss, kRes, Ns...>
-        <<<grid, kEvaluateThreads, Smem::kJetBytes, s>>>(*args);
-  } else if (!args->plain && args->output_residuals && args->output_jacobian &&
-             args->output_gradient && args->apply_loss_function) {
-    EvaluateKernel<kVariantGenericAll, Functor, Loss, kRes, Ns...>
-        <<<grid, kEvaluateThreads, Smem::kJetBytes, s>>>(*args);
-#endif
-  } else if (args->plain) {
-    EvaluateKernel<kVariantPlain, Functor, Loss, kRes, Ns...>
-        <<<grid, kEvaluateThreads, Smem::kJetBytes, s>>>(*args);
-  } else {
-    EvaluateKernel<kVariantGeneric, Functor, Loss, kRes, Ns...>
-        <<<grid, kEvaluateThreads, Smem::kJetBytes, s>>>(*args);
-  }
+  kernel<<<grid, kEvaluateThreads, smem_bytes, s>>>(*args);
   return static_cast<int>(cudaGetLastError());
+}
+
+template <typename Functor, typename Loss, int kRes, int... Ns>
+int LaunchEvaluate(const cb200_launch_args* args, void* stream) {
+  if (args->n <= 0) return 0;
+  using Tables = SmemPlan<Functor, true, kRes, Ns...>;    // int tables in shared memory
+  using Computed = SmemPlan<Functor, false, kRes, Ns...>; // affine / Jet-free: none
+  constexpr int kJetCtas = ResidentCtas(kRes, (Ns + ... + 0), true);      // table variants
+  constexpr int kAffineCtas = ResidentCtas(kRes, (Ns + ... + 0), false);  // affine variants
+  constexpr int kCostCtas = VariantCtas(kVariantCost, kAffineCtas, Computed::kCostBytes);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool all = args->output_residuals && args->output_jacobian && args->output_gradient &&
+                   args->apply_loss_function;
+  constexpr unsigned kAffinePlain =
+      CB200_AFFINE_RESIDUAL | CB200_AFFINE_JACOBIAN | CB200_AFFINE_DELTA_IS_STATE;
+  constexpr unsigned kAffineGeneric = CB200_AFFINE_RESIDUAL | CB200_AFFINE_JACOBIAN;
+  if (!(args->output_jacobian || args->output_gradient)) {
+    return LaunchVariant(EvaluateKernel<kVariantCost, false, Functor, Loss, kRes, Ns...>, kCostCtas,
+                         Computed::kCostBytes, args, s);
+  }
+#if CB200_KERNEL_SPECIALISE_ALL_OUTPUTS
+  if (all && args->plain && !args->crs) {
+    if ((args->affine & kAffinePlain) == kAffinePlain)
+      return LaunchVariant(EvaluateKernel<kVariantPlainAll, true, Functor, Loss, kRes, Ns...>,
+                           kAffineCtas, Computed::kJetBytes, args, s);
+    return LaunchVariant(EvaluateKernel<kVariantPlainAll, false, Functor, Loss, kRes, Ns...>,
+                         kJetCtas, Tables::kJetBytes, args, s);
+  }
+  if (all && !args->plain) {
+    if ((args->affine & kAffineGeneric) == kAffineGeneric)
+      return LaunchVariant(EvaluateKernel<kVariantGenericAll, true, Functor, Loss, kRes, Ns...>,
+                           kAffineCtas, Computed::kJetBytes, args, s);
+    return LaunchVariant(EvaluateKernel<kVariantGenericAll, false, Functor, Loss, kRes, Ns...>,
+                         kJetCtas, Tables::kJetBytes, args, s);
+  }
+#endif
+  if (args->plain)
+    return LaunchVariant(EvaluateKernel<kVariantPlain, false, Functor, Loss, kRes, Ns...>, kJetCtas,
+                         Tables::kJetBytes, args, s);
+  return LaunchVariant(EvaluateKernel<kVariantGeneric, false, Functor, Loss, kRes, Ns...>, kJetCtas,
+                       Tables::kJetBytes, args, s);
 }
 
 template <typename Functor, typename Loss, int kRes, int... Ns>

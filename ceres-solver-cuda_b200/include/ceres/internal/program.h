@@ -91,6 +91,8 @@ class ProblemImpl {
 
   ParameterBlock* AddParameterBlock(double* values, int size, Manifold* manifold = nullptr);
   ParameterBlock* FindParameterBlock(const double* values) const;
+  // Aborts with the reference's message when the block was never added.
+  ParameterBlock* FindParameterBlockOrDie(const double* values, const char* what) const;
   void SetManifold(double* values, Manifold* manifold);
   void SetParameterBlockConstant(const double* values);
   void SetParameterBlockVariable(double* values);

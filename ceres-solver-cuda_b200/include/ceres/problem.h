@@ -33,11 +33,11 @@ class Problem {
   }
   void SetParameterBlockVariable(double* values) { impl_->SetParameterBlockVariable(values); }
   bool IsParameterBlockConstant(const double* values) const {
-    return impl_->FindParameterBlock(values)->IsConstant();
+    return impl_->FindParameterBlockOrDie(values, "it can be queried if it is constant")->IsConstant();
   }
   void SetManifold(double* values, Manifold* manifold) { impl_->SetManifold(values, manifold); }
   const Manifold* GetManifold(const double* values) const {
-    return impl_->FindParameterBlock(values)->manifold;
+    return impl_->FindParameterBlockOrDie(values, "you can get its manifold")->manifold;
   }
   bool HasManifold(const double* values) const { return GetManifold(values) != nullptr; }
   void SetParameterLowerBound(double* values, int index, double bound) {
@@ -57,10 +57,10 @@ class Problem {
   int NumResidualBlocks() const { return impl_->NumResidualBlocks(); }
   int NumResiduals() const { return impl_->NumResiduals(); }
   int ParameterBlockSize(const double* values) const {
-    return impl_->FindParameterBlock(values)->size;
+    return impl_->FindParameterBlockOrDie(values, "you can get its size")->size;
   }
   int ParameterBlockTangentSize(const double* values) const {
-    return impl_->FindParameterBlock(values)->TangentSize();
+    return impl_->FindParameterBlockOrDie(values, "you can get its tangent size")->TangentSize();
   }
   bool HasParameterBlock(const double* values) const {
     return impl_->FindParameterBlock(values) != nullptr;

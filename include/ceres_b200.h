@@ -100,14 +100,31 @@ typedef struct cb200_launch_args {
                                       plus_jacobian_offset, 0, 0; constant blocks have
                                       delta_offset -1 and state_offset already shifted past the
                                       active state */
-  const double* state;            /* [num_parameters | constant state] */
+  const double* state;            /* [num_parameters | constant state]; 16-byte aligned and
+                                     followed by >= 2 doubles of slack (the kernel gathers
+                                     parameter blocks in aligned 16-byte pieces) */
   const double* plus_jacobians;
   double* residuals;
   double* jacobian_values;
   double* gradient;
   double* cost_partials;          /* one per thread block of this launch */
   int32_t* status;                /* set non-zero when a functor fails / yields a non-finite value */
+  /* Tables that are arithmetic progressions need not be read (found by cb200_engine_finalize;
+   * typical of a single residual-block type laid out in program order, e.g. bundle adjustment):
+   *   CB200_AFFINE_RESIDUAL        residual_pos[t] == residual_base + t * num_residuals
+   *   CB200_AFFINE_JACOBIAN        jacobian_pos[j][t] == jacobian_base[j] + t * jacobian_step[j] for
+   *                                every argument (none constant), and jacobian_row_stride[t] ==
+   *                                row_stride for the compressed-row layout
+   *   CB200_AFFINE_DELTA_IS_STATE  delta_offset[j][t] == state_offset[j][t] */
+  uint32_t affine;
+  int32_t residual_base;
+  int32_t row_stride;
+  int32_t jacobian_base[CB200_MAX_PARAMETER_BLOCKS];
+  int32_t jacobian_step[CB200_MAX_PARAMETER_BLOCKS];
 } cb200_launch_args;
+#define CB200_AFFINE_RESIDUAL 1u
+#define CB200_AFFINE_JACOBIAN 2u
+#define CB200_AFFINE_DELTA_IS_STATE 4u
 
 /* Launch thunk: the single symbol compiled in the user's translation unit per
  * <CostFunctor, LossFunctionCUDA, kNumResiduals, Ns...>.  Replaces

@@ -4,6 +4,7 @@
 // times with different -DCB200_KERNEL_* settings to A/B kernel variants on the GPU.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Iinclude \
 //        -Iceres-solver-cuda_b200/include -Iceres-solver-cuda_b200/examples scripts/kbench.cu
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -72,7 +73,14 @@ int main(int argc, char** argv) {
   cb200_launch_args a{};
   a.n = n; a.output_residuals = 1; a.output_jacobian = want_j; a.output_gradient = want_g;
   a.apply_loss_function = 1; a.crs = 0; a.plain = 1;
-  const int grid_max = (n + 127) / 128;
+  const int affine = argc > 7 ? std::atoi(argv[7]) : 1;
+  if (affine) {
+    a.affine = CB200_AFFINE_RESIDUAL | CB200_AFFINE_JACOBIAN | CB200_AFFINE_DELTA_IS_STATE;
+    a.residual_base = 0; a.row_stride = 9;
+    a.jacobian_base[0] = 6 * n; a.jacobian_step[0] = 18;
+    a.jacobian_base[1] = 0; a.jacobian_step[1] = 6;
+  }
+  const int grid_max = std::min((n + CB200_EVALUATE_THREADS - 1) / CB200_EVALUATE_THREADS, 4096);
   a.cost_partial_count = grid_max;
   a.functors = Upload(functors);
   std::vector<char> lb((char*)&loss, (char*)&loss + sizeof(loss));
@@ -110,8 +118,8 @@ int main(int argc, char** argv) {
     for (double v : jh) js += std::fabs(v);
     std::printf("checksums: gradient sum %.12e abs %.12e  jacobian abs %.12e\n", gs, ga, js);
   }
-  std::printf("KBENCH %s ctas=%d ints_smem=%d fma_check=%d stage_g=%d stage_j=%d g=%d j=%d : mean %.3f ms best %.3f ms  (%.2f G blocks/s)  status=%d cost=%.6e\n",
-              argc > 6 ? argv[6] : "", CB200_RESIDENT_CTAS_SMALL, CB200_KERNEL_INTS_IN_SMEM, CB200_KERNEL_FMA_CHECK,
+  std::printf("KBENCH %s ctas=%d affine=%d fma_check=%d stage_g=%d stage_j=%d g=%d j=%d : mean %.3f ms best %.3f ms  (%.2f G blocks/s)  status=%d cost=%.6e\n",
+              argc > 6 ? argv[6] : "", CB200_RESIDENT_CTAS_SMALL, affine, CB200_KERNEL_FMA_CHECK,
               CB200_KERNEL_STAGE_GRADIENT, CB200_KERNEL_STAGE_JACOBIAN, want_g, want_j, sum / reps, best, n / (sum / reps) / 1e6, st, cost);
   return 0;
 }
