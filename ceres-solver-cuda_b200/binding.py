@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "cb200_engine_set_layout", "cb200_engine_set_shard", "cb200_engine_finalize",
     "cb200_nccl_unique_id", "cb200_engine_comm_init", "cb200_engine_evaluate",
     "cb200_engine_evaluate_device", "cb200_engine_device_ptr", "cb200_engine_shard_info",
-    "cb200_engine_last_timing", "cb200_engine_jacobian_multiply",
+    "cb200_engine_last_timing", "cb200_engine_exchange_plan", "cb200_engine_jacobian_multiply",
     "cb200_engine_jacobian_squared_column_norm", "cb200_engine_jacobian_scale_columns",
     "cb200_engine_cgnr_solve", "cb200_host_alloc", "cb200_host_pin", "cb200_host_free",
     "cb200_version",
@@ -104,6 +104,8 @@ def driver():
         L.drv_evaluate_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.drv_timing.argtypes = [C.c_void_p, C.c_void_p]
         L.drv_shard_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.drv_callback_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.drv_exchange_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.drv_plus.argtypes = [C.c_void_p] * 4
         L.drv_plus_threads.argtypes = [C.c_void_p] * 4 + [C.c_int]
         L.drv_dense_jacobian.argtypes = [C.c_void_p, C.c_void_p]
@@ -263,8 +265,16 @@ class CudaProblem:
         driver().drv_initial_state(self.h, _p(s))
         return s
 
+    def callback_info(self):
+        """What the problem's EvaluationCallback saw at its last notification."""
+        out = np.zeros(4)
+        driver().drv_callback_info(self.h, _p(out))
+        return {"calls": int(out[0]), "evaluate_jacobians": bool(out[1]),
+                "new_evaluation_point": bool(out[2]), "user_value_sum": float(out[3])}
+
     def evaluate(self, state=None, residuals=True, gradient=True, jacobian=True,
-                 apply_loss_function=True, out_residuals=None, out_gradient=None):
+                 apply_loss_function=True, out_residuals=None, out_gradient=None,
+                 new_evaluation_point=True):
         """Evaluator::Evaluate with host buffers.  Returns (ok, cost, r, g, jacobian_values)."""
         if not self.with_device:
             raise RuntimeError("built without a device: there is no CPU fallback")
@@ -278,8 +288,9 @@ class CudaProblem:
         if gradient:
             g = out_gradient if out_gradient is not None else \
                 np.full(self.num_effective_parameters, np.nan)
-        rc = driver().drv_evaluate(self.h, _p(state), int(apply_loss_function), _p(cost), _p(r),
-                                   _p(g), int(jacobian))
+        rc = driver().drv_evaluate(self.h, _p(state),
+                                   int(apply_loss_function) | (0 if new_evaluation_point else 2),
+                                   _p(cost), _p(r), _p(g), int(jacobian))
         if rc < 0:
             raise RuntimeError("no evaluator")
         j = self.jacobian_values[:self.values_size] if jacobian else None
@@ -396,6 +407,20 @@ class CudaProblem:
         return {"rb_begin": int(info[0]), "rb_end": int(info[1]), "residual_begin": int(info[2]),
                 "residual_end": int(info[3]),
                 "segments": [tuple(int(x) for x in seg[3 * i:3 * i + 3]) for i in range(max(n, 0))]}
+
+    def exchange_plan(self):
+        """This rank's gradient exchange plan (several ranks): None when the structure only
+        allows the NCCL all-reduce, else {chunks: [n, 4] (first block, end block, gradient
+        begin, gradient end), exclusive: (begin, length), shared_count}."""
+        excl = np.zeros(2, dtype=np.int64)
+        shared = np.zeros(1, dtype=np.int32)
+        n = driver().drv_exchange_plan(self.h, None, 0, _p(excl), _p(shared))
+        if n < 0:
+            return None
+        chunks = np.zeros((max(n, 1), 4), dtype=np.int32)
+        driver().drv_exchange_plan(self.h, _p(chunks), n, _p(excl), _p(shared))
+        return {"chunks": chunks[:n], "exclusive": (int(excl[0]), int(excl[1])),
+                "shared_count": int(shared[0])}
 
     def plus(self, state, delta, num_threads=1):
         out = np.zeros(self.num_parameters)

@@ -170,24 +170,93 @@ __global__ void ReduceCostKernel(const double* __restrict__ partials, int n, dou
   }
 }
 
-// Gradient exchange, second half: every rank's exclusive range arrived in `staging`
-// (rank r at [r * chunk, r * chunk + length[r])) and goes to its place in the gradient.
-constexpr int kMaxGatherRanks = 64;
-struct GatherPlan {
-  int64_t begin[kMaxGatherRanks];
-  int32_t length[kMaxGatherRanks];
-  int32_t world, self;
-  int64_t chunk;
+// ---- gradient exchange over peer-mapped memory (several ranks on one NVLink domain).
+// After a Schur ordering the residual blocks of a point are consecutive, so almost every
+// gradient entry is touched by one rank only: the evaluation kernel itself copies those
+// into the other ranks' buffers, chunk by chunk (kChunked in evaluate_kernel.cuh).  What is
+// left - the entries several ranks add to (the cameras of a bundle adjustment problem, the
+// points at rank boundaries), the cost and the status - is about 1 MB and is summed here:
+// every rank writes its partial sums into its slot on every rank, raises a flag there, waits
+// for the others' flags and adds the slots in rank order, so all ranks end up with the same
+// bits.  Flags carry the evaluation's sequence number and are never reset.
+constexpr int kMaxRanks = CB200_MAX_PEERS + 1;
+constexpr int kMaxSharedIntervals = 32;
+struct SharedExchange {
+  int32_t world, rank;
+  int32_t num_intervals;
+  int32_t begin[kMaxSharedIntervals];   // gradient offset of each shared interval
+  int32_t start[kMaxSharedIntervals];   // its first slot entry (prefix sum of the lengths)
+  int32_t count;                        // slot entries: all intervals + cost + failed
+  double* gradient;                     // this rank's [gradient | cost | failed]
+  int32_t cost_offset;                  // num_effective
+  double* slots[kMaxRanks];             // slots[q]: rank q's staging area [world][count]
+  unsigned long long* flags[kMaxRanks]; // flags[q]: rank q's flag array [world]
+  unsigned long long epoch;
+  unsigned* arrivals;                   // this rank, zero between launches
 };
-__global__ void __launch_bounds__(256) GatherScatterKernel(const GatherPlan plan,
-                                                           const double* __restrict__ staging,
-                                                           double* __restrict__ gradient) {
-  const int64_t total = plan.chunk * plan.world;
-  for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < total;
-       k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(k / plan.chunk);
-    const int64_t i = k - r * plan.chunk;
-    if (r != plan.self && i < plan.length[r]) gradient[plan.begin[r] + i] = staging[k];
+
+// Copies this rank's exclusive gradient range into the other ranks' buffers (used when the
+// evaluation kernel of the call has no chunked variant; otherwise the kernel does it).
+struct PeerPush {
+  int32_t num_peers;
+  int64_t begin, length;
+  const double* gradient;
+  double* peer[CB200_MAX_PEERS];
+};
+__global__ void __launch_bounds__(256) PushExclusiveKernel(const PeerPush x) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < x.length;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const double v = __ldcg(x.gradient + x.begin + i);
+    for (int q = 0; q < x.num_peers; ++q) __stcg(x.peer[q] + x.begin + i, v);
+  }
+}
+
+__device__ __forceinline__ int SharedIndexToGradient(const SharedExchange& x, int i) {
+  if (i >= x.count - 2) return x.cost_offset + (i - (x.count - 2));
+  int k = 0;
+  while (k + 1 < x.num_intervals && i >= x.start[k + 1]) ++k;
+  return x.begin[k] + (i - x.start[k]);
+}
+
+__global__ void __launch_bounds__(256) ExchangeSharedKernel(const SharedExchange x) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int threads = gridDim.x * blockDim.x;
+  // (1) this rank's partial sums into its slot on every rank
+  for (int i = tid; i < x.count; i += threads) {
+    const double v = __ldcg(x.gradient + SharedIndexToGradient(x, i));
+    for (int q = 0; q < x.world; ++q)
+      __stcg(x.slots[q] + static_cast<size_t>(x.rank) * x.count + i, v);
+  }
+  // (2) once every thread block has written: raise this rank's flag on every rank
+  __shared__ bool last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(x.arrivals, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    if (threadIdx.x < x.world) {
+      unsigned long long* flag = x.flags[threadIdx.x] + x.rank;
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(x.epoch) : "memory");
+    }
+    if (threadIdx.x == 0) *x.arrivals = 0;
+  }
+  // (3) wait for every rank's flag (their slots here, and every copy the evaluation kernels
+  // of the other ranks made into this rank's gradient, are then complete) ...
+  if (threadIdx.x < x.world) {
+    const unsigned long long* flag = x.flags[x.rank] + threadIdx.x;
+    unsigned long long seen;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+    } while (seen < x.epoch);
+  }
+  __syncthreads();
+  // (4) ... and add the slots in rank order
+  const double* mine = x.slots[x.rank];
+  for (int i = tid; i < x.count; i += threads) {
+    double sum = 0.0;
+    for (int q = 0; q < x.world; ++q) sum += __ldcg(mine + static_cast<size_t>(q) * x.count + i);
+    x.gradient[SharedIndexToGradient(x, i)] = sum;
   }
 }
 
@@ -680,12 +749,23 @@ struct cb200_engine {
   int32_t rb_begin = 0, rb_end = 0, res_begin = 0, res_end = 0;
   std::vector<Segment> segments;
   int64_t local_jacobian_values = 0;
-  // Gradient exchange plan (empty = one all-reduce over [gradient | cost]).
+  // Gradient exchange plan (empty = one all-reduce over [gradient | cost | failed]).
   std::vector<GradientInterval> exchange;
-  // ... and its all-gather form: one exclusive range per rank, padded to gather_chunk
-  GatherPlan gather{};
-  bool gather_ok = false;
-  DeviceBuffer<double> d_gather;
+  // Peer exchange (cb200_engine_comm_init sets it up when the plan allows): chunks of this
+  // rank's residual blocks with their exclusive gradient ranges, the shared intervals, and a
+  // peer-mapped region [2 x gradient | 2 x world slots | flags] on every rank.
+  std::vector<int32_t> chunk_table;        // 4 ints per chunk, see cb200_launch_args::chunks
+  DeviceBuffer<int32_t> d_chunks;
+  int64_t exclusive_begin = 0, exclusive_length = 0;  // this rank's exclusive gradient range
+  bool peer_plan = false;                  // the structure allows the peer exchange
+  bool peer_ready = false;                 // ... and the region is mapped on every rank
+  char* peer_region = nullptr;             // this rank's allocation
+  void* peer_base[kMaxRanks] = {};         // every rank's region (own at [rank])
+  size_t peer_gradient_stride = 0, peer_slots_offset = 0, peer_flags_offset = 0;  // bytes
+  int32_t shared_count = 0;
+  unsigned long long epoch = 0;
+  DeviceBuffer<unsigned> d_arrivals;
+  double* gradcost = nullptr;              // [gradient | cost | failed] of the current evaluation
 
   std::vector<ResidualType*> types;
 
@@ -780,7 +860,10 @@ void cb200_engine_destroy(cb200_engine* e) {
   for (auto& b : e->la_col) b.Free();
   e->la_row.Free(); e->la_scalars.Free(); e->la_partials.Free(); e->la_arrivals.Free();
   if (e->h_la_scalars) cudaFreeHost(e->h_la_scalars);
-  e->d_gather.Free();
+  e->d_chunks.Free(); e->d_arrivals.Free();
+  for (int r = 0; r < kMaxRanks; ++r)
+    if (e->peer_base[r] && r != e->rank) cudaIpcCloseMemHandle(e->peer_base[r]);
+  if (e->peer_region) cudaFree(e->peer_region);
   e->d_state.Free(); e->d_plus.Free(); e->d_residuals.Free(); e->d_jacobian.Free();
   e->d_gradcost.Free(); e->d_cost_partials.Free(); e->d_pb_table.Free(); e->d_status.Free();
   if (e->h_scalars) cudaFreeHost(e->h_scalars);
@@ -895,15 +978,21 @@ int cb200_engine_finalize(cb200_engine* e) {
   // rank: those need no reduction, only distribution.  Every rank sees the whole
   // problem here, so all ranks derive the same plan without communicating.
   e->exchange.clear();
+  e->chunk_table.clear();
+  e->peer_plan = false;
   if (e->world > 1 && e->num_active > 0) {
     std::vector<int32_t> bound(e->world + 1);
     for (int r = 0; r <= e->world; ++r) bound[r] = static_cast<int32_t>(nrb * r / e->world);
     std::vector<int16_t> lo(e->num_active, INT16_MAX), hi(e->num_active, -1);
+    // first / last program position of the residual blocks that touch each parameter block
+    std::vector<int32_t> first(e->num_active, INT32_MAX), last(e->num_active, -1);
+    bool in_program_order = e->types.size() == 1;
     for (ResidualType* t : e->types) {
       const int nb = t->desc.num_parameter_blocks;
       for (size_t k = 0; k < t->position.size(); ++k) {
         const int32_t p = t->position[k];
         if (p < 0 || p >= nrb) continue;  // reported below
+        if (p != static_cast<int32_t>(k)) in_program_order = false;
         int r = static_cast<int>(static_cast<int64_t>(p) * e->world / std::max<int64_t>(nrb, 1));
         while (r > 0 && p < bound[r]) --r;
         while (r + 1 < e->world && p >= bound[r + 1]) ++r;
@@ -912,6 +1001,8 @@ int cb200_engine_finalize(cb200_engine* e) {
           if (id < 0 || id >= e->num_active) continue;
           lo[id] = std::min<int16_t>(lo[id], static_cast<int16_t>(r));
           hi[id] = std::max<int16_t>(hi[id], static_cast<int16_t>(r));
+          first[id] = std::min(first[id], p);
+          last[id] = std::max(last[id], p);
         }
       }
     }
@@ -934,30 +1025,90 @@ int cb200_engine_finalize(cb200_engine* e) {
     int64_t covered = 0;
     for (const auto& g : plan) covered += g.length;
     if (plan.size() <= 96 && covered == e->num_effective) e->exchange.swap(plan);
-    // All-gather form: usable when every rank owns at most one exclusive range and those
-    // ranges are most of the vector (bundle adjustment after the Schur ordering).
-    e->gather_ok = false;
-    if (!e->exchange.empty() && e->world <= kMaxGatherRanks) {
-      GatherPlan gp{};
-      gp.world = e->world;
-      gp.self = e->rank;
-      std::vector<int> count(e->world, 0);
-      int64_t exclusive = 0, chunk = 0;
+
+    // Peer exchange: possible when the residual blocks are one type in program order, every
+    // rank owns at most one exclusive range and the shared part is small.  All of these are
+    // properties of the whole problem, so every rank takes the same decision.
+    std::vector<int> owned(e->world, 0);
+    int64_t shared = 0;
+    int shared_intervals = 0;
+    for (const GradientInterval& iv : e->exchange) {
+      if (iv.owner >= 0) ++owned[iv.owner];
+      else { shared += iv.length; ++shared_intervals; }
+    }
+    bool one_each = !e->exchange.empty();
+    for (int c : owned) one_each = one_each && c <= 1;
+    const char* mode = getenv("CB200_GRADIENT_EXCHANGE");
+    e->peer_plan = one_each && in_program_order && e->world <= kMaxRanks &&
+                   shared_intervals <= kMaxSharedIntervals && 4 * shared <= e->num_effective &&
+                   !(mode && std::strcmp(mode, "nccl") == 0);
+    e->shared_count = static_cast<int32_t>(shared) + 2;
+    e->exclusive_begin = e->exclusive_length = 0;
+    if (e->peer_plan) {
+      // Chunks of this rank's residual blocks whose exclusive gradient entries form a
+      // contiguous range touched by no other chunk.  A cut between consecutive parameter
+      // blocks i, i + 1 of the exclusive range is valid at residual block position
+      // min(first[i + 1 ...]) iff every block up to i was last touched before it.
+      constexpr int kChunkBlocks = 768;  // six tiles of 128: ~8 chunks per thread block on L x 8
+      int i0 = -1, i1 = -1;  // active blocks [i0, i1) of this rank's exclusive interval
       for (const GradientInterval& iv : e->exchange) {
-        if (iv.owner < 0) continue;
-        ++count[iv.owner];
-        gp.begin[iv.owner] = iv.begin;
-        gp.length[iv.owner] = static_cast<int32_t>(iv.length);
-        exclusive += iv.length;
-        chunk = std::max(chunk, iv.length);
+        if (iv.owner != e->rank) continue;
+        e->exclusive_begin = iv.begin;
+        e->exclusive_length = iv.length;
       }
-      bool one_each = true;
-      for (int c : count) one_each = one_each && c <= 1;
-      gp.chunk = chunk;
-      if (one_each && chunk > 0 && 2 * exclusive >= e->num_effective) {
-        e->gather = gp;
-        e->gather_ok = true;
+      if (e->exclusive_length > 0) {
+        for (int i = 0; i < e->num_active; ++i) {
+          const cb200_parameter_block& b = e->blocks[i];
+          if (b.tangent_size == 0) continue;
+          if (b.delta_offset >= e->exclusive_begin &&
+              b.delta_offset < e->exclusive_begin + e->exclusive_length) {
+            if (i0 < 0) i0 = i;
+            i1 = i + 1;
+          }
+        }
       }
+      const int32_t rb0 = static_cast<int32_t>(nrb * e->rank / e->world);
+      const int32_t rb1 = static_cast<int32_t>(nrb * (e->rank + 1) / e->world);
+      int32_t start_rb = rb0;
+      int64_t start_delta = e->exclusive_begin;
+      auto close_chunk = [&](int32_t end_rb, int64_t end_delta) {
+        if (end_rb > start_rb) {
+          e->chunk_table.push_back(start_rb - rb0);
+          e->chunk_table.push_back(end_rb - rb0);
+          e->chunk_table.push_back(static_cast<int32_t>(start_delta));
+          e->chunk_table.push_back(static_cast<int32_t>(end_delta));
+          start_rb = end_rb;
+          start_delta = end_delta;
+        }
+      };
+      if (i0 >= 0) {
+        std::vector<int32_t> sufmin(static_cast<size_t>(i1 - i0) + 1, INT32_MAX);
+        for (int i = i1 - 1; i >= i0; --i) sufmin[i - i0] = std::min(sufmin[i - i0 + 1], first[i]);
+        int32_t prefmax = -1, best_rb = -1;
+        int64_t best_delta = 0;
+        for (int i = i0; i + 1 < i1; ++i) {
+          prefmax = std::max(prefmax, last[i]);
+          const int32_t cut = sufmin[i + 1 - i0];
+          if (cut == INT32_MAX || !(prefmax < cut) || e->blocks[i + 1].tangent_size == 0) continue;
+          const int64_t cut_delta = e->blocks[i + 1].delta_offset;
+          if (cut <= start_rb) continue;
+          while (cut - start_rb > kChunkBlocks && best_rb > start_rb) {
+            close_chunk(best_rb, best_delta);
+            best_rb = -1;
+          }
+          if (cut - start_rb > kChunkBlocks) {  // no cut inside the target size: a long chunk
+            close_chunk(cut, cut_delta);
+            best_rb = -1;
+          } else {
+            best_rb = cut;
+            best_delta = cut_delta;
+          }
+        }
+        if (best_rb > start_rb && rb1 - start_rb > kChunkBlocks) close_chunk(best_rb, best_delta);
+      }
+      close_chunk(rb1, e->exclusive_begin + e->exclusive_length);
+      if (e->chunk_table.size() >= 4)  // the last chunk ends the exclusive range
+        e->chunk_table.back() = static_cast<int32_t>(e->exclusive_begin + e->exclusive_length);
     }
   }
 
@@ -1142,17 +1293,86 @@ int cb200_engine_finalize(cb200_engine* e) {
   CB200_CUDA(e, e->d_plus.Resize(static_cast<size_t>(e->plus_pool) + 1));
   CB200_CUDA(e, e->d_residuals.Resize(static_cast<size_t>(e->res_end - e->res_begin) + 1));
   CB200_CUDA(e, e->d_jacobian.Resize(static_cast<size_t>(e->local_jacobian_values) + 2));
-  // (+ gather_chunk: the all-gather reads a full chunk starting at this rank's range)
-  CB200_CUDA(e, e->d_gradcost.Resize(static_cast<size_t>(e->num_effective) + 2 +
-                                     (e->gather_ok ? e->gather.chunk : 0)));
-  if (e->gather_ok)
-    CB200_CUDA(e, e->d_gather.Resize(static_cast<size_t>(e->gather.chunk) * e->world));
+  CB200_CUDA(e, e->d_gradcost.Resize(static_cast<size_t>(e->num_effective) + 2));
+  e->gradcost = e->d_gradcost.ptr;
+  if (e->peer_plan && !e->chunk_table.empty())
+    CB200_CUDA(e, e->d_chunks.Upload(e->chunk_table, e->stream));
   CB200_CUDA(e, e->d_cost_partials.Resize(static_cast<size_t>(e->total_cost_partials) + 1));
   CB200_CUDA(e, e->d_status.Resize(1));
   CB200_CUDA(e, cudaStreamSynchronize(e->stream));
   // Layout arrays were consumed.
   std::vector<int32_t>().swap(e->jpro);
   e->finalized = true;
+  return CB200_OK;
+}
+
+// Maps one region per rank into every rank (CUDA IPC over NVLink peer access):
+//   [gradient buffer 0 | gradient buffer 1 | slots parity 0 | slots parity 1 | flags]
+// Two gradient buffers / slot sets alternate between evaluations so that a fast rank's copies
+// for evaluation k + 1 never land in memory a slow rank still reads for evaluation k.  All
+// ranks agree (one NCCL sum) on whether the mapping worked; if not, every rank keeps the
+// NCCL all-reduce.
+static size_t Align256(size_t bytes) { return (bytes + 255) / 256 * 256; }
+static int SetupPeerExchange(cb200_engine* e) {
+  e->peer_ready = false;
+  if (!e->finalized || !e->peer_plan || !e->comm || e->world <= 1) return CB200_OK;
+  NcclApi* n = GetNccl();
+  if (!n->AllGather) return CB200_OK;
+  cudaStream_t s = e->stream;
+  e->peer_gradient_stride = Align256((static_cast<size_t>(e->num_effective) + 2) * sizeof(double));
+  const size_t slot_bytes = Align256(static_cast<size_t>(e->world) * e->shared_count * sizeof(double));
+  e->peer_slots_offset = 2 * e->peer_gradient_stride;
+  e->peer_flags_offset = e->peer_slots_offset + 2 * slot_bytes;
+  const size_t total = e->peer_flags_offset + 256;
+  int failed = 0;
+  cudaIpcMemHandle_t mine{};
+  if (cudaMalloc(reinterpret_cast<void**>(&e->peer_region), total) != cudaSuccess ||
+      cudaMemsetAsync(e->peer_region, 0, total, s) != cudaSuccess ||
+      cudaIpcGetMemHandle(&mine, e->peer_region) != cudaSuccess) {
+    cudaGetLastError();
+    failed = 1;
+  }
+  // exchange the handles (and, below, the verdicts) through NCCL
+  DeviceBuffer<char> wire;
+  CB200_CUDA(e, wire.Resize(static_cast<size_t>(e->world) * sizeof(mine) + 2 * sizeof(double)));
+  CB200_CUDA(e, cudaMemcpyAsync(wire.ptr + e->rank * sizeof(mine), &mine, sizeof(mine),
+                                cudaMemcpyHostToDevice, s));
+  if (n->AllGather(wire.ptr + e->rank * sizeof(mine), wire.ptr, sizeof(mine), /*ncclChar*/ 0,
+                   e->comm, s) != 0)
+    return e->Fail(CB200_ERROR_NCCL, "ncclAllGather of the IPC handles failed");
+  std::vector<cudaIpcMemHandle_t> handles(e->world);
+  CB200_CUDA(e, cudaMemcpyAsync(handles.data(), wire.ptr, e->world * sizeof(mine),
+                                cudaMemcpyDeviceToHost, s));
+  CB200_CUDA(e, cudaStreamSynchronize(s));
+  for (int r = 0; r < e->world && !failed; ++r) {
+    if (r == e->rank) {
+      e->peer_base[r] = e->peer_region;
+    } else if (cudaIpcOpenMemHandle(&e->peer_base[r], handles[r],
+                                    cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      e->peer_base[r] = nullptr;
+      failed = 1;
+    }
+  }
+  double* verdict = reinterpret_cast<double*>(wire.ptr + e->world * sizeof(mine));
+  const double flag = failed;
+  CB200_CUDA(e, cudaMemcpyAsync(verdict, &flag, sizeof(double), cudaMemcpyHostToDevice, s));
+  if (n->AllReduce(verdict, verdict, 1, kNcclFloat64, kNcclSum, e->comm, s) != 0)
+    return e->Fail(CB200_ERROR_NCCL, "NCCL all-reduce failed");
+  double total_failed = 1.0;
+  CB200_CUDA(e, cudaMemcpyAsync(&total_failed, verdict, sizeof(double), cudaMemcpyDeviceToHost, s));
+  CB200_CUDA(e, cudaStreamSynchronize(s));
+  wire.Free();
+  if (total_failed != 0.0) {
+    if (getenv("CB200_VERBOSE"))
+      std::fprintf(stderr, "ceres_b200: rank %d: peer mapping unavailable, using the NCCL all-reduce\n",
+                   e->rank);
+    return CB200_OK;
+  }
+  CB200_CUDA(e, e->d_arrivals.Resize(1));
+  CB200_CUDA(e, cudaMemsetAsync(e->d_arrivals.ptr, 0, sizeof(unsigned), s));
+  CB200_CUDA(e, cudaStreamSynchronize(s));
+  e->peer_ready = true;
   return CB200_OK;
 }
 
@@ -1175,7 +1395,7 @@ int cb200_engine_comm_init(cb200_engine* e, const void* unique_id, int32_t rank,
   if (r != 0)
     return e->Fail(CB200_ERROR_NCCL, "ncclCommInitRank: %s",
                    n->GetErrorString ? n->GetErrorString(r) : "?");
-  return CB200_OK;
+  return SetupPeerExchange(e);
 }
 
 // Shared by the host-pointer and device-pointer entry points.
@@ -1185,12 +1405,39 @@ static int EvaluateOnDevice(cb200_engine* e, uint32_t flags, bool want_r, bool w
   if (want_j) e->jacobian_resident = true;   // values of an older evaluation are overwritten
   if (want_r) e->residuals_resident = true;
   CB200_CUDA(e, cudaMemsetAsync(e->d_status.ptr, 0, sizeof(int32_t), s));
-  // Only the gradient accumulates; residuals and Jacobian cells are each written
-  // exactly once.  Cost slot and padding are zeroed with it.
-  CB200_CUDA(e, cudaMemsetAsync(e->d_gradcost.ptr, 0,
-                                (static_cast<size_t>(e->num_effective) + 2) * sizeof(double), s));
+  const size_t ne = static_cast<size_t>(e->num_effective);
+  // Several ranks with the peer exchange: this evaluation's [gradient | cost | failed] is
+  // one of the two peer-mapped buffers.  Only what this rank's blocks add to is zeroed: the
+  // rest of the buffer is written by the other ranks, possibly before this point.
+  const bool peer = want_g && e->peer_ready;
+  char* region = nullptr;
+  if (peer) {
+    ++e->epoch;
+    region = e->peer_region;
+    e->gradcost = reinterpret_cast<double*>(region + (e->epoch & 1) * e->peer_gradient_stride);
+    if (e->exclusive_length > 0)
+      CB200_CUDA(e, cudaMemsetAsync(e->gradcost + e->exclusive_begin, 0,
+                                    e->exclusive_length * sizeof(double), s));
+    for (const GradientInterval& iv : e->exchange)
+      if (iv.owner < 0)
+        CB200_CUDA(e, cudaMemsetAsync(e->gradcost + iv.begin, 0, iv.length * sizeof(double), s));
+    CB200_CUDA(e, cudaMemsetAsync(e->gradcost + ne, 0, 2 * sizeof(double), s));
+  } else {
+    e->gradcost = e->d_gradcost.ptr;
+    // Only the gradient accumulates; residuals and Jacobian cells are each written
+    // exactly once.  Cost slot and padding are zeroed with it.
+    CB200_CUDA(e, cudaMemsetAsync(e->gradcost, 0, (ne + 2) * sizeof(double), s));
+  }
+  double* peer_gradient[CB200_MAX_PEERS] = {};
+  int num_peers = 0;
+  if (peer)
+    for (int r = 0; r < e->world; ++r)
+      if (r != e->rank)
+        peer_gradient[num_peers++] = reinterpret_cast<double*>(
+            static_cast<char*>(e->peer_base[r]) + (e->epoch & 1) * e->peer_gradient_stride);
   CB200_CUDA(e, cudaEventRecord(e->ev[1], s));
   int launches = 0;
+  bool pushed_by_kernel = false;
   for (ResidualType* t : e->types) {
     if (t->n_local == 0) continue;
     cb200_launch_args a{};
@@ -1216,7 +1463,7 @@ static int EvaluateOnDevice(cb200_engine* e, uint32_t flags, bool want_r, bool w
     a.plus_jacobians = e->d_plus.ptr;
     a.residuals = e->d_residuals.ptr;
     a.jacobian_values = e->d_jacobian.ptr;
-    a.gradient = e->d_gradcost.ptr;
+    a.gradient = e->gradcost;
     a.cost_partials = e->d_cost_partials.ptr + t->cost_partial_offset;
     a.status = e->d_status.ptr;
     a.affine = t->affine;
@@ -1224,6 +1471,19 @@ static int EvaluateOnDevice(cb200_engine* e, uint32_t flags, bool want_r, bool w
     a.row_stride = t->row_stride;
     std::memcpy(a.jacobian_base, t->jacobian_base, sizeof(a.jacobian_base));
     std::memcpy(a.jacobian_step, t->jacobian_step, sizeof(a.jacobian_step));
+    // The chunked variant exists for the plain all-outputs kernel over affine tables (the
+    // same test as in the launch thunk); otherwise PushExclusiveKernel below does the copies.
+    constexpr uint32_t kAffinePlain =
+        CB200_AFFINE_RESIDUAL | CB200_AFFINE_JACOBIAN | CB200_AFFINE_DELTA_IS_STATE;
+    if (peer && t->desc.supports_chunks && e->d_chunks.ptr && t->plain && !a.crs && want_r &&
+        want_j && a.apply_loss_function && (t->affine & kAffinePlain) == kAffinePlain &&
+        !getenv("CB200_NO_CHUNKED_KERNEL")) {
+      a.chunks = e->d_chunks.ptr;
+      a.num_chunks = static_cast<int32_t>(e->chunk_table.size() / 4);
+      a.num_peers = num_peers;
+      std::memcpy(a.peer_gradient, peer_gradient, sizeof(a.peer_gradient));
+      pushed_by_kernel = true;
+    }
     const int err = t->desc.launch(&a, s);
     if (err != 0)
       return e->Fail(CB200_ERROR_CUDA, "kernel launch: %s",
@@ -1233,51 +1493,53 @@ static int EvaluateOnDevice(cb200_engine* e, uint32_t flags, bool want_r, bool w
   CB200_CUDA(e, cudaEventRecord(e->ev[2], s));
   // [gradient | cost | failed]: the last two slots are written here
   ReduceCostKernel<<<1, 256, 0, s>>>(e->d_cost_partials.ptr, e->total_cost_partials,
-                                     e->d_gradcost.ptr + e->num_effective, e->d_status.ptr);
+                                     e->gradcost + ne, e->d_status.ptr);
   ++launches;
-  if (e->comm && e->world > 1) {
-    NcclApi* n = GetNccl();
-    double* g = e->d_gradcost.ptr;
-    double* cost_slot = g + e->num_effective;
-    int r = 0;
-    if (!want_g) {
-      // cost-only evaluation: [cost | failed]
-      r = n->AllReduce(cost_slot, cost_slot, 2, kNcclFloat64, kNcclSum, e->comm, s);
-    } else if (!e->gather_ok || !n->AllGather || !n->GroupStart || !n->GroupEnd ||
-               !getenv("CB200_GRADIENT_GATHER")) {
-      // One all-reduce over [gradient | cost]: the default.  The all-gather form below is
-      // correct (scripts/check_multigpu.py) but measured no faster: BAL L, 108 MB, device
-      // time per evaluation 1.25 ms (all-reduce) vs 1.33 ms (gather) on 2 GPUs and 0.62 vs
-      // 0.63 ms on 8 - NCCL's all-reduce over NVSwitch already moves each byte once per rank.
-      // It is kept behind CB200_GRADIENT_GATHER for fabrics without in-switch reduction.
-      r = n->AllReduce(g, g, static_cast<size_t>(e->num_effective) + 2, kNcclFloat64, kNcclSum,
-                       e->comm, s);
-    } else {
-      // After a Schur ordering all but a handful of gradient entries are touched by one rank
-      // only.  Those need distribution, not reduction: one all-gather of every rank's
-      // exclusive range (padded to a common chunk) moves 1/world of the vector per rank
-      // instead of all of it, and a copy kernel puts the ranges in place; the shared entries
-      // (the cameras of a BAL problem, boundary points) and the cost are all-reduced.  (A
-      // group of per-rank broadcasts does the same job but measured no faster than the plain
-      // all-reduce on 4 GPUs and slower on 8.)
-      n->GroupStart();
-      bool cost_done = false;
-      for (const GradientInterval& iv : e->exchange) {
-        if (iv.owner >= 0) continue;
-        size_t len = static_cast<size_t>(iv.length);
-        if (iv.begin + iv.length == e->num_effective) { len += 2; cost_done = true; }
-        r |= n->AllReduce(g + iv.begin, g + iv.begin, len, kNcclFloat64, kNcclSum, e->comm, s);
-      }
-      if (!cost_done)
-        r |= n->AllReduce(cost_slot, cost_slot, 2, kNcclFloat64, kNcclSum, e->comm, s);
-      r |= n->AllGather(g + e->gather.begin[e->rank], e->d_gather.ptr,
-                        static_cast<size_t>(e->gather.chunk), kNcclFloat64, e->comm, s);
-      r |= n->GroupEnd();
-      const int64_t total = e->gather.chunk * e->world;
-      const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16));
-      GatherScatterKernel<<<grid, 256, 0, s>>>(e->gather, e->d_gather.ptr, g);
+  if (peer) {
+    if (!pushed_by_kernel && e->exclusive_length > 0) {
+      PeerPush push{};
+      push.num_peers = num_peers;
+      push.begin = e->exclusive_begin;
+      push.length = e->exclusive_length;
+      push.gradient = e->gradcost;
+      std::memcpy(push.peer, peer_gradient, sizeof(push.peer));
+      const int grid = static_cast<int>(std::min<int64_t>((push.length + 255) / 256, 148 * 4));
+      PushExclusiveKernel<<<grid, 256, 0, s>>>(push);
       ++launches;
     }
+    SharedExchange x{};
+    x.world = e->world;
+    x.rank = e->rank;
+    int32_t at = 0;
+    for (const GradientInterval& iv : e->exchange) {
+      if (iv.owner >= 0) continue;
+      x.begin[x.num_intervals] = static_cast<int32_t>(iv.begin);
+      x.start[x.num_intervals] = at;
+      at += static_cast<int32_t>(iv.length);
+      ++x.num_intervals;
+    }
+    x.count = e->shared_count;
+    x.gradient = e->gradcost;
+    x.cost_offset = e->num_effective;
+    const size_t slot_bytes = (e->peer_flags_offset - e->peer_slots_offset) / 2;
+    for (int r = 0; r < e->world; ++r) {
+      char* base = static_cast<char*>(e->peer_base[r]);
+      x.slots[r] = reinterpret_cast<double*>(base + e->peer_slots_offset + (e->epoch & 1) * slot_bytes);
+      x.flags[r] = reinterpret_cast<unsigned long long*>(base + e->peer_flags_offset);
+    }
+    x.epoch = e->epoch;
+    x.arrivals = e->d_arrivals.ptr;
+    const int grid = std::max(1, std::min((x.count + 255) / 256, 64));
+    ExchangeSharedKernel<<<grid, 256, 0, s>>>(x);
+    ++launches;
+    CB200_CUDA(e, cudaGetLastError());
+  } else if (e->comm && e->world > 1) {
+    NcclApi* n = GetNccl();
+    double* g = e->gradcost;
+    // cost-only evaluation: [cost | failed]; otherwise one all-reduce over
+    // [gradient | cost | failed] (the path for structures the peer exchange does not cover).
+    const int r = want_g ? n->AllReduce(g, g, ne + 2, kNcclFloat64, kNcclSum, e->comm, s)
+                         : n->AllReduce(g + ne, g + ne, 2, kNcclFloat64, kNcclSum, e->comm, s);
     if (r != 0) return e->Fail(CB200_ERROR_NCCL, "NCCL collective failed (%d)", r);
   }
   CB200_CUDA(e, cudaEventRecord(e->ev[3], s));
@@ -1315,7 +1577,7 @@ int cb200_engine_evaluate(cb200_engine* e, const double* state, const double* pl
   const int rc = EvaluateOnDevice(e, flags, residuals != nullptr || keep_r, gradient != nullptr,
                                   jacobian_values != nullptr || keep_j);
   if (rc != CB200_OK) return rc;
-  CB200_CUDA(e, cudaMemcpyAsync(e->h_scalars, e->d_gradcost.ptr + e->num_effective,
+  CB200_CUDA(e, cudaMemcpyAsync(e->h_scalars, e->gradcost + e->num_effective,
                                 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (!(flags & CB200_SKIP_HOST_COPY)) {
     if (residuals && !keep_r && e->res_end > e->res_begin)
@@ -1323,7 +1585,7 @@ int cb200_engine_evaluate(cb200_engine* e, const double* state, const double* pl
                                     sizeof(double) * (e->res_end - e->res_begin),
                                     cudaMemcpyDeviceToHost, s));
     if (gradient && e->num_effective > 0)
-      CB200_CUDA(e, cudaMemcpyAsync(gradient, e->d_gradcost.ptr,
+      CB200_CUDA(e, cudaMemcpyAsync(gradient, e->gradcost,
                                     sizeof(double) * e->num_effective, cudaMemcpyDeviceToHost, s));
     if (jacobian_values && !keep_j)
       for (const Segment& seg : e->segments)
@@ -1358,7 +1620,7 @@ int cb200_engine_evaluate_device(cb200_engine* e, const double* state_device,
   const int rc = EvaluateOnDevice(e, flags, want_residuals != 0, want_gradient != 0,
                                   want_jacobian != 0);
   if (rc != CB200_OK) return rc;
-  CB200_CUDA(e, cudaMemcpyAsync(e->h_scalars, e->d_gradcost.ptr + e->num_effective,
+  CB200_CUDA(e, cudaMemcpyAsync(e->h_scalars, e->gradcost + e->num_effective,
                                 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CB200_CUDA(e, cudaEventRecord(e->ev[4], s));
   CB200_CUDA(e, cudaStreamSynchronize(s));
@@ -1371,7 +1633,7 @@ void* cb200_engine_device_ptr(cb200_engine* e, int which) {
   if (!e || !e->finalized || e->planning) return nullptr;
   switch (which) {
     case 0: return e->d_residuals.ptr;
-    case 1: return e->d_gradcost.ptr;
+    case 1: return e->gradcost;
     case 2: return e->d_jacobian.ptr;
     case 3: return e->d_state.ptr;
     case 4: return e->d_plus.ptr;
@@ -1641,6 +1903,21 @@ int cb200_engine_shard_info(cb200_engine* e, int32_t* rb_begin, int32_t* rb_end,
     segments[3 * i + 1] = e->segments[i].length;
     segments[3 * i + 2] = e->segments[i].local_begin;
   }
+  return n;
+}
+
+int cb200_engine_exchange_plan(cb200_engine* e, int32_t* chunks, int32_t max_chunks,
+                               int64_t* exclusive, int32_t* shared_count) {
+  if (!e || !e->finalized || !e->peer_plan) return -1;
+  const int n = static_cast<int>(e->chunk_table.size() / 4);
+  if (chunks)
+    for (int i = 0; i < n && i < max_chunks; ++i)
+      std::memcpy(chunks + 4 * i, e->chunk_table.data() + 4 * i, 4 * sizeof(int32_t));
+  if (exclusive) {
+    exclusive[0] = e->exclusive_begin;
+    exclusive[1] = e->exclusive_length;
+  }
+  if (shared_count) *shared_count = e->shared_count;
   return n;
 }
 

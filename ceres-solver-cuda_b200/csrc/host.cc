@@ -952,6 +952,15 @@ class ProgramEvaluatorCUDA final : public Evaluator {
       std::fprintf(stderr, "Evaluate on a planning-only evaluator: no device, no CPU fallback\n");
       return false;
     }
+    // Notify the user about the evaluation point (program_evaluator_cuda.h:116-121): the
+    // user's parameter blocks are set to `state` first, like
+    // Program::StateVectorToParameterBlocks + CopyParameterBlockStateToUserState.
+    if (options_.evaluation_callback != nullptr) {
+      program_->StateVectorToParameterBlocks(state);
+      options_.evaluation_callback->PrepareForEvaluation(
+          /*evaluate_jacobians=*/gradient != nullptr || jacobian != nullptr,
+          evaluate_options.new_evaluation_point);
+    }
     // ParameterBlock::SetState -> UpdatePlusJacobian (parameter_block.h:91-99,312-338):
     // the plus-Jacobians of the blocks with a manifold, at the new state.
     if (jacobian != nullptr || gradient != nullptr) {
@@ -1099,6 +1108,7 @@ bool Problem::Evaluate(const EvaluateOptions& options, double* cost, std::vector
     eo.num_threads = options.num_threads;
     eo.use_cuda = true;
     eo.registered_cuda_evaluators = &registry;
+    eo.evaluation_callback = impl->options().evaluation_callback;
     eo.device = options.cuda_device;
     eo.num_eliminate_blocks = 0;
     std::string error;

@@ -257,6 +257,7 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
   eo.sparse_linear_algebra_library_type = options.sparse_linear_algebra_library_type;
   eo.use_cuda = true;
   eo.registered_cuda_evaluators = options.registered_cuda_evaluators;
+  eo.evaluation_callback = impl->options().evaluation_callback;
   eo.device = options.cuda_device;
   // CGNR with CUDA_SPARSE is the reference's device-resident combination
   // (cgnr_solver.cc CudaCgnrSolver): the Jacobian stays in HBM and conjugate gradients on

@@ -282,6 +282,9 @@ __device__ __forceinline__ void CpAsyncWait() {
 // before block k is computed; 0: single-buffered, issued after block k's last functor call.
 #define CB200_KERNEL_EARLY_PREFETCH 1
 #endif
+#ifndef CB200_KERNEL_CHUNKED_EXCHANGE
+#define CB200_KERNEL_CHUNKED_EXCHANGE 1  // instantiate the chunked (multi-rank) kernel variant
+#endif
 #ifndef CB200_KERNEL_SEGMENTED_GRADIENT
 #define CB200_KERNEL_SEGMENTED_GRADIENT 1  // warp-shuffle pre-reduction of long same-block runs
 #endif
@@ -400,6 +403,11 @@ struct PassPlan {
     for (int j = 0; j < kNB; ++j) if (PassOf(j) == pass) w += Dims::Size(j);
     return w;
   }
+  __host__ __device__ static constexpr int MaxWidth() {
+    int w = 0;
+    for (int p = 0; p < kNumPasses; ++p) w = Width(p) > w ? Width(p) : w;
+    return w;
+  }
   // derivative lane of parameter i of block j inside its pass
   __host__ __device__ static constexpr int Lane(int j, int i) {
     return Dims::Offset(j) - Dims::Offset(FirstBlock(PassOf(j))) + i;
@@ -473,8 +481,9 @@ struct SmemPlan {
   static constexpr int kPrefetchBytes = kFits ? kPrefetchRaw : 0;
 
   static constexpr int kCtas = ResidentCtas(kRes, Dims::kNumParameters, kInts);
-  // per warp: every argument's cells side by side (Jacobian staging) ...
-  static constexpr int kJacobianDoubles = 32 * kRes * Dims::kNumParameters;
+  // per warp: the cells of the arguments of one derivative pass side by side (Jacobian
+  // staging; with several passes the region is reused pass after pass) ...
+  static constexpr int kJacobianDoubles = 32 * kRes * PassPlan<kRes, Ns...>::MaxWidth();
   // ... and one padded row per lane for the staged gradient reductions (plus, per lane,
   // the destination offset and the live-column mask: 2 x 32 ints).  With a single
   // derivative pass every gradient is out before the first cell is staged, so the
@@ -516,11 +525,21 @@ __host__ __device__ constexpr int VariantCtas(int variant, int resident, int cos
 // the warp (v1 of this kernel: long-scoreboard stalls 7.5 of 15 cycles per issue, FP64 pipe
 // 22% busy; profiles/r1_v1_ncu_summary.txt).  a.state must be 16-byte aligned and followed
 // by at least two doubles of slack (the engine's state buffer is).
-template <int kVariant, bool kAffine, typename Functor, typename Loss, int kRes, int... Ns>
+//
+// kChunked (several ranks, cb200_launch_args::chunks): a thread block evaluates whole CHUNKS
+// of consecutive residual blocks instead of a grid stride.  The gradient entries of a chunk's
+// exclusive range (the points of a bundle adjustment problem) are touched by that chunk
+// only, so when its last tile is done the thread block copies them straight into the
+// gradient buffers of the other ranks over NVLink (peer-mapped memory): the exchange of one
+// chunk overlaps the evaluation of the next ones, tile by tile, inside the same kernel.
+template <int kVariant, bool kAffine, bool kChunked, typename Functor, typename Loss, int kRes,
+          int... Ns>
 __global__ void __launch_bounds__(
     kEvaluateThreads,
     VariantCtas(kVariant,
-                ResidentCtas(kRes, (Ns + ... + 0), kVariant != kVariantCost && !kAffine),
+                ResidentCtas(kRes, (Ns + ... + 0),
+                             kVariant != kVariantCost &&
+                                 (!kAffine || kVariant == kVariantGenericAll)),
                 SmemPlan<Functor, false, kRes, Ns...>::kCostBytes))
     EvaluateKernel(const cb200_launch_args a) {
   using Dims = BlockDims<Ns...>;
@@ -531,9 +550,12 @@ __global__ void __launch_bounds__(
   constexpr bool kGeneric = kVariant == kVariantGeneric || kVariant == kVariantGenericAll;
   constexpr bool kAll = kVariant == kVariantPlainAll || kVariant == kVariantGenericAll;
   static_assert(!kAffine || kAll, "affine tables are for the all-outputs variants");
+  static_assert(!kChunked || (kAffine && !kGeneric), "chunks: plain all-outputs affine variant");
   // The int tables ride the cp.async pipeline except where positions are computed (affine)
   // and in the Jet-free variant (it needs one or two of them: read directly).
-  constexpr bool kInts = kJets && !kAffine;
+  // Generic variants keep the parameter-block ids there even when positions are computed:
+  // the id heads a chain of two dependent loads that must not start inside the iteration.
+  constexpr bool kInts = kJets && (!kAffine || kGeneric);
   using Smem = SmemPlan<Functor, kInts, kRes, Ns...>;
   const bool out_residuals = kAll || a.output_residuals;
   const bool out_jacobian = kAll || a.output_jacobian;
@@ -649,13 +671,13 @@ __global__ void __launch_bounds__(
           const int32_t* tab = kGeneric ? a.parameter_block : a.delta_offset;
           CpAsync4(idst + (Smem::kSlotDelta + j) * kEvaluateThreads,
                    tab + static_cast<size_t>(j) * n + r);
-          if (out_jacobian)
+          if (out_jacobian && !kAffine)
             CpAsync4(idst + (Smem::kSlotJpos + j) * kEvaluateThreads,
                      a.jacobian_pos + static_cast<size_t>(j) * n + r);
         }
-        if (crs && out_jacobian)
+        if (crs && out_jacobian && !kAffine)
           CpAsync4(idst + Smem::kSlotRowStride * kEvaluateThreads, a.jacobian_row_stride + r);
-        if (out_residuals)
+        if (out_residuals && !kAffine)
           CpAsync4(idst + Smem::kSlotResidual * kEvaluateThreads, a.residual_pos + r);
         if (a.loss_index)
           CpAsync4(idst + Smem::kSlotLoss * kEvaluateThreads, a.loss_index + r);
@@ -683,21 +705,59 @@ __global__ void __launch_bounds__(
   bool all_ok = true;
   bool bulk_pending = false;  // warp-uniform: a bulk store may still read the staging buffer
 
+  // ---- the sequence of residual blocks of this thread.  Grid stride: first + k * stride.
+  // Chunked: the tiles (kEvaluateThreads blocks) of chunks blockIdx.x, + gridDim.x, ...;
+  // `walk` runs two tiles ahead of the one being computed (offsets are fetched two ahead,
+  // copies issued one ahead).
+  struct Walk { int c, t, lo, hi; };
+  const int4* const chunk_table = reinterpret_cast<const int4*>(a.chunks);
+  auto load_chunk = [&](Walk& w) {
+    if (w.c < a.num_chunks) {
+      const int4 rec = __ldg(chunk_table + w.c);
+      w.lo = rec.x;
+      w.hi = rec.y;
+    } else {
+      w.lo = w.hi = n;
+    }
+  };
+  auto walk_rb = [&](const Walk& w) { return w.lo + w.t * kEvaluateThreads + tid; };
+  auto walk_advance = [&](Walk& w) {
+    ++w.t;
+    if (w.lo + w.t * kEvaluateThreads >= w.hi) {
+      w.c += gridDim.x;
+      w.t = 0;
+      load_chunk(w);
+    }
+  };
+  Walk walk{0, 0, 0, 0};
+  int rb0 = first, hi0 = n, c0 = 0, rb1 = first + stride, hi1 = n, c1 = 0;
+  if constexpr (kChunked) {
+    walk.c = blockIdx.x;
+    load_chunk(walk);
+    rb0 = walk_rb(walk); hi0 = walk.hi; c0 = walk.c;
+    walk_advance(walk);
+    rb1 = walk_rb(walk); hi1 = walk.hi; c1 = walk.c;
+    walk_advance(walk);
+  }
+
   int soff_next[kNB];   // state offsets of the block whose prefetch is issued next
   int soff_cur[kNB];    // state offsets of the block being computed (fallback path)
-  load_offsets(first, soff_cur);
-  prefetch(0, first, soff_cur);
+  load_offsets(rb0, soff_cur);
+  prefetch(0, rb0, soff_cur);
   unsigned parity_cur = parity_of(soff_cur);
-  load_offsets(first + stride, soff_next);
+  load_offsets(rb1, soff_next);
 
-  for (int k = 0; k < iterations; ++k) {
-    const int rb = first + k * stride;
-    const bool valid = rb < n;
-    const int tt = clamp(rb);
+#pragma unroll 1
+  for (int k = 0; kChunked ? c0 < a.num_chunks : k < iterations; ++k) {
+    const int rb = kChunked ? rb0 : first + k * stride;
+    const int limit = kChunked ? hi0 : n;  // blocks [.., limit) belong to this tile's chunk
+    const bool valid = rb < limit;
+    const int tt = valid ? rb : limit - 1;
     const int stage = k & 1;
     // first residual block of this warp: affine positions of a whole warp derive from it
     const int warp_rb = rb - lane;
-    const bool warp_valid = warp_rb + 31 < n;
+    const bool warp_valid = warp_rb + 31 < limit;
+    const int rb_next = kChunked ? rb1 : rb + stride;
 
     // The offsets of the next block arrive while this one is computed; its copies are
     // issued after the last functor call below.
@@ -705,13 +765,13 @@ __global__ void __launch_bounds__(
 #pragma unroll
     for (int j = 0; j < kNB; ++j) soff_issue[j] = soff_next[j];
     const unsigned parity_issue = parity_of(soff_issue);
-    load_offsets(rb + 2 * stride, soff_next);
+    load_offsets(kChunked ? walk_rb(walk) : rb + 2 * stride, soff_next);
     bool issued = false;
     auto issue_next = [&]() {
       if (!issued) {
         // (cooperative gathers overwrite rows other lanes read: the warp must be past them)
         if constexpr (kPrefetch && kStages == 1 && CB200_KERNEL_GATHER != 1) __syncwarp();
-        prefetch(stage ^ 1, rb + stride, soff_issue);
+        prefetch(stage ^ 1, rb_next, soff_issue);
       }
       issued = true;
     };
@@ -741,8 +801,7 @@ __global__ void __launch_bounds__(
       for (int j = 0; j < kNB; ++j) {
         const size_t at = static_cast<size_t>(j) * n + tt;
         if constexpr (kGeneric) {
-          const int id = kAffine ? __ldg(a.parameter_block + at)
-                                 : table(Smem::kSlotDelta + j, a.parameter_block, at);
+          const int id = table(Smem::kSlotDelta + j, a.parameter_block, at);
           const int4* rec = reinterpret_cast<const int4*>(a.parameter_block_table) + 2 * id;
           const int4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
           delta_off[j] = r0.y;
@@ -779,7 +838,7 @@ __global__ void __launch_bounds__(
     const Loss* __restrict__ losses = static_cast<const Loss*>(a.loss_table);
     int loss_at = 0;
     if (a.loss_index)
-      loss_at = kAffine ? __ldg(a.loss_index + tt) : table(Smem::kSlotLoss, a.loss_index, tt);
+      loss_at = table(Smem::kSlotLoss, a.loss_index, tt);  // (direct load when not staged)
     const Loss& loss = losses[loss_at];
 
     const double* sp = stage_params(stage);
@@ -886,13 +945,12 @@ __global__ void __launch_bounds__(
             const int s0 = __shfl_sync(0xffffffffu, row_stride_crs, 0);
             const int base = __shfl_sync(0xffffffffu, lo, 0);
             const bool mine = valid && row_stride_crs == s0 && lo == base + lane * kRes * s0;
-            bulk_all = __all_sync(0xffffffffu, mine) && ((base & 1) == 0) && s0 > 0;
+            bulk_all = Plan::kNumPasses == 1 && __all_sync(0xffffffffu, mine) &&
+                       ((base & 1) == 0) && s0 > 0;
             bulk_all_base = base;
           }
         }
       }
-      bool bulk_issued = false;
-
       double sqrt_rho1 = 1.0, residual_scaling = 1.0, alpha_sq_norm = 0.0;
       bool correct = false;
       double res_corrected[kRes];
@@ -964,7 +1022,7 @@ __global__ void __launch_bounds__(
 
         // The staging buffer may still be read by last iteration's bulk stores: wait
         // here, after the functor, so the copy has the whole evaluation to complete.
-        if (p == 0 && kStage && bulk_pending) {
+        if (kStage && bulk_pending) {
           if (lane == 0) BulkWaitRead();
           __syncwarp();
           bulk_pending = false;
@@ -1143,7 +1201,8 @@ __global__ void __launch_bounds__(
             if (kStage && (bulk_arg[j] || bulk_all)) {
               // Stage the cell exactly as it lies in global memory.
               double* cell = bulk_all ? jbuf + (jpos[j] - bulk_all_base)
-                                      : jbuf + 32 * kRes * Dims::Offset(j) + lane * kRes * tan;
+                                      : jbuf + 32 * kRes * (Dims::Offset(j) - Dims::Offset(kFirst)) +
+                                            lane * kRes * tan;
               if (!kGeneric && !crs && (kRes * kSize) % 2 == 0) {
                 double2* mine = reinterpret_cast<double2*>(cell);  // conflict-free 128-bit
 #pragma unroll
@@ -1196,10 +1255,11 @@ __global__ void __launch_bounds__(
                   for (int j = kFirst; j < kEnd; ++j)
                     if (bulk_arg[j])
                       BulkStore(a.jacobian_values + bulk_base[j],
-                                jbuf + 32 * kRes * Dims::Offset(j),
+                                jbuf + 32 * kRes * (Dims::Offset(j) - Dims::Offset(kFirst)),
                                 32 * kRes * (kGeneric ? tangent[j] : Dims::Size(j)) * 8);
+                  BulkCommit();
                 }
-                bulk_issued = true;
+                bulk_pending = true;  // the next pass (or block) waits before it restages
               }
             }
           }
@@ -1212,12 +1272,10 @@ __global__ void __launch_bounds__(
           FenceProxyAsyncShared();
           __syncwarp();
           const int s0 = __shfl_sync(0xffffffffu, row_stride_crs, 0);
-          if (lane == 0)
+          if (lane == 0) {
             BulkStore(a.jacobian_values + bulk_all_base, jbuf, 32 * kRes * s0 * 8);
-          bulk_issued = true;
-        }
-        if (bulk_issued) {
-          if (lane == 0) BulkCommit();
+            BulkCommit();
+          }
           bulk_pending = true;
         }
       }
@@ -1243,6 +1301,26 @@ __global__ void __launch_bounds__(
 #pragma unroll
     for (int j = 0; j < kNB; ++j) soff_cur[j] = soff_issue[j];
     parity_cur = parity_issue;
+
+    if constexpr (kChunked) {
+      // Last tile of a chunk: its exclusive gradient range is final (no other chunk, on
+      // any rank, adds to it).  Make this block's reductions visible, then copy the range
+      // into every other rank's gradient buffer; meanwhile the other thread blocks of
+      // this SM keep evaluating.
+      if (rb - tid + kEvaluateThreads >= limit) {
+        __threadfence();
+        __syncthreads();
+        const int4 rec = __ldg(chunk_table + c0);
+        for (int i = rec.z + tid; i < rec.w; i += kEvaluateThreads) {
+          const double v = __ldcg(a.gradient + i);
+#pragma unroll 1
+          for (int q = 0; q < a.num_peers; ++q) __stcg(a.peer_gradient[q] + i, v);
+        }
+      }
+      rb0 = rb1; hi0 = hi1; c0 = c1;
+      rb1 = walk_rb(walk); hi1 = walk.hi; c1 = walk.c;
+      walk_advance(walk);
+    }
   }
   if constexpr (kPrefetch) CpAsyncWait<0>();
   if (bulk_pending && lane == 0) BulkWaitAll();
@@ -1274,7 +1352,7 @@ __global__ void __launch_bounds__(
 // set for the kernel being launched on the current device every time (~1 us).
 template <typename Kernel>
 int LaunchVariant(Kernel kernel, int wanted_ctas_per_sm, int smem_bytes,
-                  const cb200_launch_args* args, cudaStream_t s) {
+                  const cb200_launch_args* args, cudaStream_t s, int work_items = -1) {
   int device = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&device);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -1282,7 +1360,9 @@ int LaunchVariant(Kernel kernel, int wanted_ctas_per_sm, int smem_bytes,
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return static_cast<int>(e);
   const int wanted = (sms > 0 ? sms : 148) * wanted_ctas_per_sm;
-  const int needed = (args->n + kEvaluateThreads - 1) / kEvaluateThreads;
+  // one thread block per tile of kEvaluateThreads residual blocks, or per chunk
+  const int needed =
+      work_items >= 0 ? work_items : (args->n + kEvaluateThreads - 1) / kEvaluateThreads;
   int grid = needed < wanted ? needed : wanted;
   if (grid > args->cost_partial_count) grid = args->cost_partial_count;
   kernel<<<grid, kEvaluateThreads, smem_bytes, s>>>(*args);
@@ -1304,29 +1384,35 @@ int LaunchEvaluate(const cb200_launch_args* args, void* stream) {
       CB200_AFFINE_RESIDUAL | CB200_AFFINE_JACOBIAN | CB200_AFFINE_DELTA_IS_STATE;
   constexpr unsigned kAffineGeneric = CB200_AFFINE_RESIDUAL | CB200_AFFINE_JACOBIAN;
   if (!(args->output_jacobian || args->output_gradient)) {
-    return LaunchVariant(EvaluateKernel<kVariantCost, false, Functor, Loss, kRes, Ns...>, kCostCtas,
+    return LaunchVariant(EvaluateKernel<kVariantCost, false, false, Functor, Loss, kRes, Ns...>, kCostCtas,
                          Computed::kCostBytes, args, s);
   }
 #if CB200_KERNEL_SPECIALISE_ALL_OUTPUTS
   if (all && args->plain && !args->crs) {
+#if CB200_KERNEL_CHUNKED_EXCHANGE
+    if (args->chunks && (args->affine & kAffinePlain) == kAffinePlain)
+      return LaunchVariant(
+          EvaluateKernel<kVariantPlainAll, true, true, Functor, Loss, kRes, Ns...>, kAffineCtas,
+          Computed::kJetBytes, args, s, args->num_chunks);
+#endif
     if ((args->affine & kAffinePlain) == kAffinePlain)
-      return LaunchVariant(EvaluateKernel<kVariantPlainAll, true, Functor, Loss, kRes, Ns...>,
+      return LaunchVariant(EvaluateKernel<kVariantPlainAll, true, false, Functor, Loss, kRes, Ns...>,
                            kAffineCtas, Computed::kJetBytes, args, s);
-    return LaunchVariant(EvaluateKernel<kVariantPlainAll, false, Functor, Loss, kRes, Ns...>,
+    return LaunchVariant(EvaluateKernel<kVariantPlainAll, false, false, Functor, Loss, kRes, Ns...>,
                          kJetCtas, Tables::kJetBytes, args, s);
   }
   if (all && !args->plain) {
     if ((args->affine & kAffineGeneric) == kAffineGeneric)
-      return LaunchVariant(EvaluateKernel<kVariantGenericAll, true, Functor, Loss, kRes, Ns...>,
-                           kAffineCtas, Computed::kJetBytes, args, s);
-    return LaunchVariant(EvaluateKernel<kVariantGenericAll, false, Functor, Loss, kRes, Ns...>,
+      return LaunchVariant(EvaluateKernel<kVariantGenericAll, true, false, Functor, Loss, kRes, Ns...>,
+                           kJetCtas, Tables::kJetBytes, args, s);  // (block ids stay staged)
+    return LaunchVariant(EvaluateKernel<kVariantGenericAll, false, false, Functor, Loss, kRes, Ns...>,
                          kJetCtas, Tables::kJetBytes, args, s);
   }
 #endif
   if (args->plain)
-    return LaunchVariant(EvaluateKernel<kVariantPlain, false, Functor, Loss, kRes, Ns...>, kJetCtas,
+    return LaunchVariant(EvaluateKernel<kVariantPlain, false, false, Functor, Loss, kRes, Ns...>, kJetCtas,
                          Tables::kJetBytes, args, s);
-  return LaunchVariant(EvaluateKernel<kVariantGeneric, false, Functor, Loss, kRes, Ns...>, kJetCtas,
+  return LaunchVariant(EvaluateKernel<kVariantGeneric, false, false, Functor, Loss, kRes, Ns...>, kJetCtas,
                        Tables::kJetBytes, args, s);
 }
 
@@ -1342,6 +1428,7 @@ cb200_residual_type MakeResidualType() {
   t.functor_size = static_cast<int32_t>(sizeof(Functor));
   t.loss_size = static_cast<int32_t>(sizeof(Loss));
   t.threads_per_block = kEvaluateThreads;
+  t.supports_chunks = CB200_KERNEL_CHUNKED_EXCHANGE;
   t.launch = &LaunchEvaluate<Functor, Loss, kRes, Ns...>;
   return t;
 }

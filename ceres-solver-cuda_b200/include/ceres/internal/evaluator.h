@@ -13,6 +13,7 @@
 #ifndef CERES_B200_INTERNAL_EVALUATOR_H_
 #define CERES_B200_INTERNAL_EVALUATOR_H_
 
+#include "ceres/evaluation_callback.h"
 #include <map>
 #include <memory>
 #include <string>
@@ -78,6 +79,7 @@ class Evaluator {
     bool dynamic_sparsity = false;
     bool use_cuda = true;
     RegisteredCUDAEvaluators* registered_cuda_evaluators = nullptr;
+    EvaluationCallback* evaluation_callback = nullptr;  // internal/ceres/evaluator.h:76
     // Extensions (not in the reference): device ordinal and residual-block sharding.
     int device = 0;
     int shard_rank = 0;

@@ -14,6 +14,7 @@
 #ifndef CERES_B200_INTERNAL_PROGRAM_H_
 #define CERES_B200_INTERNAL_PROGRAM_H_
 
+#include "ceres/evaluation_callback.h"
 #include <cstdint>
 #include <memory>
 #include <string>
@@ -80,6 +81,8 @@ struct ProblemOptions {
   Ownership manifold_ownership = TAKE_OWNERSHIP;
   bool enable_fast_removal = false;
   bool disable_all_safety_checks = false;
+  // Notified before every evaluation (include/ceres/problem.h:166-183); not owned.
+  EvaluationCallback* evaluation_callback = nullptr;
 };
 
 class ProblemImpl {

@@ -36,6 +36,7 @@ AFFINE_FAIL = 13        # <20, 3, 2, 3, 4>(succeeds=false)
 PARAMETER_SENSITIVE = 14
 POSE_GRAPH_3D = 15      # <6, 3, 4, 3, 4> examples/slam/pose_graph_3d/pose_graph_3d_error_term.h
 JET_BATTERY = 16        # <40, 2> every Jet operation (jet_cuda_test.cu.cc)
+SQRT_OF_CONSTANT = 17   # <1, 1>  x + sqrt(T(c)): derivative of a constant sub-expression
 
 # (num_residuals, block sizes, functor data length)
 COST_TYPES = {
@@ -56,11 +57,13 @@ COST_TYPES = {
     PARAMETER_SENSITIVE: (2, (2,), 0),
     POSE_GRAPH_3D: (6, (3, 4, 3, 4), 43),
     JET_BATTERY: (40, (2,), 0),
+    SQRT_OF_CONSTANT: (1, (1,), 1),
 }
 
 # ---- loss kinds (include/ceres/loss_function_cuda.h:62-149)
 LOSS_NONE, LOSS_TRIVIAL, LOSS_HUBER, LOSS_CAUCHY = 0, 1, 2, 3
 LOSS_SCALED_HUBER, LOSS_SCALED_CAUCHY, LOSS_SCALED_TRIVIAL = 4, 5, 6
+LOSS_CONVEX_TEST = 7  # test-only user loss rho(s) = s + a s^2 (rho'' > 0)
 
 # ---- manifold kinds (internal/ceres/manifold.cc, include/ceres/product_manifold.h)
 MANIFOLD_NONE, MANIFOLD_SUBSET, MANIFOLD_QUATERNION, MANIFOLD_EIGEN_QUATERNION = 0, 1, 2, 3

@@ -23,6 +23,7 @@ extern "C" {
 #endif
 
 #define CB200_MAX_PARAMETER_BLOCKS 10 /* include/ceres/internal/parameter_dims.h users: <= 10 */
+#define CB200_MAX_PEERS 15             /* other ranks of one NVLink domain */
 
 /* status codes */
 #define CB200_OK 0
@@ -121,7 +122,17 @@ typedef struct cb200_launch_args {
   int32_t row_stride;
   int32_t jacobian_base[CB200_MAX_PARAMETER_BLOCKS];
   int32_t jacobian_step[CB200_MAX_PARAMETER_BLOCKS];
+  /* Several ranks, gradient exchange fused into the evaluation kernel (NULL otherwise): a
+   * thread block evaluates whole chunks; chunk c is residual blocks [chunks[4c], chunks[4c+1])
+   * of this launch and gradient entries [chunks[4c+2], chunks[4c+3]) are touched by it alone,
+   * so the kernel copies them into peer_gradient[0 .. num_peers) — the gradient buffers of
+   * the other ranks, peer-mapped — as soon as the chunk is done. */
+  const int32_t* chunks;
+  int32_t num_chunks;
+  int32_t num_peers;
+  double* peer_gradient[CB200_MAX_PEERS];
 } cb200_launch_args;
+
 #define CB200_AFFINE_RESIDUAL 1u
 #define CB200_AFFINE_JACOBIAN 2u
 #define CB200_AFFINE_DELTA_IS_STATE 4u
@@ -143,6 +154,7 @@ typedef struct cb200_residual_type {
   int32_t functor_size;      /* bytes */
   int32_t loss_size;         /* bytes */
   int32_t threads_per_block; /* of the launch thunk; fixes the number of cost partials */
+  int32_t supports_chunks;   /* the thunk honours cb200_launch_args::chunks (fused exchange) */
   cb200_launch_fn launch;
 } cb200_residual_type;
 
@@ -237,6 +249,16 @@ void* cb200_engine_device_ptr(cb200_engine* engine, int which);
 int cb200_engine_shard_info(cb200_engine* engine, int32_t* rb_begin, int32_t* rb_end,
                             int32_t* residual_begin, int32_t* residual_end,
                             int64_t* segments, int32_t max_segments);
+
+/* Multi-GPU gradient exchange plan of this rank (derived by cb200_engine_finalize from the
+ * whole problem; works on planning-only engines).  Returns the number of chunks, or -1 when
+ * the structure does not allow the peer exchange (several residual-block types, no
+ * exclusive ranges, ...: the ranks then use one NCCL all-reduce).  chunks receives up to
+ * max_chunks records of 4 ints (cb200_launch_args::chunks); exclusive = {begin, length} of
+ * the gradient range only this rank's residual blocks touch; *shared_count = entries several
+ * ranks add to, plus cost and status. */
+int cb200_engine_exchange_plan(cb200_engine* engine, int32_t* chunks, int32_t max_chunks,
+                               int64_t* exclusive, int32_t* shared_count);
 
 /* ---- linear algebra on the device-resident Jacobian of the last evaluation
  * (SURVEY.md section 8(f) items 1-2).  The 5.6 GB of Jacobian values of a large bundle

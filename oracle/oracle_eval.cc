@@ -145,6 +145,7 @@ static const std::vector<CostTypeInfo>& CostTypes() {
       /* 14 */ MakeType<ParameterSensitiveCost, 2, 2>(0),
       /* 15 */ MakeType<PoseGraph3dErrorTerm, 6, 3, 4, 3, 4>(43),
       /* 16 */ MakeType<JetBatteryCost, 40, 2>(0),
+      /* 17 */ MakeType<SqrtOfConstantCost, 1, 1>(1),
   };
   return types;
 }
@@ -158,7 +159,8 @@ enum LossKind {
   kLossCauchy = 3,
   kLossScaledHuber = 4,   // ScaledLossCUDA<HuberLossCUDA>(Huber(a), b)
   kLossScaledCauchy = 5,  // ScaledLossCUDA<CauchyLossCUDA>(Cauchy(a), b)
-  kLossScaledTrivial = 6  // ScaledLossCUDA<TrivialLossCUDA>(_, b)
+  kLossScaledTrivial = 6,  // ScaledLossCUDA<TrivialLossCUDA>(_, b)
+  kLossConvexTest = 7      // test loss rho(s) = s + a s^2: rho'' = 2a > 0 (Corrector alpha path)
 };
 
 static void HuberEvaluate(double a_, double s, double rho[3]) {
@@ -206,6 +208,9 @@ static void LossEvaluate(int kind, double a, double b, double s, double rho[3]) 
       return;
     case kLossScaledTrivial:
       rho[0] = b * s; rho[1] = b; rho[2] = 0.0;
+      return;
+    case kLossConvexTest:
+      rho[0] = s + a * s * s; rho[1] = 1.0 + 2.0 * a * s; rho[2] = 2.0 * a;
       return;
     default:
       rho[0] = s; rho[1] = 1.0; rho[2] = 0.0;

@@ -271,6 +271,17 @@ struct OnlyFillsOneOutputFunctor {
   }
 };
 
+// <1, 1>  r = x + sqrt(T(c)): with c == 0 the reference's dense Jets give the constant's
+// derivative lanes 0 * inf = NaN (jet.h:617-621), so the CPU evaluator rejects the evaluation
+// (residual_block.cc:110-129); see tests/test_gpu_robustness.py for the product's behaviour.
+struct SqrtOfConstantCost {
+  template <typename T>
+  bool operator()(const double* data, const T* x, T* residual) const {
+    residual[0] = x[0] + sqrt(T(data[0]));
+    return true;
+  }
+};
+
 // Autodiff restatement of internal/ceres/evaluator_test.cc:59-100
 // ParameterIgnoringCostFunction<kFactor, kNumResiduals, Ns...>: residual i is
 // (i + 1) and d r_i / d x_k[j] = kFactor * (j + 1).  As an autodiff functor it

@@ -3,7 +3,9 @@
 // The REFERENCE's own arithmetic for the evaluation path, compiled from the sources
 // where they lie under /root/reference (never copied) over oracle/eigen_shim:
 //   include/ceres/jet.h, rotation.h, autodiff_cost_function.h (-> internal/autodiff.h),
-//   internal/corrector.h, loss_function_cuda.h, examples/snavely_reprojection_error.h.
+//   internal/corrector.h, loss_function_cuda.h, examples/snavely_reprojection_error.h,
+//   internal/ceres/autodiff_benchmarks/relative_pose_error.h,
+//   examples/slam/pose_graph_3d/pose_graph_3d_error_term.h (+ types.h).
 // Output: oracle/_ref/libref_arith.so (git-ignored).  Used by
 // tests/golden/make_golden.py to validate the restatement (oracle_eval.cc) and to
 // generate the golden vectors in tests/golden/.  /root/reference does not exist on
@@ -15,7 +17,9 @@
 #include "ceres/jet.h"
 #include "ceres/loss_function_cuda.h"
 #include "ceres/rotation.h"
+#include "examples/slam/pose_graph_3d/pose_graph_3d_error_term.h"
 #include "examples/snavely_reprojection_error.h"
+#include "internal/ceres/autodiff_benchmarks/relative_pose_error.h"
 
 namespace {
 template <typename CostFunctionT>
@@ -56,6 +60,37 @@ void ref_loss(int kind, double a, double b, double s, double* rho) {
     case 5: ceres::ScaledLossCUDA<ceres::CauchyLossCUDA>(ceres::CauchyLossCUDA(a), b).Evaluate(s, rho); break;
     case 6: ceres::ScaledLossCUDA<ceres::TrivialLossCUDA>(ceres::TrivialLossCUDA(), b).Evaluate(s, rho); break;
   }
+}
+
+// internal/ceres/autodiff_benchmarks/relative_pose_error.h:46-92 through
+// AutoDiffCostFunction<RelativePoseError, 6, 7, 7>.  pose = [q(x, y, z, w), t];
+// meas = [q_i_j(x, y, z, w), t_i_j].  Jacobians row-major 6 x 7.
+int ref_relative_pose(const double* pose_i, const double* pose_j, const double* meas,
+                      double* residuals, double* jac_i, double* jac_j) {
+  ceres::AutoDiffCostFunction<ceres::RelativePoseError, 6, 7, 7> f(new ceres::RelativePoseError(
+      Eigen::Quaterniond(meas[3], meas[0], meas[1], meas[2]),
+      Eigen::Vector3d(meas[4], meas[5], meas[6])));
+  return Eval(f, pose_i, pose_j, residuals, jac_i, jac_j);
+}
+
+// examples/slam/pose_graph_3d/pose_graph_3d_error_term.h:71-124 through its own Create():
+// AutoDiffCostFunction<PoseGraph3dErrorTerm, 6, 3, 4, 3, 4>.  data = [p_ab(3),
+// q_ab(x, y, z, w), sqrt_information row-major 6 x 6].  jac: 4 row-major blocks
+// 6 x 3, 6 x 4, 6 x 3, 6 x 4.
+int ref_pose_graph_3d(const double* p_a, const double* q_a, const double* p_b, const double* q_b,
+                      const double* data, double* residuals, double* j0, double* j1, double* j2,
+                      double* j3) {
+  ceres::examples::Pose3d t_ab;
+  t_ab.p = Eigen::Vector3d(data[0], data[1], data[2]);
+  t_ab.q = Eigen::Quaterniond(data[6], data[3], data[4], data[5]);
+  Eigen::Matrix<double, 6, 6> sqrt_information;
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) sqrt_information(i, j) = data[7 + 6 * i + j];
+  std::unique_ptr<ceres::CostFunction> f(
+      ceres::examples::PoseGraph3dErrorTerm::Create(t_ab, sqrt_information));
+  const double* params[4] = {p_a, q_a, p_b, q_b};
+  double* jac[4] = {j0, j1, j2, j3};
+  return f->Evaluate(params, residuals, j0 ? jac : nullptr) ? 1 : 0;
 }
 
 // include/ceres/internal/corrector.h:82-213.

@@ -18,9 +18,27 @@
 namespace driver {
 
 // Loss kinds / manifold kinds / cost type ids: see problems.py.
-enum LossKind { kNone = 0, kTrivial, kHuber, kCauchy, kScaledHuber, kScaledCauchy, kScaledTrivial };
+enum LossKind { kNone = 0, kTrivial, kHuber, kCauchy, kScaledHuber, kScaledCauchy, kScaledTrivial,
+                kConvexTest };
+
+// Problem::Options::evaluation_callback of every driver problem: counts the notifications and
+// remembers what it saw (the flags, and the user's parameter values at that moment).
+struct RecordingCallback : ceres::EvaluationCallback {
+  int calls = 0;
+  bool evaluate_jacobians = false, new_evaluation_point = false;
+  double user_value_sum = 0.0;
+  const std::vector<double>* values = nullptr;
+  void PrepareForEvaluation(bool jacobians, bool new_point) override {
+    ++calls;
+    evaluate_jacobians = jacobians;
+    new_evaluation_point = new_point;
+    user_value_sum = 0.0;
+    if (values) for (double v : *values) user_value_sum += v;
+  }
+};
 
 struct DriverProblem {
+  RecordingCallback callback;      // (before `problem`: its options point at it)
   std::vector<double> values;      // user state of every parameter block
   std::vector<int64_t> pb_offset;  // into values
   std::vector<int> pb_size;
@@ -35,9 +53,10 @@ struct DriverProblem {
   // results of the last drv_problem_evaluate
   std::vector<double> pe_residuals, pe_gradient;
   ceres::CRSMatrix pe_jacobian;
-  DriverProblem() : problem(MakeOptions()) {}
-  static ceres::Problem::Options MakeOptions() {
+  DriverProblem() : problem(MakeOptions(&callback)) { callback.values = &values; }
+  static ceres::Problem::Options MakeOptions(RecordingCallback* callback) {
     ceres::Problem::Options o;
+    o.evaluation_callback = callback;
     return o;
   }
   double* pb(int id) { return values.data() + pb_offset[id]; }

@@ -48,9 +48,9 @@ ceres::Manifold* MakeManifold(int kind, int param, int size) {
   return nullptr;
 }
 
-const int kNumTypes = 17;
-const int kTypeBlocks[kNumTypes] = {2, 2, 2, 1, 2, 2, 10, 1, 3, 3, 2, 2, 2, 3, 1, 4, 1};
-const int kTypeFdata[kNumTypes] = {2, 2, 2, 3, 7, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 43, 0};
+const int kNumTypes = 18;
+const int kTypeBlocks[kNumTypes] = {2, 2, 2, 1, 2, 2, 10, 1, 3, 3, 2, 2, 2, 3, 1, 4, 1, 1};
+const int kTypeFdata[kNumTypes] = {2, 2, 2, 3, 7, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 43, 0, 1};
 }  // namespace
 
 extern "C" {
@@ -155,6 +155,7 @@ int drv_build(void* h, int reduce, int schur_reorder, int num_eliminate_blocks,
   options.shard_rank = rank;
   options.shard_world_size = world_size;
   options.nccl_unique_id = nccl_unique_id;
+  options.evaluation_callback = dp->problem.mutable_problem()->options().evaluation_callback;
   dp->evaluator = Evaluator::Create(options, dp->program.get(), &dp->error);
   if (!dp->evaluator) return 0;
   dp->layout = *dp->evaluator->layout();
@@ -237,12 +238,24 @@ double* drv_jacobian_values(void* h) {
 
 // Evaluator::Evaluate.  want_jacobian writes into drv_jacobian_values().
 // Returns 1 (true), 0 (false: evaluation failed), -1 (no evaluator).
+// out: [calls, evaluate_jacobians, new_evaluation_point, sum of the user's parameter values]
+// as the EvaluationCallback saw them at its last notification.
+void drv_callback_info(void* h, double* out4) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  out4[0] = dp->callback.calls;
+  out4[1] = dp->callback.evaluate_jacobians;
+  out4[2] = dp->callback.new_evaluation_point;
+  out4[3] = dp->callback.user_value_sum;
+}
+
+// apply_loss_function: bit 0; bit 1 set = EvaluateOptions::new_evaluation_point false
 int drv_evaluate(void* h, const double* state, int apply_loss_function, double* cost,
                  double* residuals, double* gradient, int want_jacobian) {
   auto* dp = static_cast<DriverProblem*>(h);
   if (!dp->evaluator) return -1;
   Evaluator::EvaluateOptions eo;
-  eo.apply_loss_function = apply_loss_function != 0;
+  eo.apply_loss_function = (apply_loss_function & 1) != 0;
+  eo.new_evaluation_point = (apply_loss_function & 2) == 0;
   return dp->evaluator->Evaluate(eo, state, cost, residuals, gradient,
                                  want_jacobian ? dp->jacobian.get() : nullptr)
              ? 1
@@ -367,6 +380,14 @@ int drv_shard_info(void* h, int32_t* info4, int64_t* segments, int max_segments)
   if (!dp->evaluator) return -1;
   return cb200_engine_shard_info(dp->evaluator->engine(), info4, info4 + 1, info4 + 2, info4 + 3,
                                  segments, max_segments);
+}
+
+int drv_exchange_plan(void* h, int32_t* chunks, int max_chunks, int64_t* exclusive,
+                      int32_t* shared_count) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  if (!dp->evaluator) return -2;
+  return cb200_engine_exchange_plan(dp->evaluator->engine(), chunks, max_chunks, exclusive,
+                                    shared_count);
 }
 
 int drv_plus(void* h, const double* state, const double* delta, double* out) {

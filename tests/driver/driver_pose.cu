@@ -2,21 +2,17 @@
 #include "relative_pose_error.h"
 
 namespace driver {
+bool AddRunPose3d(DriverProblem& dp, int type, int loss_kind, double a, double b, int n,
+                  const int* pb, const double* fdata, bool bulk, bool* handled);
+
 bool AddRunPose(DriverProblem& dp, int type, int loss_kind, double a, double b, int n,
                 const int* pb, const double* fdata, bool bulk, bool* handled) {
   using namespace ceres::examples;
   *handled = true;
-  switch (type) {
-    case 4:
-      return AddRunCommonLosses<RelativePoseError, 6, 7, 7>(
-          dp, loss_kind, a, b, n, pb, fdata, 7, bulk,
-          [](const double* d) { return RelativePoseError(d); });
-    case 15:
-      return AddRunCommonLosses<PoseGraph3dErrorTerm, 6, 3, 4, 3, 4>(
-          dp, loss_kind, a, b, n, pb, fdata, 43, bulk,
-          [](const double* d) { return PoseGraph3dErrorTerm(d); });
-  }
-  *handled = false;
-  return false;
+  if (type == 4)
+    return AddRunCommonLosses<RelativePoseError, 6, 7, 7>(
+        dp, loss_kind, a, b, n, pb, fdata, 7, bulk,
+        [](const double* d) { return RelativePoseError(d); });
+  return AddRunPose3d(dp, type, loss_kind, a, b, n, pb, fdata, bulk, handled);
 }
 }  // namespace driver

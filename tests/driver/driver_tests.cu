@@ -50,6 +50,10 @@ bool AddRunTests(DriverProblem& dp, int type, int loss_kind, double a, double b,
       return AddRunNoLoss<ParameterSensitiveCost, 2, 2>(
           dp, loss_kind, n, pb, fdata, 0, bulk,
           [](const double*) { return ParameterSensitiveCost(); });
+    case 17:
+      return AddRunNoLoss<SqrtOfConstantCost, 1, 1>(
+          dp, loss_kind, n, pb, fdata, 1, bulk,
+          [](const double* d) { return SqrtOfConstantCost(d[0]); });
     case 16:
       return AddRunNoLoss<JetBatteryCost, 40, 2>(
           dp, loss_kind, n, pb, fdata, 0, bulk, [](const double*) { return JetBatteryCost(); });

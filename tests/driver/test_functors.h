@@ -4,6 +4,7 @@
 #define TESTS_DRIVER_TEST_FUNCTORS_H_
 
 #include "ceres/internal/cuda_defs.h"
+#include "ceres/loss_function_cuda.h"
 #include "ceres/rotation.h"
 
 namespace test_functors {
@@ -75,6 +76,33 @@ struct OnlyFillsOneOutputFunctor {
     return true;
   }
   char unused = 0;
+};
+
+// <1, 1>  r = x + sqrt(T(c)): a constant sub-expression whose derivative the reference
+// computes as 0 * inf = NaN when c == 0 (tests/test_gpu_robustness.py).
+struct SqrtOfConstantCost {
+  HOST_DEVICE explicit SqrtOfConstantCost(double c) : c(c) {}
+  template <typename T>
+  HOST_DEVICE bool operator()(const T* x, T* residual) const {
+    residual[0] = x[0] + sqrt(T(c));
+    return true;
+  }
+  double c;
+};
+
+// A user-defined loss with positive curvature, rho(s) = s + a s^2: the only way into the
+// Corrector's alpha branch (corrector.cc:105-130); none of the library's losses has rho'' > 0.
+class ConvexTestLoss : public ceres::LossFunctionCUDABase {
+ public:
+  HOST_DEVICE explicit ConvexTestLoss(double a) : a_(a) {}
+  HOST_DEVICE void Evaluate(double s, double rho[3]) const {
+    rho[0] = s + a_ * s * s;
+    rho[1] = 1.0 + 2.0 * a_ * s;
+    rho[2] = 2.0 * a_;
+  }
+
+ private:
+  double a_;
 };
 
 // Autodiff form of evaluator_test.cc:59-100 ParameterIgnoringCostFunction:

@@ -104,3 +104,46 @@ out["jet_xy"] = xy; out["jet_battery"] = np.array(bat)
 np.savez_compressed(os.path.join(HERE, "reference_arith.npz"), **out)
 print("wrote", os.path.join(HERE, "reference_arith.npz"),
       {k: v.shape for k, v in out.items()})
+
+# ---- pose-graph functors (second file, so reference_arith.npz stays byte-identical):
+# RelativePoseError<6,7,7> (internal/ceres/autodiff_benchmarks/relative_pose_error.h:46-92) and
+# PoseGraph3dErrorTerm<6,3,4,3,4> (examples/slam/pose_graph_3d/pose_graph_3d_error_term.h:71-124)
+# compiled unmodified over oracle/eigen_shim/Eigen/{Core,Geometry}.
+pose = {}
+n = 192
+
+
+def unit_quats(k, spread=1.0):
+    q = rng.normal(0, 1, (k, 4))
+    q[:, 3] = np.abs(q[:, 3]) + spread          # (x, y, z, w), w > 0
+    return q / np.linalg.norm(q, axis=1, keepdims=True)
+
+
+pi = np.concatenate([unit_quats(n), rng.normal(0, 3, (n, 3))], axis=1)
+pj = np.concatenate([unit_quats(n), rng.normal(0, 3, (n, 3))], axis=1)
+pj[:8] = pi[:8]                                  # identical poses: relative rotation = identity
+pi[8:16, :4] *= rng.uniform(0.9, 1.1, (8, 1))    # slightly non-unit state quaternions
+meas = np.concatenate([unit_quats(n, 3.0), rng.normal(0, 1, (n, 3))], axis=1)
+meas[:8, :4] = [0, 0, 0, 1]                      # ... and identity measurement: theta = 0 branch
+res = np.zeros((n, 6)); ji = np.zeros((n, 42)); jj = np.zeros((n, 42))
+for i in range(n):
+    assert L.ref_relative_pose(p(pi[i]), p(pj[i]), p(meas[i]), p(res[i]), p(ji[i]), p(jj[i])) == 1
+pose.update(rp_pose_i=pi, rp_pose_j=pj, rp_meas=meas, rp_res=res, rp_jac_i=ji, rp_jac_j=jj)
+
+pa, pb = rng.normal(0, 3, (n, 3)), rng.normal(0, 3, (n, 3))
+qa, qb = unit_quats(n), unit_quats(n)
+data = np.zeros((n, 43))
+data[:, 0:3] = rng.normal(0, 1, (n, 3))
+data[:, 3:7] = unit_quats(n, 2.0)
+for i in range(n):
+    a = rng.normal(0, 1, (6, 6))
+    data[i, 7:] = np.linalg.cholesky(a @ a.T + 6 * np.eye(6)).T.ravel()   # a sqrt-information
+res = np.zeros((n, 6))
+j0 = np.zeros((n, 18)); j1 = np.zeros((n, 24)); j2 = np.zeros((n, 18)); j3 = np.zeros((n, 24))
+for i in range(n):
+    assert L.ref_pose_graph_3d(p(pa[i]), p(qa[i]), p(pb[i]), p(qb[i]), p(data[i]), p(res[i]),
+                               p(j0[i]), p(j1[i]), p(j2[i]), p(j3[i])) == 1
+pose.update(pg_p_a=pa, pg_q_a=qa, pg_p_b=pb, pg_q_b=qb, pg_data=data, pg_res=res,
+            pg_j0=j0, pg_j1=j1, pg_j2=j2, pg_j3=j3)
+np.savez_compressed(os.path.join(HERE, "reference_pose.npz"), **pose)
+print("wrote", os.path.join(HERE, "reference_pose.npz"), {k: v.shape for k, v in pose.items()})

@@ -329,6 +329,52 @@ def test_golden_reprojection_errors(name, cost_type, csize):
         assert np.max(np.abs(jp[i] - jp_ref[i])) <= 1e-12 * np.max(np.abs(jp_ref[i]))
 
 
+_GP = np.load(_os.path.join(_os.path.dirname(__file__), "golden", "reference_pose.npz"))
+
+
+def test_golden_relative_pose_error():
+    """RelativePoseError<6,7,7> on the device against the reference's own header
+    (internal/ceres/autodiff_benchmarks/relative_pose_error.h:46-92 over the Eigen shim)."""
+    n = _GP["rp_pose_i"].shape[0]
+    b = P.ProblemBuilder()
+    for i in range(n):
+        pi = b.add_parameter_block(_GP["rp_pose_i"][i])
+        pj = b.add_parameter_block(_GP["rp_pose_j"][i])
+        b.add_residual_block(P.RELATIVE_POSE, [pi, pj], _GP["rp_meas"][i])
+    cp = B.CudaProblem(b.build(), reduce=False)
+    ok, c, r, g, j = cp.evaluate()
+    assert ok
+    r = r.reshape(n, 6)
+    cell = j[:n * 84].reshape(n, 84)   # block sparse: cell of pose i, then of pose j (6 x 7 each)
+    for i in range(n):
+        scale = max(float(np.max(np.abs(_GP["rp_res"][i]))), 1.0)
+        assert np.max(np.abs(r[i] - _GP["rp_res"][i])) <= 1e-12 * scale
+        for got, want in ((cell[i, :42], _GP["rp_jac_i"][i]), (cell[i, 42:], _GP["rp_jac_j"][i])):
+            assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
+
+
+def test_golden_pose_graph_3d_error_term():
+    """PoseGraph3dErrorTerm<6,3,4,3,4> on the device against the reference's own header
+    (examples/slam/pose_graph_3d/pose_graph_3d_error_term.h:71-124 over the Eigen shim)."""
+    n = _GP["pg_p_a"].shape[0]
+    b = P.ProblemBuilder()
+    for i in range(n):
+        ids = [b.add_parameter_block(_GP[k][i]) for k in ("pg_p_a", "pg_q_a", "pg_p_b", "pg_q_b")]
+        b.add_residual_block(P.POSE_GRAPH_3D, ids, _GP["pg_data"][i])
+    cp = B.CudaProblem(b.build(), reduce=False)
+    ok, c, r, g, j = cp.evaluate()
+    assert ok
+    r = r.reshape(n, 6)
+    cell = j[:n * 84].reshape(n, 84)   # cells 6 x 3, 6 x 4, 6 x 3, 6 x 4 in block order
+    for i in range(n):
+        assert np.max(np.abs(r[i] - _GP["pg_res"][i])) <= 1e-12 * np.max(np.abs(_GP["pg_res"][i]))
+        at = 0
+        for name, width in (("pg_j0", 18), ("pg_j1", 24), ("pg_j2", 18), ("pg_j3", 24)):
+            want = _GP[name][i]
+            assert np.max(np.abs(cell[i, at:at + width] - want)) <= 1e-12 * np.max(np.abs(want))
+            at += width
+
+
 def test_golden_jet_operations_on_device():
     """Every Jet operation evaluated by the device Jet (ceres/jet.h of this repo) against
     the reference's jet.h; tolerance 1e-13 as in internal/ceres/jet_cuda_test.cu.cc:72-98."""
