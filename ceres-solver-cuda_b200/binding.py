@@ -23,7 +23,11 @@ ABI_SYMBOLS = [
     "cb200_engine_set_layout", "cb200_engine_set_shard", "cb200_engine_finalize",
     "cb200_nccl_unique_id", "cb200_engine_comm_init", "cb200_engine_evaluate",
     "cb200_engine_evaluate_device", "cb200_engine_device_ptr", "cb200_engine_shard_info",
-    "cb200_engine_last_timing", "cb200_engine_exchange_plan", "cb200_engine_jacobian_multiply",
+    "cb200_engine_last_timing", "cb200_engine_exchange_plan", "cb200_engine_exchange_mode",
+    "cb200_engine_state_upload", "cb200_engine_state_download", "cb200_engine_evaluate_state",
+    "cb200_engine_jacobi_scale", "cb200_engine_trust_region_step",
+    "cb200_engine_accept_candidate", "cb200_engine_gradient_max_norm",
+    "cb200_engine_jacobian_multiply",
     "cb200_engine_jacobian_squared_column_norm", "cb200_engine_jacobian_scale_columns",
     "cb200_engine_cgnr_solve", "cb200_host_alloc", "cb200_host_pin", "cb200_host_free",
     "cb200_version",
@@ -105,6 +109,7 @@ def driver():
         L.drv_timing.argtypes = [C.c_void_p, C.c_void_p]
         L.drv_shard_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.drv_callback_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.drv_exchange_mode.argtypes = [C.c_void_p]
         L.drv_exchange_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.drv_plus.argtypes = [C.c_void_p] * 4
         L.drv_plus_threads.argtypes = [C.c_void_p] * 4 + [C.c_int]
@@ -407,6 +412,10 @@ class CudaProblem:
         return {"rb_begin": int(info[0]), "rb_end": int(info[1]), "residual_begin": int(info[2]),
                 "residual_end": int(info[3]),
                 "segments": [tuple(int(x) for x in seg[3 * i:3 * i + 3]) for i in range(max(n, 0))]}
+
+    def exchange_mode(self):
+        """0: one rank; 1: NCCL all-reduce; 2: peer exchange fused into the evaluation kernel."""
+        return int(driver().drv_exchange_mode(self.h))
 
     def exchange_plan(self):
         """This rank's gradient exchange plan (several ranks): None when the structure only

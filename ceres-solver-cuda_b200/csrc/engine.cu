@@ -723,6 +723,107 @@ __global__ void __launch_bounds__(256) CgModelKernel(int n, const double* __rest
   FinishScalars<2>(red, v, S, slot);
 }
 
+// ---- trust-region vector kernels (state, step and diagonals resident in HBM)
+__global__ void __launch_bounds__(256) JacobiScaleKernel(int n, const double* __restrict__ colnorm,
+                                                         double* __restrict__ scale) {
+  // trust_region_minimizer.cc:259-275: 1 / (1 + sqrt(column norm^2))
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    scale[i] = 1.0 / (1.0 + sqrt(colnorm[i]));
+}
+__global__ void __launch_bounds__(256) ClampKernel(int n, const double* __restrict__ in, double lo,
+                                                   double hi, double* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = fmin(fmax(in[i], lo), hi);
+}
+__global__ void __launch_bounds__(256) DivideKernel(int n, const double* __restrict__ in,
+                                                    double divisor, double* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = in[i] / divisor;
+}
+// delta = -y * scale;  S[0] = |delta|^2
+__global__ void __launch_bounds__(256) StepKernel(int n, const double* __restrict__ y,
+                                                  const double* __restrict__ scale,
+                                                  double* __restrict__ delta, double* S,
+                                                  const ScalarReduce red) {
+  double acc = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double d = -y[i] * (scale ? scale[i] : 1.0);
+    delta[i] = d;
+    acc += d * d;
+  }
+  const double v[1] = {BlockSum(acc)};
+  const int slot[1] = {0};
+  FinishScalars<1>(red, v, S, slot);
+}
+__global__ void __launch_bounds__(256) SquaredNormKernel(int n, const double* __restrict__ x,
+                                                         double* S, const ScalarReduce red) {
+  double acc = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    acc += x[i] * x[i];
+  const double v[1] = {BlockSum(acc)};
+  const int slot[1] = {0};
+  FinishScalars<1>(red, v, S, slot);
+}
+// max |g|: non-negative doubles order like their bit patterns
+__global__ void __launch_bounds__(256) MaxAbsKernel(int n, const double* __restrict__ g,
+                                                    unsigned long long* out) {
+  double m = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    m = fmax(m, fabs(g[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, static_cast<unsigned long long>(__double_as_longlong(m)));
+}
+
+// Program::Plus (internal/ceres/program.cc:121-150): one thread per parameter block applies
+// x (+) delta for the manifolds the device knows (ceres/manifold.h of this repository:
+// SubsetManifold, (Eigen)QuaternionManifold and their products with Euclidean factors,
+// internal/ceres/manifold.cc:28-58,184-197).
+__device__ __forceinline__ void QuaternionPlusDevice(const double* x, const double* d, double* out,
+                                                     int kW, int kX, int kY, int kZ) {
+  const double norm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  if (norm == 0.0) {
+    for (int i = 0; i < 4; ++i) out[i] = x[i];
+    return;
+  }
+  const double k = sin(norm) / norm;
+  const double qw = cos(norm), qx = k * d[0], qy = k * d[1], qz = k * d[2];
+  const double xw = x[kW], xx = x[kX], xy = x[kY], xz = x[kZ];
+  out[kW] = qw * xw - qx * xx - qy * xy - qz * xz;
+  out[kX] = qw * xx + qx * xw + qy * xz - qz * xy;
+  out[kY] = qw * xy - qx * xz + qy * xw + qz * xx;
+  out[kZ] = qw * xz + qx * xy - qy * xx + qz * xw;
+}
+__global__ void __launch_bounds__(256) PlusKernel(int num_blocks, const int32_t* __restrict__ table,
+                                                  const double* __restrict__ state,
+                                                  const double* __restrict__ delta,
+                                                  double* __restrict__ out, int32_t* status) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < num_blocks;
+       b += gridDim.x * blockDim.x) {
+    const int4 r0 = __ldg(reinterpret_cast<const int4*>(table) + 2 * b);
+    const int4 r1 = __ldg(reinterpret_cast<const int4*>(table) + 2 * b + 1);
+    const int soff = r0.x, doff = r0.y, kind = r0.w, mparam = r1.x, size = r1.z;
+    const double* x = state + soff;
+    const double* d = delta + doff;
+    double* o = out + soff;
+    if (doff < 0) {  // constant block inside the program: unchanged
+      for (int i = 0; i < size; ++i) o[i] = x[i];
+    } else if (kind == CB200_MANIFOLD_NONE) {
+      for (int i = 0; i < size; ++i) o[i] = x[i] + d[i];
+    } else if (kind == CB200_MANIFOLD_SUBSET) {
+      int j = 0;
+      for (int i = 0; i < size; ++i) o[i] = ((mparam >> i) & 1) ? x[i] : x[i] + d[j++];
+    } else if (kind == CB200_MANIFOLD_QUATERNION_TAIL) {
+      QuaternionPlusDevice(x, d, o, 0, 1, 2, 3);
+      for (int i = 4; i < size; ++i) o[i] = x[i] + d[i - 1];
+    } else if (kind == CB200_MANIFOLD_EIGEN_QUATERNION_TAIL) {
+      QuaternionPlusDevice(x, d, o, 3, 0, 1, 2);
+      for (int i = 4; i < size; ++i) o[i] = x[i] + d[i - 1];
+    } else {
+      *status = 1;
+    }
+  }
+}
+
 }  // namespace
 
 struct cb200_engine {
@@ -785,6 +886,11 @@ struct cb200_engine {
   DeviceBuffer<double> la_partials; // per-thread-block partial sums of the scalar reductions
   DeviceBuffer<unsigned> la_arrivals;
   double* h_la_scalars = nullptr;   // pinned, 3 x kSCount
+  // trust-region state resident in HBM: accepted state and candidate, Jacobi scale, LM
+  // diagonal, step
+  DeviceBuffer<double> tr_state[2], tr_scale, tr_diagonal, tr_delta;
+  bool tr_state_valid = false, tr_scale_valid = false, tr_diagonal_valid = false;
+  bool plus_on_device = true;       // every manifold of the program is one PlusKernel knows
 
   void* comm = nullptr;
   double timing[4] = {0, 0, 0, 0};
@@ -859,6 +965,8 @@ void cb200_engine_destroy(cb200_engine* e) {
   }
   for (auto& b : e->la_col) b.Free();
   e->la_row.Free(); e->la_scalars.Free(); e->la_partials.Free(); e->la_arrivals.Free();
+  for (auto& b : e->tr_state) b.Free();
+  e->tr_scale.Free(); e->tr_diagonal.Free(); e->tr_delta.Free();
   if (e->h_la_scalars) cudaFreeHost(e->h_la_scalars);
   e->d_chunks.Free(); e->d_arrivals.Free();
   for (int r = 0; r < kMaxRanks; ++r)
@@ -971,6 +1079,8 @@ int cb200_engine_finalize(cb200_engine* e) {
     table[8 * i + 3] = constant ? CB200_MANIFOLD_NONE : b.manifold_kind;
     table[8 * i + 4] = b.manifold_param;
     table[8 * i + 5] = constant ? -1 : b.plus_jacobian_offset;
+    table[8 * i + 6] = b.size;
+    if (!constant && b.manifold_kind == CB200_MANIFOLD_GENERIC) e->plus_on_device = false;
   }
 
   // Gradient exchange plan.  After a Schur ordering the residual blocks of one point
@@ -1778,19 +1888,23 @@ int cb200_engine_jacobian_scale_columns(cb200_engine* e, const double* scale) {
   return CB200_OK;
 }
 
-int cb200_engine_cgnr_solve(cb200_engine* e, const double* d_squared,
-                            const cb200_cgnr_options* options, double* solution,
-                            cb200_cgnr_summary* summary) {
+// The solve itself.  d_squared: host pointer (copied in), or with d_squared_on_device the
+// LM diagonal already in la_col[6]; the solution stays in la_col[0] and is copied to
+// `solution` when that is not NULL.
+static int CgnrSolve(cb200_engine* e, const double* d_squared, bool d_squared_on_device,
+                     const cb200_cgnr_options* options, double* solution,
+                     cb200_cgnr_summary* summary) {
   int rc = PrepareLinearAlgebra(e, true);
   if (rc != CB200_OK) return rc;
-  if (!options || !solution || !summary)
-    return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "options, solution and summary are required");
+  if (!options || !summary)
+    return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "options and summary are required");
   cudaStream_t s = e->stream;
   const int ne = e->num_effective, m = e->res_end - e->res_begin;
   const size_t col_bytes = static_cast<size_t>(ne) * sizeof(double);
   double *x = e->la_col[0].ptr, *r = e->la_col[1].ptr, *p = e->la_col[2].ptr,
          *q = e->la_col[3].ptr, *b = e->la_col[4].ptr, *minv = e->la_col[5].ptr,
-         *d2 = d_squared ? e->la_col[6].ptr : nullptr, *colnorm = e->la_col[7].ptr;
+         *d2 = (d_squared || d_squared_on_device) ? e->la_col[6].ptr : nullptr,
+         *colnorm = e->la_col[7].ptr;
   double* w = e->la_row.ptr;
   const double* residuals = e->d_residuals.ptr;
   double* S = e->la_scalars.ptr;  // three rotating sets of scalars
@@ -1803,7 +1917,8 @@ int cb200_engine_cgnr_solve(cb200_engine* e, const double* d_squared,
     if (t->n_local > 0 && t->desc.num_residuals > kNormalRows) one_pass = false;
 
   CB200_CUDA(e, cudaEventRecord(e->ev[0], s));
-  if (d2) CB200_CUDA(e, cudaMemcpyAsync(d2, d_squared, col_bytes, cudaMemcpyHostToDevice, s));
+  if (d2 && !d_squared_on_device)
+    CB200_CUDA(e, cudaMemcpyAsync(d2, d_squared, col_bytes, cudaMemcpyHostToDevice, s));
   // b = J' residuals, preconditioner from the column norms
   CB200_CUDA(e, cudaMemsetAsync(b, 0, col_bytes, s));
   CB200_CUDA(e, cudaMemsetAsync(colnorm, 0, col_bytes, s));
@@ -1878,7 +1993,8 @@ int cb200_engine_cgnr_solve(cb200_engine* e, const double* d_squared,
   }
   CB200_CUDA(e, cudaMemcpyAsync(e->h_la_scalars, Sm, kSCount * sizeof(double),
                                 cudaMemcpyDeviceToHost, s));
-  CB200_CUDA(e, cudaMemcpyAsync(solution, x, col_bytes, cudaMemcpyDeviceToHost, s));
+  if (solution)
+    CB200_CUDA(e, cudaMemcpyAsync(solution, x, col_bytes, cudaMemcpyDeviceToHost, s));
   CB200_CUDA(e, cudaEventRecord(e->ev[4], s));
   CB200_CUDA(e, cudaStreamSynchronize(s));
   summary->jy_dot_b = e->h_la_scalars[kSJyB];
@@ -1886,6 +2002,161 @@ int cb200_engine_cgnr_solve(cb200_engine* e, const double* d_squared,
   float ms = 0;
   cudaEventElapsedTime(&ms, e->ev[0], e->ev[4]);
   summary->solve_ms = ms;
+  return CB200_OK;
+}
+
+int cb200_engine_cgnr_solve(cb200_engine* e, const double* d_squared,
+                            const cb200_cgnr_options* options, double* solution,
+                            cb200_cgnr_summary* summary) {
+  if (e && !solution) return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "solution is required");
+  return CgnrSolve(e, d_squared, false, options, solution, summary);
+}
+
+// ---- the trust-region iteration without the host: the state, the
+// step and the LM / Jacobi diagonals live in HBM between iterations.
+static int PrepareTrustRegion(cb200_engine* e) {
+  if (!e) return CB200_ERROR_INVALID_ARGUMENT;
+  if (!e->finalized) return e->Fail(CB200_ERROR_NOT_FINALIZED, "not finalized");
+  if (e->planning) return e->Fail(CB200_ERROR_CUDA, "planning-only engine: no device, no CPU fallback");
+  CB200_CUDA(e, cudaSetDevice(e->device));
+  for (auto& b : e->tr_state) CB200_CUDA(e, b.Resize(static_cast<size_t>(e->num_parameters) + 4));
+  CB200_CUDA(e, e->tr_scale.Resize(static_cast<size_t>(e->num_effective) + 1));
+  CB200_CUDA(e, e->tr_diagonal.Resize(static_cast<size_t>(e->num_effective) + 1));
+  CB200_CUDA(e, e->tr_delta.Resize(static_cast<size_t>(e->num_effective) + 1));
+  return CB200_OK;
+}
+
+int cb200_engine_state_upload(cb200_engine* e, const double* state) {
+  int rc = PrepareTrustRegion(e);
+  if (rc != CB200_OK) return rc;
+  if (!state) return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "state is required");
+  CB200_CUDA(e, cudaMemcpyAsync(e->tr_state[0].ptr, state, sizeof(double) * e->num_parameters,
+                                cudaMemcpyHostToDevice, e->stream));
+  CB200_CUDA(e, cudaStreamSynchronize(e->stream));
+  e->tr_state_valid = true;
+  return CB200_OK;
+}
+
+int cb200_engine_state_download(cb200_engine* e, int which, double* state) {
+  int rc = PrepareTrustRegion(e);
+  if (rc != CB200_OK) return rc;
+  if (!state || which < 0 || which > 1 || !e->tr_state_valid)
+    return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "state_download: no such state");
+  CB200_CUDA(e, cudaMemcpyAsync(state, e->tr_state[which].ptr, sizeof(double) * e->num_parameters,
+                                cudaMemcpyDeviceToHost, e->stream));
+  CB200_CUDA(e, cudaStreamSynchronize(e->stream));
+  return CB200_OK;
+}
+
+int cb200_engine_evaluate_state(cb200_engine* e, int which, uint32_t flags, int want_residuals,
+                                int want_gradient, int want_jacobian, double* cost) {
+  int rc = PrepareTrustRegion(e);
+  if (rc != CB200_OK) return rc;
+  if (which < 0 || which > 1 || !e->tr_state_valid)
+    return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "evaluate_state: upload a state first");
+  if (e->plus_pool > 0)
+    return e->Fail(CB200_ERROR_INVALID_ARGUMENT,
+                   "evaluate_state: a manifold needs host plus-Jacobians (use cb200_engine_evaluate)");
+  return cb200_engine_evaluate_device(e, e->tr_state[which].ptr, nullptr, flags, want_residuals,
+                                      want_gradient, want_jacobian, cost);
+}
+
+int cb200_engine_accept_candidate(cb200_engine* e) {
+  if (!e || !e->tr_state_valid) return CB200_ERROR_INVALID_ARGUMENT;
+  std::swap(e->tr_state[0], e->tr_state[1]);
+  return CB200_OK;
+}
+
+int cb200_engine_jacobi_scale(cb200_engine* e, int compute) {
+  int rc = PrepareLinearAlgebra(e, false);
+  if (rc == CB200_OK) rc = PrepareTrustRegion(e);
+  if (rc != CB200_OK) return rc;
+  cudaStream_t s = e->stream;
+  const int ne = e->num_effective;
+  const int grid = std::max(1, std::min((ne + 255) / 256, kMaxVectorGrid));
+  if (compute) {
+    double* col = e->la_col[7].ptr;
+    CB200_CUDA(e, cudaMemsetAsync(col, 0, static_cast<size_t>(ne) * sizeof(double), s));
+    if ((rc = RunJacobianWalk(e, kOpColumnNorm, nullptr, col)) != CB200_OK) return rc;
+    if ((rc = SumOverRanks(e, col, ne)) != CB200_OK) return rc;
+    JacobiScaleKernel<<<grid, 256, 0, s>>>(ne, col, e->tr_scale.ptr);
+    e->tr_scale_valid = true;
+  }
+  if (!e->tr_scale_valid)
+    return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "jacobi_scale: no scale computed yet");
+  if ((rc = RunJacobianWalk(e, kOpScale, e->tr_scale.ptr, nullptr)) != CB200_OK) return rc;
+  CB200_CUDA(e, cudaStreamSynchronize(s));
+  return CB200_OK;
+}
+
+int cb200_engine_trust_region_step(cb200_engine* e, const cb200_step_options* options,
+                                   cb200_step_summary* summary) {
+  int rc = PrepareLinearAlgebra(e, true);
+  if (rc == CB200_OK) rc = PrepareTrustRegion(e);
+  if (rc != CB200_OK) return rc;
+  if (!options || !summary || !e->tr_state_valid)
+    return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "trust_region_step: options, summary and an "
+                                                 "uploaded state are required");
+  if (!e->plus_on_device)
+    return e->Fail(CB200_ERROR_INVALID_ARGUMENT,
+                   "trust_region_step: a parameter block has a manifold the device cannot apply");
+  cudaStream_t s = e->stream;
+  const int ne = e->num_effective;
+  const int grid = std::max(1, std::min((ne + 255) / 256, kMaxVectorGrid));
+  std::memset(summary, 0, sizeof(*summary));
+  // LM diagonal (levenberg_marquardt_strategy.cc:83-96): clamp(diag(J'J)) / radius
+  if (!options->reuse_diagonal || !e->tr_diagonal_valid) {
+    double* col = e->la_col[7].ptr;
+    CB200_CUDA(e, cudaMemsetAsync(col, 0, static_cast<size_t>(ne) * sizeof(double), s));
+    if ((rc = RunJacobianWalk(e, kOpColumnNorm, nullptr, col)) != CB200_OK) return rc;
+    if ((rc = SumOverRanks(e, col, ne)) != CB200_OK) return rc;
+    ClampKernel<<<grid, 256, 0, s>>>(ne, col, options->min_lm_diagonal, options->max_lm_diagonal,
+                                     e->tr_diagonal.ptr);
+    e->tr_diagonal_valid = true;
+  }
+  DivideKernel<<<grid, 256, 0, s>>>(ne, e->tr_diagonal.ptr, options->radius, e->la_col[6].ptr);
+  if ((rc = CgnrSolve(e, nullptr, true, &options->cg, nullptr, &summary->cg)) != CB200_OK) return rc;
+  // step = -y (times the Jacobi scale); |step|, |x|; candidate = x (+) step
+  const ScalarReduce red{e->la_partials.ptr, e->la_arrivals.ptr};
+  double* S = e->la_scalars.ptr;
+  StepKernel<<<grid, 256, 0, s>>>(ne, e->la_col[0].ptr,
+                                  e->tr_scale_valid ? e->tr_scale.ptr : nullptr, e->tr_delta.ptr, S,
+                                  red);
+  const int np = e->num_parameters;
+  const int pgrid = std::max(1, std::min((np + 255) / 256, kMaxVectorGrid));
+  SquaredNormKernel<<<pgrid, 256, 0, s>>>(np, e->tr_state[0].ptr, S + 1, red);
+  const int bgrid = std::max(1, std::min((e->num_active + 255) / 256, 148 * 16));
+  CB200_CUDA(e, cudaMemsetAsync(e->d_status.ptr, 0, sizeof(int32_t), s));
+  PlusKernel<<<bgrid, 256, 0, s>>>(e->num_active, e->d_pb_table.ptr, e->tr_state[0].ptr,
+                                   e->tr_delta.ptr, e->tr_state[1].ptr, e->d_status.ptr);
+  CB200_CUDA(e, cudaMemcpyAsync(e->h_la_scalars, S, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CB200_CUDA(e, cudaMemcpyAsync(e->h_la_scalars + 2, e->d_status.ptr, sizeof(int32_t),
+                                cudaMemcpyDeviceToHost, s));
+  CB200_CUDA(e, cudaStreamSynchronize(s));
+  int32_t bad = 0;
+  std::memcpy(&bad, e->h_la_scalars + 2, sizeof(bad));
+  summary->step_norm = std::sqrt(e->h_la_scalars[0]);
+  summary->state_norm = std::sqrt(e->h_la_scalars[1]);
+  summary->plus_ok = bad == 0;
+  // step = -y: model cost change = (J y).r - |J y|^2 / 2
+  summary->model_cost_change = summary->cg.jy_dot_b - 0.5 * summary->cg.jy_squared_norm;
+  return CB200_OK;
+}
+
+int cb200_engine_gradient_max_norm(cb200_engine* e, double* out) {
+  if (!e || !out) return CB200_ERROR_INVALID_ARGUMENT;
+  if (!e->finalized || e->planning) return e->Fail(CB200_ERROR_NOT_FINALIZED, "no device state");
+  int rc = PrepareLinearAlgebra(e, false);
+  if (rc != CB200_OK) return rc;
+  cudaStream_t s = e->stream;
+  const int ne = e->num_effective;
+  const int grid = std::max(1, std::min((ne + 255) / 256, kMaxVectorGrid));
+  unsigned long long* slot = reinterpret_cast<unsigned long long*>(e->la_scalars.ptr + 2);
+  CB200_CUDA(e, cudaMemsetAsync(slot, 0, sizeof(*slot), s));
+  MaxAbsKernel<<<grid, 256, 0, s>>>(ne, e->gradcost, slot);
+  CB200_CUDA(e, cudaMemcpyAsync(e->h_la_scalars, slot, sizeof(double), cudaMemcpyDeviceToHost, s));
+  CB200_CUDA(e, cudaStreamSynchronize(s));
+  *out = e->h_la_scalars[0];
   return CB200_OK;
 }
 
@@ -1919,6 +2190,11 @@ int cb200_engine_exchange_plan(cb200_engine* e, int32_t* chunks, int32_t max_chu
   }
   if (shared_count) *shared_count = e->shared_count;
   return n;
+}
+
+int cb200_engine_exchange_mode(cb200_engine* e) {
+  if (!e || e->world <= 1) return 0;
+  return e->peer_ready ? 2 : 1;
 }
 
 int cb200_engine_last_timing(cb200_engine* e, double* out4) {

@@ -201,6 +201,161 @@ std::string Solver::Summary::FullReport() const {
   return buf;
 }
 
+// The trust-region loop with state, step, gradient and diagonals resident in HBM
+// (cb200_engine_trust_region_step and friends, include/ceres_b200.h): per iteration the host
+// reads a handful of scalars.  Same decisions as the host loop below
+// (trust_region_minimizer.cc step acceptance, levenberg_marquardt_strategy.cc radius update).
+// Returns false when the program needs the host loop (bounds, a manifold only the host knows,
+// an EvaluationCallback that must see the parameter blocks).
+namespace {
+bool DeviceLoopPossible(const Solver::Options& options, const internal::Program& program,
+                        const internal::ProblemImpl& problem) {
+  if (std::getenv("CB200_HOST_TRUST_REGION")) return false;
+  if (problem.options().evaluation_callback != nullptr) return false;
+  for (const internal::ParameterBlock* pb : program.parameter_blocks()) {
+    if (pb->lower_bounds || pb->upper_bounds) return false;
+    int kind = 0, param = 0;
+    if (pb->manifold && !pb->manifold->DeviceDescription(&kind, &param)) return false;
+  }
+  return true;
+}
+
+void MinimizeOnDevice(const Solver::Options& options, cb200_engine* engine, double fixed_cost,
+                      double start, double* x, Solver::Summary* summary) {
+  auto fail = [&](const char* what) {
+    summary->termination_type = FAILURE;
+    summary->message = std::string(what) + ": " + cb200_engine_last_error(engine);
+  };
+  const uint32_t kLoss = CB200_APPLY_LOSS_FUNCTION;
+  double evaluation_seconds[2] = {0.0, 0.0};
+  int evaluation_calls[2] = {0, 0};
+  auto evaluate = [&](int which, bool jacobian, double* cost) {
+    const double t0 = Seconds();
+    const int rc = cb200_engine_evaluate_state(
+        engine, which, kLoss | CB200_KEEP_JACOBIAN_ON_DEVICE | CB200_KEEP_RESIDUALS_ON_DEVICE,
+        jacobian, jacobian, jacobian, cost);
+    evaluation_seconds[jacobian] += Seconds() - t0;
+    ++evaluation_calls[jacobian];
+    return rc;
+  };
+  double cost = 0.0;
+  if (cb200_engine_state_upload(engine, x) != CB200_OK) return fail("cb200_engine_state_upload");
+  int rc = evaluate(0, true, &cost);
+  if (rc != CB200_OK) {
+    summary->message = "Initial residual and Jacobian evaluation failed.";
+    if (rc < 0) fail("cb200_engine_evaluate_state");
+    return;
+  }
+  summary->initial_cost = cost + fixed_cost;
+  if (options.jacobi_scaling && cb200_engine_jacobi_scale(engine, 1) != CB200_OK)
+    return fail("cb200_engine_jacobi_scale");
+  double radius = options.initial_trust_region_radius, decrease_factor = 2.0;
+  bool reuse_diagonal = false;
+  summary->termination_type = NO_CONVERGENCE;
+  summary->message = "Maximum number of iterations reached.";
+  if (options.minimizer_progress_to_stdout)
+    std::printf("iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius  ls_iter\n"
+                "%4d  %.6e    %.2e   %.2e   %.2e  %.2e  %.2e   %5d\n",
+                0, cost + fixed_cost, 0.0, 0.0, 0.0, 0.0, radius, 0);
+  for (int it = 1; it <= options.max_num_iterations; ++it) {
+    if (Seconds() - start > options.max_solver_time_in_seconds) {
+      summary->message = "Maximum solver time reached.";
+      break;
+    }
+    cb200_step_options so{};
+    so.radius = radius;
+    so.min_lm_diagonal = options.min_lm_diagonal;
+    so.max_lm_diagonal = options.max_lm_diagonal;
+    so.reuse_diagonal = reuse_diagonal;
+    so.cg.min_num_iterations = options.min_linear_solver_iterations;
+    so.cg.max_num_iterations = options.max_linear_solver_iterations;
+    so.cg.r_tolerance = -1.0;
+    so.cg.q_tolerance = options.eta;  // levenberg_marquardt_strategy.cc:97-118
+    cb200_step_summary ss;
+    const double ls_start = Seconds();
+    if (cb200_engine_trust_region_step(engine, &so, &ss) != CB200_OK) {
+      fail("cb200_engine_trust_region_step");
+      break;
+    }
+    summary->linear_solver_time_in_seconds += Seconds() - ls_start;
+    Solver::IterationSummary is;
+    is.iteration = it;
+    is.linear_solver_iterations = ss.cg.num_iterations;
+    is.step_norm = ss.step_norm;
+    double new_cost = 0.0;
+    bool ok = ss.cg.termination != 2 && ss.model_cost_change > 0.0 && ss.plus_ok;
+    if (ok) {
+      rc = evaluate(1, false, &new_cost);
+      if (rc < 0) { fail("cb200_engine_evaluate_state"); break; }
+      ok = rc == CB200_OK;
+    }
+    const double relative_decrease = ok ? (cost - new_cost) / ss.model_cost_change : -1.0;
+    is.relative_decrease = relative_decrease;
+    if (ok && relative_decrease > options.min_relative_decrease) {
+      is.step_is_successful = true;
+      is.cost_change = cost - new_cost;
+      cb200_engine_accept_candidate(engine);
+      rc = evaluate(0, true, &cost);
+      if (rc != CB200_OK) {
+        summary->termination_type = FAILURE;
+        summary->message = "Residual and Jacobian evaluation failed.";
+        break;
+      }
+      if (options.jacobi_scaling && cb200_engine_jacobi_scale(engine, 0) != CB200_OK) {
+        fail("cb200_engine_jacobi_scale");
+        break;
+      }
+      radius = std::min(options.max_trust_region_radius,
+                        radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * relative_decrease - 1.0, 3)));
+      decrease_factor = 2.0;
+      reuse_diagonal = false;
+      ++summary->num_successful_steps;
+    } else {
+      radius /= decrease_factor;
+      decrease_factor *= 2.0;
+      reuse_diagonal = true;
+      ++summary->num_unsuccessful_steps;
+    }
+    double gmax = 0.0;
+    cb200_engine_gradient_max_norm(engine, &gmax);
+    is.cost = cost + fixed_cost;
+    is.gradient_max_norm = gmax;
+    is.trust_region_radius = radius;
+    summary->iterations.push_back(is);
+    if (options.minimizer_progress_to_stdout)
+      std::printf("%4d  %.6e    %.2e   %.2e   %.2e  %.2e  %.2e   %5d\n", it, is.cost, is.cost_change,
+                  gmax, ss.step_norm, relative_decrease, radius, ss.cg.num_iterations);
+    if (is.step_is_successful) {
+      if (std::fabs(is.cost_change) <= options.function_tolerance * cost) {
+        summary->termination_type = CONVERGENCE;
+        summary->message = "Function tolerance reached.";
+        break;
+      }
+      if (gmax <= options.gradient_tolerance) {
+        summary->termination_type = CONVERGENCE;
+        summary->message = "Gradient tolerance reached.";
+        break;
+      }
+      if (ss.step_norm <= options.parameter_tolerance * (ss.state_norm + options.parameter_tolerance)) {
+        summary->termination_type = CONVERGENCE;
+        summary->message = "Parameter tolerance reached.";
+        break;
+      }
+    } else if (radius < options.min_trust_region_radius) {
+      summary->termination_type = CONVERGENCE;
+      summary->message = "Minimum trust region radius reached.";
+      break;
+    }
+  }
+  cb200_engine_state_download(engine, 0, x);
+  summary->final_cost = cost + fixed_cost;
+  summary->residual_evaluation_time_in_seconds = evaluation_seconds[0];
+  summary->num_residual_evaluations = evaluation_calls[0];
+  summary->jacobian_evaluation_time_in_seconds = evaluation_seconds[1];
+  summary->num_jacobian_evaluations = evaluation_calls[1];
+}
+}  // namespace
+
 void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
   const double start = Seconds();
   *summary = Summary();
@@ -291,6 +446,13 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
   if (!resident) {
     residuals.resize(m);
     model.resize(m);
+  }
+  if (resident && DeviceLoopPossible(options, *program, *impl)) {
+    MinimizeOnDevice(options, resident->engine(), fixed_cost, start, x.data(), summary);
+    program->StateVectorToParameterBlocks(x.data());  // results back into the user's arrays
+    summary->minimizer_time_in_seconds = Seconds() - minimizer_start;
+    summary->total_time_in_seconds = Seconds() - start;
+    return;
   }
   double* const residuals_out = resident ? nullptr : residuals.data();
   double cost = 0.0;

@@ -304,6 +304,48 @@ int cb200_engine_cgnr_solve(cb200_engine* engine, const double* d_squared,
                             const cb200_cgnr_options* options, double* solution,
                             cb200_cgnr_summary* summary);
 
+/* ---- the trust-region iteration with the state in HBM.
+ * Replaces, for CGNR + CUDA_SPARSE, what TrustRegionMinimizer does on the host around the
+ * evaluator (internal/ceres/trust_region_minimizer.cc:246-275,518,780): Jacobi scaling
+ * (SquaredColumnNorm / ScaleColumns), the LM diagonal (levenberg_marquardt_strategy.cc:83-96),
+ * the linear solve, Program::Plus (program.cc:121-150, manifolds of manifold.cc:28-58,184-197)
+ * and the step / state / gradient norms.  Per iteration only a few scalars cross PCIe.
+ * State slot 0 is the accepted state, slot 1 the candidate x (+) step. */
+typedef struct cb200_step_options {
+  double radius;            /* LM diagonal = clamp(diag(J'J), min, max) / radius */
+  double min_lm_diagonal;
+  double max_lm_diagonal;
+  int32_t reuse_diagonal;   /* keep diag(J'J) of the last accepted point (step was rejected) */
+  cb200_cgnr_options cg;
+} cb200_step_options;
+
+typedef struct cb200_step_summary {
+  cb200_cgnr_summary cg;
+  double model_cost_change; /* (J y).r - |J y|^2 / 2 for the step -y */
+  double step_norm;         /* |delta| in the parameters' scale */
+  double state_norm;        /* |x| */
+  int32_t plus_ok;          /* 0: a block has a manifold only the host can apply */
+} cb200_step_summary;
+
+int cb200_engine_state_upload(cb200_engine* engine, const double* state);
+int cb200_engine_state_download(cb200_engine* engine, int which, double* state);
+/* cb200_engine_evaluate_device at state slot `which` (no host plus-Jacobians: every manifold
+ * must be one the kernel applies by itself). */
+int cb200_engine_evaluate_state(cb200_engine* engine, int which, uint32_t flags,
+                                int want_residuals, int want_gradient, int want_jacobian,
+                                double* cost);
+/* compute != 0: scale = 1 / (1 + sqrt(diag(J'J))) of the resident Jacobian, kept in HBM; then
+ * (always) J <- J diag(scale). */
+int cb200_engine_jacobi_scale(cb200_engine* engine, int compute);
+/* LM diagonal, conjugate gradients, step = -y * scale, candidate = state (+) step. */
+int cb200_engine_trust_region_step(cb200_engine* engine, const cb200_step_options* options,
+                                   cb200_step_summary* summary);
+int cb200_engine_accept_candidate(cb200_engine* engine); /* candidate becomes the state */
+int cb200_engine_gradient_max_norm(cb200_engine* engine, double* max_norm);
+/* 0: one rank; 1: NCCL all-reduce of [gradient | cost | failed]; 2: peer exchange fused into
+ * the evaluation kernel (cb200_engine_exchange_plan). */
+int cb200_engine_exchange_mode(cb200_engine* engine);
+
 /* Timing of the last evaluation in milliseconds (CUDA events on the engine's
  * stream): out[0] kernels only, out[1] kernels + reductions + all-reduce,
  * out[2] whole call including host<->device copies.  out[3] = kernel launches. */

@@ -55,7 +55,14 @@ for fmt, kw in ((0, {}), (1, {"subset_manifold": True})):
           f"({s1['ms'] / 30:.3f} ms/iteration sharded, {s0['ms'] / 30:.3f} unsharded) "
           f"{'OK' if e_la <= 1e-11 and e_cg <= 1e-8 else 'MISMATCH'}", flush=True)
     t = sh.timing()
-    print(f"rank {rank}/{world} fmt {fmt}: cost {e_cost:.1e} grad {e_grad:.1e} res {e_res:.1e} jac {e_jac:.1e} "
+    mode = {0: "single", 1: "nccl all-reduce", 2: "peer exchange"}[sh.exchange_mode()]
+    # the other output combinations take the unfused path (PushExclusiveKernel)
+    ok2, c2, r2, g2, _ = sh.evaluate(x, jacobian=False)
+    e_grad = max(e_grad, np.max(np.abs(g2 - g0)) / np.max(np.abs(g0)))
+    ok3, c3, *_ = sh.evaluate(x, gradient=False, jacobian=False)
+    e_cost = max(e_cost, abs(c2 - c0) / abs(c0), abs(c3 - c0) / abs(c0))
+    print(f"rank {rank}/{world} fmt {fmt}: exchange = {mode}; "
+          f"cost {e_cost:.1e} grad {e_grad:.1e} res {e_res:.1e} jac {e_jac:.1e} "
           f"segments {len(info['segments'])} kernel {t['kernel_ms']:.3f} device {t['device_ms']:.3f} ms "
           f"{'OK' if max(e_cost, e_grad) <= 1e-10 and max(e_res, e_jac) <= 1e-12 else 'MISMATCH'}", flush=True)
     full.close(); sh.close()

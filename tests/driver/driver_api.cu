@@ -382,6 +382,11 @@ int drv_shard_info(void* h, int32_t* info4, int64_t* segments, int max_segments)
                                  segments, max_segments);
 }
 
+int drv_exchange_mode(void* h) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  return dp->evaluator ? cb200_engine_exchange_mode(dp->evaluator->engine()) : -1;
+}
+
 int drv_exchange_plan(void* h, int32_t* chunks, int max_chunks, int64_t* exclusive,
                       int32_t* shared_count) {
   auto* dp = static_cast<DriverProblem*>(h);

@@ -112,6 +112,31 @@ def test_device_resident_solve_reaches_the_exact_solve_cost(subset_manifold):
     assert abs(out["final_cost"] - host["final_cost"]) <= 0.02 * host["final_cost"]
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["bal", "bal_subset", "pose_graph"])
+def test_trust_region_loop_on_the_device_matches_the_host_loop(kind, monkeypatch):
+    """With CGNR + CUDA_SPARSE the whole iteration runs in HBM (cb200_engine_trust_region_step:
+    LM diagonal, conjugate gradients, Program::Plus with the manifolds, norms).  The host loop
+    around the same device Jacobian (CB200_HOST_TRUST_REGION=1: Plus, diagonals and norms on
+    the host, state and step over PCIe) must take the same steps."""
+    if kind == "pose_graph":
+        spec = P.pose_graph_problem(120, 420, seed=8)     # EigenQuaternion x R^3 Plus, pose 0 fixed
+    else:
+        spec = P.bal_problem(12, 600, 2600, seed=33, subset_manifold=kind == "bal_subset")
+        rng = np.random.default_rng(33)
+        spec.pb_values[:] += rng.normal(0, 0.02, spec.pb_values.size) * (np.abs(spec.pb_values) < 50)
+    dev = B.solve(spec, B.CGNR, max_num_iterations=12, cuda_sparse=True)
+    monkeypatch.setenv("CB200_HOST_TRUST_REGION", "1")
+    host = B.solve(spec, B.CGNR, max_num_iterations=12, cuda_sparse=True)
+    assert dev["usable"] and host["usable"], (dev["message"], host["message"])
+    assert dev["iterations"] == host["iterations"]
+    assert dev["successful_steps"] == host["successful_steps"]
+    assert abs(dev["initial_cost"] - host["initial_cost"]) <= 1e-12 * host["initial_cost"]
+    assert abs(dev["final_cost"] - host["final_cost"]) <= 1e-7 * host["final_cost"]
+    assert np.max(np.abs(dev["x"] - host["x"])) <= 1e-6 * np.max(np.abs(host["x"]))
+    assert dev["final_cost"] < 0.9 * dev["initial_cost"]
+
+
 def test_abi_exports_the_linear_algebra_entry_points():
     lib = B.abi()
     for name in ("cb200_engine_jacobian_multiply", "cb200_engine_jacobian_squared_column_norm",
