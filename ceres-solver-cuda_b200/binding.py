@@ -208,11 +208,12 @@ class CudaProblem:
 
     def __init__(self, spec, jacobian_format=0, reduce=True, schur_reorder=False,
                  num_eliminate_blocks=None, with_device=True, device=0, rank=0, world_size=1,
-                 nccl_id: bytes | None = None, bulk=None):
+                 nccl_id: bytes | None = None, bulk=None, evaluation_callback=False):
         L = driver()
         self.spec = spec
         if bulk is None:
             bulk = spec.num_rb > 5000
+        bulk = int(bool(bulk)) | (2 if evaluation_callback else 0)
         self.h = L.drv_create(
             spec.num_pb, _p(spec.pb_size), _p(spec.pb_values), _p(spec.pb_constant),
             _p(spec.pb_manifold_kind), _p(spec.pb_manifold_param), spec.num_rb,

@@ -1159,7 +1159,12 @@ int cb200_engine_finalize(cb200_engine* e) {
       // contiguous range touched by no other chunk.  A cut between consecutive parameter
       // blocks i, i + 1 of the exclusive range is valid at residual block position
       // min(first[i + 1 ...]) iff every block up to i was last touched before it.
-      constexpr int kChunkBlocks = 768;  // six tiles of 128: ~8 chunks per thread block on L x 8
+      // A chunk is a warp's unit of work (tiles of 32 blocks, one fence and one copy at its
+      // end): about 8 chunks per warp of a full persistent grid (148 SMs x 12 warps) keeps
+      // the warps balanced, 128..2048 blocks bounds the overhead of partial tiles and fences.
+      const int64_t local_blocks = nrb * (e->rank + 1) / e->world - nrb * e->rank / e->world;
+      const int kChunkBlocks = static_cast<int>(
+          std::min<int64_t>(2048, std::max<int64_t>(128, local_blocks / (148 * 12 * 8) / 32 * 32)));
       int i0 = -1, i1 = -1;  // active blocks [i0, i1) of this rank's exclusive interval
       for (const GradientInterval& iv : e->exchange) {
         if (iv.owner != e->rank) continue;

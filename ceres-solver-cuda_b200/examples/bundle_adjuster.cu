@@ -6,6 +6,7 @@
 //   bundle_adjuster --input=problem.txt [--robustify] [--num_iterations=20]
 //                   [--linear_solver=iterative_schur|cgnr|cgnr_cuda] [--constant_first_camera]
 //   bundle_adjuster --synthetic=16,2000,8000 ...
+//   bundle_adjuster --input=problem.txt --check_input     (parse only, no GPU needed)
 //
 // The input is a BAL text file (https://grail.cs.washington.edu/projects/bal/):
 // "num_cameras num_points num_observations", then "camera point x y" per observation,
@@ -95,6 +96,19 @@ int main(int argc, char** argv) {
     std::fprintf(stderr, "usage: %s --input=<bal file> | --synthetic=nc,np,nobs [--robustify] "
                  "[--num_iterations=N] [--linear_solver=iterative_schur|cgnr|cgnr_cuda] [--bulk]\n", argv[0]);
     return 1;
+  }
+  if (Flag(argc, argv, "--check_input")) {
+    // what the reader understood, without touching a GPU (tests/test_bal_reader.py)
+    double sum = 0.0;
+    for (double v : bal.observations) sum += v;
+    for (double v : bal.cameras) sum += v;
+    for (double v : bal.points) sum += v;
+    long long index_sum = 0;
+    for (int i = 0; i < bal.num_observations; ++i)
+      index_sum += bal.camera_index[i] + 3LL * bal.point_index[i];
+    std::printf("cameras %d points %d observations %d index_sum %lld value_sum %.17g\n",
+                bal.num_cameras, bal.num_points, bal.num_observations, index_sum, sum);
+    return 0;
   }
   const bool robustify = Flag(argc, argv, "--robustify") != nullptr;
   const char* ls = Flag(argc, argv, "--linear_solver");

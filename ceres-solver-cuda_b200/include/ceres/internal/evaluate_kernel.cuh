@@ -526,8 +526,8 @@ __host__ __device__ constexpr int VariantCtas(int variant, int resident, int cos
 // 22% busy; profiles/r1_v1_ncu_summary.txt).  a.state must be 16-byte aligned and followed
 // by at least two doubles of slack (the engine's state buffer is).
 //
-// kChunked (several ranks, cb200_launch_args::chunks): a thread block evaluates whole CHUNKS
-// of consecutive residual blocks instead of a grid stride.  The gradient entries of a chunk's
+// kChunked (several ranks, cb200_launch_args::chunks): a warp evaluates whole CHUNKS of
+// consecutive residual blocks instead of a grid stride.  The gradient entries of a chunk's
 // exclusive range (the points of a bundle adjustment problem) are touched by that chunk
 // only, so when its last tile is done the thread block copies them straight into the
 // gradient buffers of the other ranks over NVLink (peer-mapped memory): the exchange of one
@@ -720,11 +720,13 @@ __global__ void __launch_bounds__(
       w.lo = w.hi = n;
     }
   };
-  auto walk_rb = [&](const Walk& w) { return w.lo + w.t * kEvaluateThreads + tid; };
+  // (chunks belong to WARPS: a warp that finishes a chunk fences and copies on its own while
+  // the other warps of the thread block keep evaluating)
+  auto walk_rb = [&](const Walk& w) { return w.lo + w.t * 32 + lane; };
   auto walk_advance = [&](Walk& w) {
     ++w.t;
-    if (w.lo + w.t * kEvaluateThreads >= w.hi) {
-      w.c += gridDim.x;
+    if (w.lo + w.t * 32 >= w.hi) {
+      w.c += gridDim.x * (kEvaluateThreads / 32);
       w.t = 0;
       load_chunk(w);
     }
@@ -732,7 +734,7 @@ __global__ void __launch_bounds__(
   Walk walk{0, 0, 0, 0};
   int rb0 = first, hi0 = n, c0 = 0, rb1 = first + stride, hi1 = n, c1 = 0;
   if constexpr (kChunked) {
-    walk.c = blockIdx.x;
+    walk.c = blockIdx.x * (kEvaluateThreads / 32) + (tid >> 5);
     load_chunk(walk);
     rb0 = walk_rb(walk); hi0 = walk.hi; c0 = walk.c;
     walk_advance(walk);
@@ -1304,14 +1306,14 @@ __global__ void __launch_bounds__(
 
     if constexpr (kChunked) {
       // Last tile of a chunk: its exclusive gradient range is final (no other chunk, on
-      // any rank, adds to it).  Make this block's reductions visible, then copy the range
-      // into every other rank's gradient buffer; meanwhile the other thread blocks of
-      // this SM keep evaluating.
-      if (rb - tid + kEvaluateThreads >= limit) {
+      // any rank, adds to it).  Make this warp's reductions visible, then copy the range
+      // into every other rank's gradient buffer; meanwhile the other warps of this SM keep
+      // evaluating.
+      if (warp_rb + 32 >= limit) {
         __threadfence();
-        __syncthreads();
+        __syncwarp();
         const int4 rec = __ldg(chunk_table + c0);
-        for (int i = rec.z + tid; i < rec.w; i += kEvaluateThreads) {
+        for (int i = rec.z + lane; i < rec.w; i += 32) {
           const double v = __ldcg(a.gradient + i);
 #pragma unroll 1
           for (int q = 0; q < a.num_peers; ++q) __stcg(a.peer_gradient[q] + i, v);
@@ -1393,7 +1395,8 @@ int LaunchEvaluate(const cb200_launch_args* args, void* stream) {
     if (args->chunks && (args->affine & kAffinePlain) == kAffinePlain)
       return LaunchVariant(
           EvaluateKernel<kVariantPlainAll, true, true, Functor, Loss, kRes, Ns...>, kAffineCtas,
-          Computed::kJetBytes, args, s, args->num_chunks);
+          Computed::kJetBytes, args, s,
+          (args->num_chunks + kEvaluateThreads / 32 - 1) / (kEvaluateThreads / 32));
 #endif
     if ((args->affine & kAffinePlain) == kAffinePlain)
       return LaunchVariant(EvaluateKernel<kVariantPlainAll, true, false, Functor, Loss, kRes, Ns...>,

@@ -123,7 +123,7 @@ typedef struct cb200_launch_args {
   int32_t jacobian_base[CB200_MAX_PARAMETER_BLOCKS];
   int32_t jacobian_step[CB200_MAX_PARAMETER_BLOCKS];
   /* Several ranks, gradient exchange fused into the evaluation kernel (NULL otherwise): a
-   * thread block evaluates whole chunks; chunk c is residual blocks [chunks[4c], chunks[4c+1])
+   * warp evaluates whole chunks; chunk c is residual blocks [chunks[4c], chunks[4c+1])
    * of this launch and gradient entries [chunks[4c+2], chunks[4c+3]) are touched by it alone,
    * so the kernel copies them into peer_gradient[0 .. num_peers) — the gradient buffers of
    * the other ranks, peer-mapped — as soon as the chunk is done. */

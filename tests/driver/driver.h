@@ -53,7 +53,11 @@ struct DriverProblem {
   // results of the last drv_problem_evaluate
   std::vector<double> pe_residuals, pe_gradient;
   ceres::CRSMatrix pe_jacobian;
-  DriverProblem() : problem(MakeOptions(&callback)) { callback.values = &values; }
+  // with_callback: install the recording EvaluationCallback (it makes every Evaluate copy the
+  // state into the user's parameter blocks first, so the benchmarks leave it out)
+  explicit DriverProblem(bool with_callback) : problem(MakeOptions(with_callback ? &callback : nullptr)) {
+    callback.values = &values;
+  }
   static ceres::Problem::Options MakeOptions(RecordingCallback* callback) {
     ceres::Problem::Options o;
     o.evaluation_callback = callback;

@@ -63,7 +63,8 @@ void* drv_create(int num_pb, const int* pb_size, const double* pb_values,
                  const int* pb_manifold_param, int num_rb, const int* rb_type, const int* rb_pb,
                  const int* rb_loss_kind, const double* rb_loss_a, const double* rb_loss_b,
                  const double* fdata, int bulk) {
-  auto* dp = new DriverProblem;
+  auto* dp = new DriverProblem((bulk & 2) != 0);  // bit 1: install the EvaluationCallback
+  bulk &= 1;
   dp->pb_offset.resize(num_pb);
   dp->pb_size.assign(pb_size, pb_size + num_pb);
   int64_t off = 0;

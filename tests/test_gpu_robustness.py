@@ -85,7 +85,7 @@ def test_derivative_of_a_constant_subexpression_is_zero():
 
 def test_evaluation_callback_sees_every_evaluation_point():
     spec = P.bal_problem(6, 120, 500, seed=3)
-    cp = B.CudaProblem(spec, jacobian_format=0)
+    cp = B.CudaProblem(spec, jacobian_format=0, evaluation_callback=True)
     x = cp.initial_state()
     before = cp.callback_info()["calls"]
     x1 = x + 0.001
