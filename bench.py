@@ -64,6 +64,9 @@ def parse():
                     help="residual blocks of the CPU leg (default: 6 M inside the GPU arm, the "
                          "whole workload for --impl reference)")
     ap.add_argument("--no-multi-gpu-check", action="store_true")
+    ap.add_argument("--pose-edge-order", default="temporal", choices=["temporal", "random"],
+                    help="P5: edges sorted by their later pose (as g2o files list them) or the "
+                         "loop closures in random order (worst case for locality)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -129,7 +132,8 @@ def make_spec(args):
         return P.bal_shape(w["shape"], scale=args.scale,
                            subset_manifold=bool(w.get("subset_manifold")))
     return P.pose_graph_problem(max(10, int(w["poses"] * args.scale)),
-                                max(20, int(w["edges"] * args.scale)), seed=5)
+                                max(20, int(w["edges"] * args.scale)), seed=5,
+                                order=args.pose_edge_order)
 
 
 def workload_config(args, spec):
@@ -146,8 +150,8 @@ def workload_config(args, spec):
     else:
         what = (f"synthetic pose graph {spec.num_pb} poses / {spec.num_rb} edges, "
                 "RelativePoseError<6,7,7>, ProductManifold<EigenQuaternion, Euclidean<3>>, pose 0 "
-                "constant, no loss, BlockSparseMatrix Jacobian, outputs: "
-                "cost+residuals+gradient+Jacobian")
+                f"constant, no loss, edges in {m.get('edge_order', 'temporal')} order, "
+                "BlockSparseMatrix Jacobian, outputs: cost+residuals+gradient+Jacobian")
         jbytes = spec.num_rb * 576
     return {"workload": what, "shape": args.workload, "scale": args.scale, "seed": m["seed"],
             # identical in both arms: the reference arm evaluates the same problem on the host

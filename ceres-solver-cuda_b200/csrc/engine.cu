@@ -1782,6 +1782,29 @@ static int RunJacobianWalk(cb200_engine* e, int op, const double* x, double* y) 
       case kOpLeft: JacobianWalkKernel<kOpLeft><<<grid, 256, 0, s>>>(w, x, y); break;
       case kOpColumnNorm: JacobianWalkKernel<kOpColumnNorm><<<grid, 256, 0, s>>>(w, x, y); break;
       case kOpNormal: {
+        // The per-type kernel (compile-time sizes, coalesced cell runs) where the structure
+        // allows it; the table-walk kernels below otherwise.
+        constexpr uint32_t kAffinePlain =
+            CB200_AFFINE_RESIDUAL | CB200_AFFINE_JACOBIAN | CB200_AFFINE_DELTA_IS_STATE;
+        bool contiguous = t->desc.normal_product != nullptr && t->plain && !w.crs &&
+                          (t->affine & kAffinePlain) == kAffinePlain &&
+                          !getenv("CB200_GENERIC_NORMAL_PRODUCT");
+        for (int j = 0; j < w.nb && contiguous; ++j)
+          contiguous = t->jacobian_step[j] == w.kres * w.sizes[j];
+        if (contiguous) {
+          cb200_normal_args na{};
+          na.n = t->n_local;
+          na.offset = t->d_soff.ptr;
+          na.x = x;
+          na.y = y;
+          na.values = e->d_jacobian.ptr;
+          std::memcpy(na.base, t->jacobian_base, sizeof(na.base));
+          const int rc = t->desc.normal_product(&na, s);
+          if (rc == 0) break;
+          if (rc > 0)
+            return e->Fail(CB200_ERROR_CUDA, "normal product launch: %s",
+                           cudaGetErrorString(static_cast<cudaError_t>(rc)));
+        }
         int cell_doubles = 0;
         for (int j = 0; j < w.nb; ++j) cell_doubles += w.kres * w.sizes[j];
         const size_t smem =
@@ -1826,7 +1849,7 @@ static int PrepareLinearAlgebra(cb200_engine* e, bool need_residuals) {
     return e->Fail(CB200_ERROR_INVALID_ARGUMENT,
                    "no residuals on the device: evaluate with residuals first");
   CB200_CUDA(e, cudaSetDevice(e->device));
-  for (auto& b : e->la_col) CB200_CUDA(e, b.Resize(static_cast<size_t>(e->num_effective) + 1));
+  for (auto& b : e->la_col) CB200_CUDA(e, b.Resize(static_cast<size_t>(e->num_effective) + 4));
   CB200_CUDA(e, e->la_row.Resize(static_cast<size_t>(e->res_end - e->res_begin) + 1));
   CB200_CUDA(e, e->la_scalars.Resize(3 * kSCount));
   CB200_CUDA(e, e->la_partials.Resize(3 * kMaxVectorGrid));

@@ -95,6 +95,16 @@ struct BlockDims {
   // chunks per thread; odd, so that the 16-byte copies of 8 consecutive threads (one
   // shared-memory wavefront) fall into distinct banks
   __host__ __device__ static constexpr int RowChunks() { return ChunksBefore(kNumBlocks) | 1; }
+  // Cooperative gather: a lane's window of block j occupies WindowPitch(j) chunks, odd, so
+  // that the owner's reads (lane stride = pitch * 16 bytes) spread over the banks: an even
+  // pitch of 2 or 4 chunks puts 32 lanes on 2 or 4 bank groups (measured on the pose graph
+  // <6,7,7>: 217 shared-memory wavefronts per tile for 58 ideal).
+  __host__ __device__ static constexpr int WindowPitch(int j) { return WindowChunks(j) | 1; }
+  __host__ __device__ static constexpr int PitchChunksBefore(int j) {
+    int o = 0;
+    for (int i = 0; i < j; ++i) o += WindowPitch(i);
+    return o;
+  }
 };
 
 template <typename Dims, typename Functor, typename T, std::size_t... Is>
@@ -457,7 +467,7 @@ struct SmemPlan {
   static constexpr int kParamBytes =
       CB200_KERNEL_GATHER == 0 ? Dims::PitchBefore(kNB) * 8
                                : (CB200_KERNEL_GATHER == 1 ? Dims::RowChunks() * 16
-                                                           : Dims::ChunksBefore(kNB) * 16);
+                                                           : Dims::PitchChunksBefore(kNB) * 16);
   static constexpr int kStages = CB200_KERNEL_EARLY_PREFETCH ? 2 : 1;
   static constexpr bool kFunctorInSmem =
       (sizeof(Functor) % 4 == 0) && (alignof(Functor) <= 16) && (sizeof(Functor) <= 128);
@@ -485,12 +495,13 @@ struct SmemPlan {
   // staging; with several passes the region is reused pass after pass) ...
   static constexpr int kJacobianDoubles = 32 * kRes * PassPlan<kRes, Ns...>::MaxWidth();
   // ... and one padded row per lane for the staged gradient reductions (plus, per lane,
-  // the destination offset and the live-column mask: 2 x 32 ints).  With a single
-  // derivative pass every gradient is out before the first cell is staged, so the
-  // gradient staging reuses the Jacobian staging buffer.
+  // the destination offset and the live-column mask: 2 x 32 ints).  Within a derivative
+  // pass every gradient is out before the first cell is staged, so the gradient staging
+  // reuses the Jacobian staging buffer.
   static constexpr int kGradientStage = 32 * StagePitch(Dims::MaxSize()) + 32;
-  static constexpr bool kGradientAliasesJacobian =
-      PassPlan<kRes, Ns...>::kNumPasses == 1 && kGradientStage <= kJacobianDoubles;
+  // (several passes: each pass waits for the previous pass's stores to leave the staging
+  // region before its own gradient uses it, so the alias holds pass by pass)
+  static constexpr bool kGradientAliasesJacobian = kGradientStage <= kJacobianDoubles;
   static constexpr int kGradientDoubles = kGradientAliasesJacobian ? 0 : kGradientStage;
   static constexpr int kWarps = kEvaluateThreads / 32;
   static constexpr bool kStageJacobian =
@@ -628,8 +639,8 @@ __global__ void __launch_bounds__(
       } else if constexpr (CB200_KERNEL_GATHER == 2) {
         // The warp copies the 32 windows of argument j as one stream of 32 * W 16-byte
         // pieces (W = Size/2 + 1): consecutive lanes fetch consecutive pieces of a window,
-        // so a copy instruction touches a handful of cache lines instead of 32, and its
-        // 512 bytes land contiguously in shared memory ([argument][lane][W pieces]).
+        // so a copy instruction touches a handful of cache lines instead of 32; shared
+        // layout [argument][lane][odd pitch of W | 1 pieces].
 #pragma unroll
         for (int j = 0; j < kNB; ++j) {
           const int kW = Dims::WindowChunks(j);  // constant after unrolling
@@ -639,7 +650,8 @@ __global__ void __launch_bounds__(
             const int owner = e / kW;
             const int c = e - owner * kW;
             const int so = __shfl_sync(0xffffffffu, soff[j], owner);
-            CpAsync16(dst + 2 * (32 * Dims::ChunksBefore(j) + e), a.state + ((so & ~1) + 2 * c));
+            CpAsync16(dst + 2 * (32 * Dims::PitchChunksBefore(j) + owner * Dims::WindowPitch(j) + c),
+                      a.state + ((so & ~1) + 2 * c));
           }
         }
       } else {
@@ -848,7 +860,7 @@ __global__ void __launch_bounds__(
       if constexpr (kPrefetch && CB200_KERNEL_GATHER == 1) {
         return sp[2 * Dims::ChunksBefore(j) + ((parity_cur >> j) & 1) + i];
       } else if constexpr (kPrefetch && CB200_KERNEL_GATHER == 2) {
-        return sp[2 * (32 * Dims::ChunksBefore(j) + lane * Dims::WindowChunks(j)) +
+        return sp[2 * (32 * Dims::PitchChunksBefore(j) + lane * Dims::WindowPitch(j)) +
                   ((parity_cur >> j) & 1) + i];
       } else if constexpr (kPrefetch) {
         return sp[32 * Dims::PitchBefore(j) + lane * (Dims::Size(j) | 1) + i];
@@ -913,11 +925,12 @@ __global__ void __launch_bounds__(
       // BlockSparse: argument j's 32 cells are one run of the values array (always true
       // inside the E or F region); CompressedRow: the warp's 32 row groups are one run.
       bool bulk_arg[kNB];
+      bool coop_arg[kNB];  // cells staged and written cooperatively, cell after cell
       bool bulk_all = false;
       int bulk_base[kNB];
       int bulk_all_base = 0;
 #pragma unroll
-      for (int j = 0; j < kNB; ++j) { bulk_arg[j] = false; bulk_base[j] = 0; }
+      for (int j = 0; j < kNB; ++j) { bulk_arg[j] = false; coop_arg[j] = false; bulk_base[j] = 0; }
       if constexpr (kStage) {
         if (out_jacobian && CB200_KERNEL_BULK_STORE) {
           if (!crs) {
@@ -937,6 +950,11 @@ __global__ void __launch_bounds__(
                                   jpos[j] == base + lane * kRes * t0;
                 bulk_arg[j] = __all_sync(0xffffffffu, mine) && ((base & 1) == 0);
                 bulk_base[j] = base;
+                if (!bulk_arg[j]) {
+                  const bool separate = valid && delta_off[j] >= 0 && tangent[j] == t0 &&
+                                        ((jpos[j] & 1) == 0) && ((kRes * t0) % 2 == 0);
+                  coop_arg[j] = kRes * Dims::Size(j) >= 16 && __all_sync(0xffffffffu, separate);
+                }
               }
             }
           } else {
@@ -1218,6 +1236,31 @@ __global__ void __launch_bounds__(
                   for (int c = 0; c < kSize; ++c)
                     if (is_live(c)) cell[r * row_stride + dcol(c)] = out[r].v[kLane0 + c];
               }
+            } else if (kStage && !crs && coop_arg[j]) {
+              // The warp's cells of this argument are not one run (two cells per row block,
+              // a pose graph) but each cell is contiguous: stage them side by side, then
+              // write cell after cell with consecutive lanes on consecutive 16-byte pieces,
+              // so a store instruction fills whole sectors (a thread writing its own cell
+              // with 8-byte stores at a 288-byte stride costs four requests per sector:
+              // 2340 L2 write requests per tile measured on the pose graph for 576 ideal).
+              const int cell_doubles = kRes * tan;
+              double* stage = jbuf + 32 * kRes * (Dims::Offset(j) - Dims::Offset(kFirst));
+              double* cell = stage + lane * cell_doubles;
+#pragma unroll
+              for (int r = 0; r < kRes; ++r)
+#pragma unroll
+                for (int c = 0; c < kSize; ++c)
+                  if (is_live(c)) cell[r * tan + dcol(c)] = out[r].v[kLane0 + c];
+              __syncwarp();
+              const int pairs = cell_doubles / 2;
+#pragma unroll 4
+              for (int owner = 0; owner < 32; ++owner) {
+                const int base = __shfl_sync(0xffffffffu, jpos[j], owner);
+                for (int w = lane; w < pairs; w += 32)
+                  reinterpret_cast<double2*>(a.jacobian_values + base)[w] =
+                      reinterpret_cast<const double2*>(stage + owner * cell_doubles)[w];
+              }
+              __syncwarp();
             } else if (valid && active) {
               double* __restrict__ dst = a.jacobian_values + jpos[j];
               if (!kGeneric && row_stride == kSize && ((jpos[j] & 1) == 0) &&
@@ -1419,6 +1462,10 @@ int LaunchEvaluate(const cb200_launch_args* args, void* stream) {
                        Tables::kJetBytes, args, s);
 }
 
+// ceres/internal/normal_kernel.cuh (included at the end of this file)
+template <int kRes, int... Ns>
+int LaunchNormalProduct(const cb200_normal_args* args, void* stream);
+
 template <typename Functor, typename Loss, int kRes, int... Ns>
 cb200_residual_type MakeResidualType() {
   static_assert(sizeof...(Ns) >= 1 && sizeof...(Ns) <= CB200_MAX_PARAMETER_BLOCKS,
@@ -1433,10 +1480,13 @@ cb200_residual_type MakeResidualType() {
   t.threads_per_block = kEvaluateThreads;
   t.supports_chunks = CB200_KERNEL_CHUNKED_EXCHANGE;
   t.launch = &LaunchEvaluate<Functor, Loss, kRes, Ns...>;
+  t.normal_product = &LaunchNormalProduct<kRes, Ns...>;
   return t;
 }
 
 }  // namespace internal
 }  // namespace ceres
+
+#include "ceres/internal/normal_kernel.cuh"
 
 #endif  // CERES_B200_INTERNAL_EVALUATE_KERNEL_CUH_

@@ -1,0 +1,225 @@
+// y += J'(J x) on the Jacobian the evaluation kernel left in HBM, one instantiation per
+// <kNumResiduals, Ns...> (the functor does not matter: the cells are plain numbers).  It is
+// the product conjugate gradients on the normal equations spend their time in
+// (reference: CgnrSolver / CudaCgnrSolver, internal/ceres/cgnr_solver.cc:190-330, two cuSPARSE
+// SpMVs per iteration over a compressed-row copy of J).  Reaches the engine as a second thunk
+// of cb200_residual_type; the engine's size-generic table-walk kernels (csrc/engine.cu) remain
+// the fallback for every structure this kernel does not take.
+//
+// Preconditions (checked by the engine, cb200_normal_args): block-sparse values, no manifold
+// and no constant block in the type (tangent == ambient size, gradient offset == state offset),
+// and cell positions that are arithmetic progressions with step kRes * Size(j), i.e. the 32
+// cells of a warp's tile are one contiguous run per argument (bundle adjustment after the
+// Schur ordering).
+//
+// Design: a warp owns tiles of 32 consecutive residual blocks (grid stride).  Per tile it reads
+// its two contiguous runs of cells with fully coalesced 16-byte cp.async copies into shared
+// memory (the table-walk kernel reads a cell per thread at a 144-byte stride: 32 cache lines
+// per instruction, L1-tag bound at 25 % of the HBM roof), gathers the x entries of its
+// parameter blocks exactly like the evaluation kernel gathers parameters (aligned 16-byte
+// windows, cooperative), keeps one tile in flight while the previous one is consumed, and
+// adds J' t with the evaluation kernel's staged reductions (consecutive lanes on consecutive
+// addresses).  Sizes are compile-time, so the 24 multiply-adds per block are straight-line.
+#ifndef CERES_B200_INTERNAL_NORMAL_KERNEL_CUH_
+#define CERES_B200_INTERNAL_NORMAL_KERNEL_CUH_
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "ceres_b200.h"
+// (included from the end of ceres/internal/evaluate_kernel.cuh, whose helpers it uses)
+
+namespace ceres {
+namespace internal {
+
+constexpr int kNormalThreads = 128;
+
+template <int kRes, int... Ns>
+struct NormalPlan {
+  using Dims = BlockDims<Ns...>;
+  static constexpr int kNB = Dims::kNumBlocks;
+  static constexpr int kNP = Dims::kNumParameters;
+  static constexpr int kXDoubles = 32 * 2 * Dims::PitchChunksBefore(kNB);  // one x stage of a warp
+  static constexpr int kJDoubles = 32 * kRes * kNP;                    // one cell stage of a warp
+  // the staged reductions reuse the cell stage just consumed: [lane][pitch] sums + 32 offsets
+  static constexpr int kGradientDoubles = 32 * StagePitch(Dims::MaxSize()) + 16;
+  static constexpr int kStageDoubles = kJDoubles > kGradientDoubles ? kJDoubles : kGradientDoubles;
+  static constexpr int kWarpDoubles = 2 * kXDoubles + 2 * kStageDoubles;
+  static constexpr int kBytes = (kNormalThreads / 32) * kWarpDoubles * 8;
+  static constexpr int kCtas = (228 * 1024) / (kBytes + 1024) >= 3 ? 3
+                               : ((228 * 1024) / (kBytes + 1024) >= 2 ? 2 : 1);
+  static constexpr bool kFits = kBytes <= 227 * 1024 && (kRes * kNP) % 2 == 0;
+};
+
+template <int kRes, int... Ns>
+__global__ void __launch_bounds__(kNormalThreads, NormalPlan<kRes, Ns...>::kCtas)
+    NormalProductKernel(const cb200_normal_args a) {
+  using Dims = BlockDims<Ns...>;
+  using Plan = NormalPlan<kRes, Ns...>;
+  constexpr int kNB = Plan::kNB;
+  constexpr int kNP = Plan::kNP;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  double* const wbuf = reinterpret_cast<double*>(smem) + warp * Plan::kWarpDoubles;
+  auto xstage = [&](int s) { return wbuf + s * Plan::kXDoubles; };
+  auto jstage = [&](int s) { return wbuf + 2 * Plan::kXDoubles + s * Plan::kStageDoubles; };
+  const int n = a.n;
+  const int num_tiles = (n + 31) / 32;
+  const int warps = gridDim.x * (kNormalThreads / 32);
+  const int first_tile = blockIdx.x * (kNormalThreads / 32) + warp;
+
+  auto load_offsets = [&](int tile, int (&soff)[kNB]) {
+    const int rb = min(tile * 32 + lane, n - 1);
+#pragma unroll
+    for (int j = 0; j < kNB; ++j)
+      soff[j] = tile < num_tiles ? __ldg(a.offset + static_cast<size_t>(j) * n + rb) : 0;
+  };
+  // copies of one tile: the x windows of its parameter blocks and its runs of cells
+  auto prefetch = [&](int s, int tile, const int (&soff)[kNB]) {
+    if (tile < num_tiles) {
+      double* xs = xstage(s);
+#pragma unroll
+      for (int j = 0; j < kNB; ++j) {
+        const int kW = Dims::WindowChunks(j);
+#pragma unroll
+        for (int it = 0; it < kW; ++it) {
+          const int e = it * 32 + lane;
+          const int owner = e / kW;
+          const int c = e - owner * kW;
+          const int so = __shfl_sync(0xffffffffu, soff[j], owner);
+          CpAsync16(xs + 2 * (32 * Dims::PitchChunksBefore(j) + owner * Dims::WindowPitch(j) + c),
+                    a.x + ((so & ~1) + 2 * c));
+        }
+      }
+      double* js = jstage(s);
+      const int rb0 = tile * 32;
+      const int blocks = min(32, n - rb0);
+#pragma unroll
+      for (int j = 0; j < kNB; ++j) {
+        const int kCell = kRes * Dims::Size(j);  // doubles per cell, constant after unrolling
+        const double* src = a.values + (a.base[j] + static_cast<int64_t>(rb0) * kCell);
+        double* dst = js + 32 * kRes * Dims::Offset(j);
+        const int doubles = blocks * kCell;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+          for (int it = 0; it < (kCell + 1) / 2; ++it) {
+            const int e = 2 * (it * 32 + lane);
+            if (e + 1 < doubles) CpAsync16(dst + e, src + e);
+            else if (e < doubles) CpAsync8(dst + e, src + e);
+          }
+        } else {
+#pragma unroll
+          for (int it = 0; it < kCell; ++it) {
+            const int e = it * 32 + lane;
+            if (e < doubles) CpAsync8(dst + e, src + e);
+          }
+        }
+      }
+    }
+    CpAsyncCommit();
+  };
+
+  int soff_cur[kNB], soff_next[kNB];
+  load_offsets(first_tile, soff_cur);
+  prefetch(0, first_tile, soff_cur);
+  load_offsets(first_tile + warps, soff_next);
+
+  int k = 0;
+  for (int tile = first_tile; tile < num_tiles; tile += warps, ++k) {
+    const int s = k & 1;
+    int soff_issue[kNB];
+#pragma unroll
+    for (int j = 0; j < kNB; ++j) soff_issue[j] = soff_next[j];
+    prefetch(s ^ 1, tile + warps, soff_issue);
+    load_offsets(tile + 2 * warps, soff_next);
+    CpAsyncWait<1>();
+    __syncwarp();
+
+    const int rb = tile * 32 + lane;
+    const bool valid = rb < n;
+    const double* xs = xstage(s);
+    const double* js = jstage(s);
+    // this lane's cells and x entries -> registers
+    double J[kRes][kNP], x[kNP];
+#pragma unroll
+    for (int j = 0; j < kNB; ++j) {
+      const int kS = Dims::Size(j);
+      const double* cell = js + 32 * kRes * Dims::Offset(j) + lane * kRes * kS;
+#pragma unroll
+      for (int r = 0; r < kRes; ++r)
+#pragma unroll
+        for (int c = 0; c < kS; ++c) J[r][Dims::Offset(j) + c] = valid ? cell[r * kS + c] : 0.0;
+      const double* xw = xs + 2 * (32 * Dims::PitchChunksBefore(j) + lane * Dims::WindowPitch(j)) +
+                         (soff_cur[j] & 1);
+#pragma unroll
+      for (int c = 0; c < kS; ++c) x[Dims::Offset(j) + c] = valid ? xw[c] : 0.0;
+    }
+    double t[kRes];
+#pragma unroll
+    for (int r = 0; r < kRes; ++r) {
+      double acc = 0.0;
+#pragma unroll
+      for (int c = 0; c < kNP; ++c) acc += J[r][c] * x[c];
+      t[r] = acc;
+    }
+    __syncwarp();  // every lane has its cells: the stage can take the sums
+    double* gbuf = jstage(s);
+    int* obuf = reinterpret_cast<int*>(gbuf + 32 * StagePitch(Dims::MaxSize()));
+#pragma unroll
+    for (int j = 0; j < kNB; ++j) {
+      const int kS = Dims::Size(j);
+      const int kPitch = StagePitch(kS);
+#pragma unroll
+      for (int c = 0; c < kS; ++c) {
+        double acc = 0.0;
+#pragma unroll
+        for (int r = 0; r < kRes; ++r) acc += J[r][Dims::Offset(j) + c] * t[r];
+        gbuf[lane * kPitch + c] = acc;
+      }
+      obuf[lane] = valid ? soff_cur[j] : -1;
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < kS; ++it) {
+        const int e = it * 32 + lane;
+        const int row = e / kS;
+        const int c = e - row * kS;
+        const int d = obuf[row];
+        RedAddIf(d >= 0, a.y + (d + c), gbuf[row * kPitch + c]);
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < kNB; ++j) soff_cur[j] = soff_issue[j];
+  }
+  CpAsyncWait<0>();
+}
+
+template <int kRes, int... Ns>
+int LaunchNormalProduct(const cb200_normal_args* args, void* stream) {
+  using Plan = NormalPlan<kRes, Ns...>;
+  if constexpr (!Plan::kFits) {
+    return -1;  // the engine falls back to its table-walk kernel
+  } else {
+    if (args->n <= 0) return 0;
+    int device = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(NormalProductKernel<kRes, Ns...>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const int tiles = (args->n + 31) / 32;
+    const int needed = (tiles + kNormalThreads / 32 - 1) / (kNormalThreads / 32);
+    const int wanted = (sms > 0 ? sms : 148) * Plan::kCtas;
+    NormalProductKernel<kRes, Ns...><<<needed < wanted ? needed : wanted, kNormalThreads,
+                                       Plan::kBytes, static_cast<cudaStream_t>(stream)>>>(*args);
+    return static_cast<int>(cudaGetLastError());
+  }
+}
+
+}  // namespace internal
+}  // namespace ceres
+
+#endif  // CERES_B200_INTERNAL_NORMAL_KERNEL_CUH_

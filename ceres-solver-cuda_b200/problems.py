@@ -318,10 +318,15 @@ def _small_quat(rng, n, sigma):
     return q
 
 
-def pose_graph_problem(num_poses, num_edges, seed=5, loss="none") -> ProblemSpec:
+def pose_graph_problem(num_poses, num_edges, seed=5, loss="none", order="temporal") -> ProblemSpec:
     """Pose-graph SLAM, RelativePoseError<6,7,7>, pose = [q(x,y,z,w), t],
     ProductManifold<EigenQuaternionManifold, EuclideanManifold<3>> (7 -> 6),
-    pose 0 constant."""
+    pose 0 constant.
+
+    order="temporal" (default): edges in the order a SLAM front end emits them and g2o files
+    list them - an edge appears when its later pose is created, so the list is sorted by
+    max(i, j).  order="random": odometry edges first, then the loop closures in random order
+    (the same edges; worst case for locality: every edge touches two random poses)."""
     assert num_edges >= num_poses - 1
     rng = np.random.default_rng(seed)
     n = num_poses
@@ -354,6 +359,11 @@ def pose_graph_problem(num_poses, num_edges, seed=5, loss="none") -> ProblemSpec
     meas_q /= np.linalg.norm(meas_q, axis=1, keepdims=True)
     meas_t = -_quat_rot_xyzw(meas_q, est_t) + rng.normal(0, 0.01, (num_edges, 3))
     fdata = np.concatenate([meas_q, meas_t], axis=1)
+    if order == "temporal":
+        perm = np.argsort(np.maximum(i_idx, j_idx), kind="stable")
+        i_idx, j_idx, fdata = i_idx[perm], j_idx[perm], fdata[perm]
+    else:
+        assert order == "random"
     # evaluate at a perturbed state
     qn = _quat_mul_xyzw(q, _small_quat(rng, n, 0.02))
     qn /= np.linalg.norm(qn, axis=1, keepdims=True)
@@ -369,7 +379,7 @@ def pose_graph_problem(num_poses, num_edges, seed=5, loss="none") -> ProblemSpec
         pb_manifold_param=np.zeros(n, np.int32),
         rb_loss_kind=np.full(num_edges, kind, np.int32), rb_loss_a=np.full(num_edges, 1.0),
         rb_loss_b=np.zeros(num_edges), num_eliminate_blocks=0,
-        meta={"workload": f"pose-graph-{n}x{num_edges}", "seed": seed})
+        meta={"workload": f"pose-graph-{n}x{num_edges}", "seed": seed, "edge_order": order})
 
 
 # ------------------------------------------------------ reference fixtures

@@ -144,6 +144,22 @@ typedef struct cb200_launch_args {
  * `stream` is a cudaStream_t.  Returns a cudaError_t value. */
 typedef int (*cb200_launch_fn)(const cb200_launch_args* args, void* stream);
 
+/* y += J'(J x) for one residual-block type on the Jacobian values left in HBM (conjugate
+ * gradients on the normal equations; reference: CgnrSolver's two SpMVs per iteration,
+ * internal/ceres/cgnr_solver.cc:190-330).  Compiled per <kNumResiduals, Ns...> next to the
+ * launch thunk (ceres/internal/normal_kernel.cuh).  Only for block-sparse values of a type
+ * without manifolds or constant blocks whose cells are an arithmetic progression with step
+ * num_residuals * size[j]; the engine's generic kernels serve everything else. */
+typedef struct cb200_normal_args {
+  int32_t n;               /* residual blocks of this type on this rank */
+  const int32_t* offset;   /* [num_blocks][n] gradient (== state) offset of every argument */
+  const double* x;         /* 16-byte aligned, followed by >= 2 doubles of slack */
+  double* y;
+  const double* values;    /* this rank's Jacobian values */
+  int32_t base[CB200_MAX_PARAMETER_BLOCKS]; /* cell (t, j) starts at base[j] + t * kRes * size[j] */
+} cb200_normal_args;
+typedef int (*cb200_normal_fn)(const cb200_normal_args* args, void* stream);
+
 /* Static description of a residual-block type; replaces the template arguments of
  * AutoDiffResidualBlockCUDAEvaluator<CostFunctor, LossFunctionCUDA, kNumResiduals, Ns...>
  * (include/ceres/internal/autodiff_residual_block_cuda_evaluator.h:60-94). */
@@ -156,6 +172,7 @@ typedef struct cb200_residual_type {
   int32_t threads_per_block; /* of the launch thunk; fixes the number of cost partials */
   int32_t supports_chunks;   /* the thunk honours cb200_launch_args::chunks (fused exchange) */
   cb200_launch_fn launch;
+  cb200_normal_fn normal_product; /* may be NULL; returns -1 when the sizes do not fit */
 } cb200_residual_type;
 
 /* ---- lifetime.  Replaces ContextImpl::InitCuda + RegisteredCUDAEvaluators ctor

@@ -24,11 +24,11 @@ def _write_bal(spec, path):
     with open(path, "w") as f:
         f.write(f"{nc} {npts} {nobs}\n")
         for (cam, pt), (x, y) in zip(rb, obs):
-            f.write(f"{cam - npts} {pt} {x!r} {y!r}\n")      # repr: round-trip exact doubles
+            f.write(f"{cam - npts} {pt} {float(x)!r} {float(y)!r}\n")  # repr: exact round trip
         for v in spec.pb_values[3 * npts:]:                   # cameras, 9 per camera
-            f.write(f"{v!r}\n")
+            f.write(f"{float(v)!r}\n")
         for v in spec.pb_values[:3 * npts]:                   # points
-            f.write(f"{v!r}\n")
+            f.write(f"{float(v)!r}\n")
     return rb[:, 0] - npts, rb[:, 1]
 
 

@@ -322,3 +322,33 @@ def test_schur_reorder_groups_by_e_block():
     # buckets are filled back to front (reorder_program.cc:296-312)
     first = np.flatnonzero(pts == pts[0])
     assert np.all(np.diff(rbs[first]) < 0)
+
+
+def test_convex_test_loss_and_the_corrector_alpha_branch():
+    """The test-only loss rho(s) = s + a s^2 (rho'' = 2a > 0) is the way into the Corrector's
+    alpha branch (corrector.cc:105-130); the corrected residual and Jacobian must satisfy the
+    Gauss-Newton identities of Triggs et al. that corrector_test.cc:56-271 checks:
+    J'J (corrected) = rho' J'J + 2 rho'' J'r r'J and J'r (corrected) = rho' J'r."""
+    a = 0.07
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        r = rng.normal(0, 1.5, 3)
+        J = rng.normal(0, 2.0, (3, 4))
+        s = float(r @ r)
+        rho = O.loss_evaluate(P.LOSS_CONVEX_TEST, a, 0.0, s)
+        assert np.allclose(rho, [s + a * s * s, 1 + 2 * a * s, 2 * a], rtol=1e-15)
+        rc, Jc = O.corrector(s, rho, r, J.ravel())
+        Jc = Jc.reshape(3, 4)
+        g_want = rho[1] * J.T @ r
+        H_want = rho[1] * J.T @ J + 2 * rho[2] * np.outer(J.T @ r, J.T @ r)
+        assert np.allclose(Jc.T @ rc, g_want, rtol=1e-12, atol=1e-12)
+        assert np.allclose(Jc.T @ Jc, H_want, rtol=1e-12, atol=1e-12)
+
+
+def test_sqrt_of_a_constant_zero_is_rejected_like_the_reference():
+    """jet.h:617-621: sqrt(Jet(0)) has derivative lanes (1 / (2 sqrt(0))) * 0 = NaN, so the
+    reference (and the oracle that restates it) rejects r = x + sqrt(T(0))."""
+    ok, r, J = O.cost_evaluate(P.SQRT_OF_CONSTANT, [4.0], [[1.5]])
+    assert ok and r[0] == 3.5 and J[0].ravel()[0] == 1.0
+    ok, r, J = O.cost_evaluate(P.SQRT_OF_CONSTANT, [0.0], [[1.5]])
+    assert not np.isfinite(J[0]).all()
