@@ -278,6 +278,10 @@ void MinimizeOnDevice(const Solver::Options& options, cb200_engine* engine, doub
       break;
     }
     summary->linear_solver_time_in_seconds += Seconds() - ls_start;
+    if (std::getenv("CB200_SOLVER_TIMING"))
+      std::fprintf(stderr, "iteration %d: trust-region step %.1f ms wall, conjugate gradients %.1f ms "
+                   "on the device (%d iterations)\n", it, (Seconds() - ls_start) * 1e3,
+                   ss.cg.solve_ms, ss.cg.num_iterations);
     Solver::IterationSummary is;
     is.iteration = it;
     is.linear_solver_iterations = ss.cg.num_iterations;

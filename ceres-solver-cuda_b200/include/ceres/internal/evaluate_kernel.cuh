@@ -425,6 +425,29 @@ struct PassPlan {
 };
 
 __host__ __device__ constexpr int StagePitch(int n) { return n | 1; }
+// Cells of at least this many doubles that do not form one run are written cooperatively
+// (stage, then cell after cell with coalesced 16-byte stores) instead of by their thread.
+constexpr int kCooperativeCellDoubles = 32;
+// Where argument j's 32 cells start in a warp's Jacobian staging region, for a pass that
+// begins at block `first`; j == `end` gives the size of the region.  Arguments whose cells
+// can take the cooperative path get four doubles of slack per lane for its padded pitch.
+template <int kRes, typename Dims>
+__host__ __device__ constexpr int StageOffset(int first, int j) {
+  int doubles = 0;
+  for (int i = first; i < j; ++i)
+    doubles += kRes * Dims::Size(i) + (kRes * Dims::Size(i) >= kCooperativeCellDoubles ? 4 : 0);
+  return 32 * doubles;
+}
+template <int kRes, int... Ns>
+__host__ __device__ constexpr int MaxStageDoubles() {
+  using Plan = PassPlan<kRes, Ns...>;
+  int m = 0;
+  for (int p = 0; p < Plan::kNumPasses; ++p) {
+    const int d = StageOffset<kRes, BlockDims<Ns...>>(Plan::FirstBlock(p), Plan::EndBlock(p));
+    m = d > m ? d : m;
+  }
+  return m;
+}
 
 // CTAs per SM the Jet kernels are compiled for.  Measured on B200 for the BAL functor
 // (scripts/kbench.cu, profiles/r2_kbench_variants.txt): 3 CTAs x 128 threads (162 registers)
@@ -493,7 +516,7 @@ struct SmemPlan {
   static constexpr int kCtas = ResidentCtas(kRes, Dims::kNumParameters, kInts);
   // per warp: the cells of the arguments of one derivative pass side by side (Jacobian
   // staging; with several passes the region is reused pass after pass) ...
-  static constexpr int kJacobianDoubles = 32 * kRes * PassPlan<kRes, Ns...>::MaxWidth();
+  static constexpr int kJacobianDoubles = MaxStageDoubles<kRes, Ns...>();
   // ... and one padded row per lane for the staged gradient reductions (plus, per lane,
   // the destination offset and the live-column mask: 2 x 32 ints).  Within a derivative
   // pass every gradient is out before the first cell is staged, so the gradient staging
@@ -953,7 +976,8 @@ __global__ void __launch_bounds__(
                 if (!bulk_arg[j]) {
                   const bool separate = valid && delta_off[j] >= 0 && tangent[j] == t0 &&
                                         ((jpos[j] & 1) == 0) && ((kRes * t0) % 2 == 0);
-                  coop_arg[j] = kRes * Dims::Size(j) >= 16 && __all_sync(0xffffffffu, separate);
+                  coop_arg[j] = kRes * Dims::Size(j) >= kCooperativeCellDoubles &&
+                                __all_sync(0xffffffffu, separate);
                 }
               }
             }
@@ -1221,7 +1245,7 @@ __global__ void __launch_bounds__(
             if (kStage && (bulk_arg[j] || bulk_all)) {
               // Stage the cell exactly as it lies in global memory.
               double* cell = bulk_all ? jbuf + (jpos[j] - bulk_all_base)
-                                      : jbuf + 32 * kRes * (Dims::Offset(j) - Dims::Offset(kFirst)) +
+                                      : jbuf + StageOffset<kRes, Dims>(kFirst, j) +
                                             lane * kRes * tan;
               if (!kGeneric && !crs && (kRes * kSize) % 2 == 0) {
                 double2* mine = reinterpret_cast<double2*>(cell);  // conflict-free 128-bit
@@ -1243,9 +1267,13 @@ __global__ void __launch_bounds__(
               // so a store instruction fills whole sectors (a thread writing its own cell
               // with 8-byte stores at a 288-byte stride costs four requests per sector:
               // 2340 L2 write requests per tile measured on the pose graph for 576 ideal).
+              // (cells padded to a pitch whose 16-byte multiple is odd mod 8: a 288-byte
+              // pitch puts every fourth lane on the same banks, 604 wavefronts for 172)
               const int cell_doubles = kRes * tan;
-              double* stage = jbuf + 32 * kRes * (Dims::Offset(j) - Dims::Offset(kFirst));
-              double* cell = stage + lane * cell_doubles;
+              constexpr int kPitch = (kRes * kSize + 2) | 2;  // even, and pitch / 2 is odd
+              static_assert(kPitch <= kRes * kSize + 4, "stage pitch within the argument's slack");
+              double* stage = jbuf + StageOffset<kRes, Dims>(kFirst, j);
+              double* cell = stage + lane * kPitch;
 #pragma unroll
               for (int r = 0; r < kRes; ++r)
 #pragma unroll
@@ -1253,12 +1281,15 @@ __global__ void __launch_bounds__(
                   if (is_live(c)) cell[r * tan + dcol(c)] = out[r].v[kLane0 + c];
               __syncwarp();
               const int pairs = cell_doubles / 2;
-#pragma unroll 4
+              constexpr int kMaxPairs = kRes * kSize / 2;
+#pragma unroll 8
               for (int owner = 0; owner < 32; ++owner) {
                 const int base = __shfl_sync(0xffffffffu, jpos[j], owner);
-                for (int w = lane; w < pairs; w += 32)
-                  reinterpret_cast<double2*>(a.jacobian_values + base)[w] =
-                      reinterpret_cast<const double2*>(stage + owner * cell_doubles)[w];
+                double2* __restrict__ dst = reinterpret_cast<double2*>(a.jacobian_values + base);
+                const double2* src = reinterpret_cast<const double2*>(stage + owner * kPitch);
+#pragma unroll
+                for (int w0 = 0; w0 < kMaxPairs; w0 += 32)
+                  if (w0 + lane < pairs) dst[w0 + lane] = src[w0 + lane];
               }
               __syncwarp();
             } else if (valid && active) {
@@ -1300,7 +1331,7 @@ __global__ void __launch_bounds__(
                   for (int j = kFirst; j < kEnd; ++j)
                     if (bulk_arg[j])
                       BulkStore(a.jacobian_values + bulk_base[j],
-                                jbuf + 32 * kRes * (Dims::Offset(j) - Dims::Offset(kFirst)),
+                                jbuf + StageOffset<kRes, Dims>(kFirst, j),
                                 32 * kRes * (kGeneric ? tangent[j] : Dims::Size(j)) * 8);
                   BulkCommit();
                 }

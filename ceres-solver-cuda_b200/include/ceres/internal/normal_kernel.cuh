@@ -35,6 +35,42 @@ namespace internal {
 
 constexpr int kNormalThreads = 128;
 
+// ---- TMA bulk load global -> shared, completion on an mbarrier (cp.async.bulk; SASS UBLKCP):
+// the copy engine writes shared memory by itself, so the 6 KB of cells per tile cost no LSU
+// wavefronts (with 16-byte cp.async they cost one wavefront per returned sector, four times
+// the 128-byte ideal, and made this kernel L1-bound at 88 %: profiles/r2_normal_product_*).
+__device__ __forceinline__ unsigned SharedAddress(const void* p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void MbarrierInit(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SharedAddress(bar)), "r"(count)
+               : "memory");
+}
+__device__ __forceinline__ void MbarrierExpect(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SharedAddress(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void MbarrierWait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      "  .reg .pred p;\n"
+      "WAIT_%=:\n"
+      "  mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "  @!p bra WAIT_%=;\n"
+      "}" ::"r"(SharedAddress(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void BulkLoad(void* smem, const void* gmem, unsigned bytes,
+                                         unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(SharedAddress(smem)),
+      "l"(gmem), "r"(bytes), "r"(SharedAddress(bar))
+      : "memory");
+}
+
 template <int kRes, int... Ns>
 struct NormalPlan {
   using Dims = BlockDims<Ns...>;
@@ -45,7 +81,7 @@ struct NormalPlan {
   // the staged reductions reuse the cell stage just consumed: [lane][pitch] sums + 32 offsets
   static constexpr int kGradientDoubles = 32 * StagePitch(Dims::MaxSize()) + 16;
   static constexpr int kStageDoubles = kJDoubles > kGradientDoubles ? kJDoubles : kGradientDoubles;
-  static constexpr int kWarpDoubles = 2 * kXDoubles + 2 * kStageDoubles;
+  static constexpr int kWarpDoubles = 2 * kXDoubles + 2 * kStageDoubles + 2;  // + two mbarriers
   static constexpr int kBytes = (kNormalThreads / 32) * kWarpDoubles * 8;
   static constexpr int kCtas = (228 * 1024) / (kBytes + 1024) >= 3 ? 3
                                : ((228 * 1024) / (kBytes + 1024) >= 2 ? 2 : 1);
@@ -65,6 +101,19 @@ __global__ void __launch_bounds__(kNormalThreads, NormalPlan<kRes, Ns...>::kCtas
   double* const wbuf = reinterpret_cast<double*>(smem) + warp * Plan::kWarpDoubles;
   auto xstage = [&](int s) { return wbuf + s * Plan::kXDoubles; };
   auto jstage = [&](int s) { return wbuf + 2 * Plan::kXDoubles + s * Plan::kStageDoubles; };
+  unsigned long long* const bars =
+      reinterpret_cast<unsigned long long*>(wbuf + 2 * Plan::kXDoubles + 2 * Plan::kStageDoubles);
+  // bulk loads need 16-byte aligned sources: the cell size is even, so only the bases matter
+  bool bulk = true;
+#pragma unroll
+  for (int j = 0; j < kNB; ++j)
+    bulk = bulk && ((reinterpret_cast<uintptr_t>(a.values + a.base[j]) & 15) == 0);
+  if (bulk && lane == 0) {
+    MbarrierInit(bars, 1);
+    MbarrierInit(bars + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
   const int n = a.n;
   const int num_tiles = (n + 31) / 32;
   const int warps = gridDim.x * (kNormalThreads / 32);
@@ -96,19 +145,15 @@ __global__ void __launch_bounds__(kNormalThreads, NormalPlan<kRes, Ns...>::kCtas
       double* js = jstage(s);
       const int rb0 = tile * 32;
       const int blocks = min(32, n - rb0);
+      if (bulk && lane == 0) MbarrierExpect(bars + s, blocks * kRes * kNP * 8);
 #pragma unroll
       for (int j = 0; j < kNB; ++j) {
         const int kCell = kRes * Dims::Size(j);  // doubles per cell, constant after unrolling
         const double* src = a.values + (a.base[j] + static_cast<int64_t>(rb0) * kCell);
         double* dst = js + 32 * kRes * Dims::Offset(j);
         const int doubles = blocks * kCell;
-        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-#pragma unroll
-          for (int it = 0; it < (kCell + 1) / 2; ++it) {
-            const int e = 2 * (it * 32 + lane);
-            if (e + 1 < doubles) CpAsync16(dst + e, src + e);
-            else if (e < doubles) CpAsync8(dst + e, src + e);
-          }
+        if (bulk) {
+          if (lane == 0) BulkLoad(dst, src, doubles * 8, bars + s);
         } else {
 #pragma unroll
           for (int it = 0; it < kCell; ++it) {
@@ -136,6 +181,7 @@ __global__ void __launch_bounds__(kNormalThreads, NormalPlan<kRes, Ns...>::kCtas
     load_offsets(tile + 2 * warps, soff_next);
     CpAsyncWait<1>();
     __syncwarp();
+    if (bulk) MbarrierWait(bars + s, (k >> 1) & 1);  // stage s is used every other tile
 
     const int rb = tile * 32 + lane;
     const bool valid = rb < n;
@@ -146,11 +192,15 @@ __global__ void __launch_bounds__(kNormalThreads, NormalPlan<kRes, Ns...>::kCtas
 #pragma unroll
     for (int j = 0; j < kNB; ++j) {
       const int kS = Dims::Size(j);
-      const double* cell = js + 32 * kRes * Dims::Offset(j) + lane * kRes * kS;
+      // (16-byte reads: the lane stride kRes * kS * 8 is a multiple of 16, conflict free)
+      const double2* cell =
+          reinterpret_cast<const double2*>(js + 32 * kRes * Dims::Offset(j) + lane * kRes * kS);
 #pragma unroll
-      for (int r = 0; r < kRes; ++r)
-#pragma unroll
-        for (int c = 0; c < kS; ++c) J[r][Dims::Offset(j) + c] = valid ? cell[r * kS + c] : 0.0;
+      for (int e = 0; e < kRes * kS; e += 2) {
+        const double2 v = cell[e / 2];
+        J[e / kS][Dims::Offset(j) + e % kS] = valid ? v.x : 0.0;
+        J[(e + 1) / kS][Dims::Offset(j) + (e + 1) % kS] = valid ? v.y : 0.0;
+      }
       const double* xw = xs + 2 * (32 * Dims::PitchChunksBefore(j) + lane * Dims::WindowPitch(j)) +
                          (soff_cur[j] & 1);
 #pragma unroll
@@ -190,6 +240,9 @@ __global__ void __launch_bounds__(kNormalThreads, NormalPlan<kRes, Ns...>::kCtas
       }
       __syncwarp();
     }
+    // the stage was read and rewritten through the generic proxy; the copy engine (async
+    // proxy) overwrites it two tiles from now
+    if (bulk) FenceProxyAsyncShared();
 #pragma unroll
     for (int j = 0; j < kNB; ++j) soff_cur[j] = soff_issue[j];
   }
