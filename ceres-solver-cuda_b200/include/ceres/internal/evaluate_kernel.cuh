@@ -802,7 +802,7 @@ __global__ void __launch_bounds__(
 #pragma unroll
     for (int j = 0; j < kNB; ++j) soff_issue[j] = soff_next[j];
     const unsigned parity_issue = parity_of(soff_issue);
-    load_offsets(kChunked ? walk_rb(walk) : rb + 2 * stride, soff_next);
+    if constexpr (kStages == 1) load_offsets(kChunked ? walk_rb(walk) : rb + 2 * stride, soff_next);
     bool issued = false;
     auto issue_next = [&]() {
       if (!issued) {
@@ -812,7 +812,15 @@ __global__ void __launch_bounds__(
       }
       issued = true;
     };
-    if constexpr (kStages > 1) issue_next();
+    if constexpr (kStages > 1) {
+      // The copies are issued first: the load below then writes the registers the copies
+      // just released.  In the other order ptxas keeps the loaded value in a temporary and
+      // moves it into the loop-carried register right here, i.e. it waits for a load it
+      // issued ~40 instructions earlier (one fifth of the kernel's stall samples,
+      // profiles/r2_L_ncu_summary.txt).
+      issue_next();
+      load_offsets(kChunked ? walk_rb(walk) : rb + 2 * stride, soff_next);
+    }
 
     if constexpr (kPrefetch) {
       // this thread's copies for block k have landed ...

@@ -1,5 +1,6 @@
 // C interface of the test/bench driver (see driver.h).  Python binds it with
 // ctypes (ceres-solver-cuda_b200/binding.py).
+#include <cstdlib>
 #include <cstring>
 
 #include "driver.h"
@@ -417,6 +418,9 @@ int drv_solve(void* h, int linear_solver_type, int cuda_sparse, int max_num_iter
   if (cuda_sparse) options.sparse_linear_algebra_library_type = ceres::CUDA_SPARSE;
   options.max_num_iterations = max_num_iterations;
   options.cuda_device = device;
+  // (tests that compare two trust-region loops ask for near-exact steps: with the default
+  // eta = 0.1 the point where conjugate gradients stop depends on the last bits of the sums)
+  if (const char* eta = std::getenv("CB200_DRIVER_ETA")) options.eta = std::atof(eta);
   if (ordering) {
     auto* o = new ceres::ParameterBlockOrdering;
     for (size_t k = 0; k < dp->pb_offset.size(); ++k)

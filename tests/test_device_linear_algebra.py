@@ -125,6 +125,11 @@ def test_trust_region_loop_on_the_device_matches_the_host_loop(kind, monkeypatch
         spec = P.bal_problem(12, 600, 2600, seed=33, subset_manifold=kind == "bal_subset")
         rng = np.random.default_rng(33)
         spec.pb_values[:] += rng.normal(0, 0.02, spec.pb_values.size) * (np.abs(spec.pb_values) < 50)
+    # near-exact steps: with the default eta = 0.1 conjugate gradients stop on the model
+    # decrease after a handful of iterations, the stopping iteration depends on the last bits
+    # of the (atomic) sums and the two trajectories drift apart (measured up to 6e-5 on the
+    # final cost, run to run)
+    monkeypatch.setenv("CB200_DRIVER_ETA", "1e-9")
     dev = B.solve(spec, B.CGNR, max_num_iterations=12, cuda_sparse=True)
     monkeypatch.setenv("CB200_HOST_TRUST_REGION", "1")
     host = B.solve(spec, B.CGNR, max_num_iterations=12, cuda_sparse=True)
@@ -132,8 +137,6 @@ def test_trust_region_loop_on_the_device_matches_the_host_loop(kind, monkeypatch
     assert dev["iterations"] == host["iterations"]
     assert dev["successful_steps"] == host["successful_steps"]
     assert abs(dev["initial_cost"] - host["initial_cost"]) <= 1e-12 * host["initial_cost"]
-    # (inexact steps: conjugate gradients stop on the model decrease, so rounding in the
-    # reductions moves the iterates a little; measured 2e-7 on the final cost)
     assert abs(dev["final_cost"] - host["final_cost"]) <= 1e-5 * host["final_cost"]
     assert np.max(np.abs(dev["x"] - host["x"])) <= 1e-3 * np.max(np.abs(host["x"]))
     assert dev["final_cost"] < 0.9 * dev["initial_cost"]
