@@ -1569,6 +1569,11 @@ static int EvaluateOnDevice(cb200_engine* e, uint32_t flags, bool want_r, bool w
     a.functors = t->d_functors.ptr;
     a.loss_table = t->d_loss_table.ptr;
     a.loss_index = t->num_losses > 1 ? t->d_loss_index.ptr : nullptr;
+    if (t->num_losses == 1 && t->loss_table.size() <= CB200_INLINE_LOSS_BYTES &&
+        t->loss_table.size() % 8 == 0 && !t->loss_table.empty()) {
+      a.loss_inline_size = static_cast<uint32_t>(t->loss_table.size());
+      std::memcpy(a.loss_inline, t->loss_table.data(), t->loss_table.size());
+    }
     a.parameter_block = t->d_pb.ptr;
     a.jacobian_pos = t->d_jpos.ptr;
     a.jacobian_row_stride = t->d_jstride.ptr;

@@ -118,6 +118,19 @@ __device__ __forceinline__ void ForEachBlock(F&& f, std::index_sequence<Js...>) 
   (f(std::integral_constant<int, static_cast<int>(Js)>{}), ...);
 }
 
+// sqrt(rho') of the Corrector.  rho' is 1 for most blocks and a positive finite number
+// otherwise: reciprocal square root + one correction step (within 1 ulp) instead of the
+// library's sequence with its slow-path call; other arguments take the library function.
+__device__ __forceinline__ double DeviceSqrt(double x) {
+  if (x > 0.0 && x < 1.7976931348623157e308) {
+    const double r = rsqrt(x);
+    const double y = x * r;
+    const double root = fma(fma(-y, y, x), 0.5 * r, y);
+    return x == 1.0 ? 1.0 : root;  // (exactly 1 in the quadratic region of a robust loss)
+  }
+  return ::sqrt(x);
+}
+
 __device__ __forceinline__ bool IsValidValue(double x) {
   return ::fabs(x) <= 1.7976931348623157e308 && x != 1e302;
 }
@@ -280,6 +293,14 @@ __device__ __forceinline__ void CpAsyncWait() {
 #ifndef CB200_KERNEL_BULK_STORE
 #define CB200_KERNEL_BULK_STORE 1     // staged cells leave through TMA bulk copies (UBLKCP)
 #endif
+#ifndef CB200_KERNEL_GRADIENT_DESTINATIONS
+// 1: the lane that stages its gradient sums also stages the destination of every element, so
+// a reduction round is two shared loads, one 64-bit multiply-add for the address and the
+// red (4 instructions); 0: destinations are staged per lane and every round recomputes the
+// (row, column) of its element (9 instructions, measured: 111 of the BAL kernel's 1184
+// instructions per tile were address arithmetic of the rounds).
+#define CB200_KERNEL_GRADIENT_DESTINATIONS 1
+#endif
 #ifndef CB200_KERNEL_GATHER
 // How a warp's 32 residual blocks fetch their parameter blocks into shared memory:
 // 0 = warp-cooperative, 8-byte copies, consecutive lanes on consecutive doubles of a block;
@@ -386,7 +407,10 @@ template <int kRes, int... Ns>
 struct PassPlan {
   using Dims = BlockDims<Ns...>;
   static constexpr int kNB = Dims::kNumBlocks;
-  static constexpr bool kSinglePass = kRes * Dims::kNumParameters <= 40;
+#ifndef CB200_SINGLE_PASS_LIMIT
+#define CB200_SINGLE_PASS_LIMIT 40  // live output doubles (residuals x parameters) up to which one pass is used
+#endif
+  static constexpr bool kSinglePass = kRes * Dims::kNumParameters <= CB200_SINGLE_PASS_LIMIT;
   static constexpr int kMaxWidth = Dims::MaxSize() > 8 ? Dims::MaxSize() : 8;
   // pass index of block j: greedy grouping of consecutive blocks up to kMaxWidth lanes
   __host__ __device__ static constexpr int PassOf(int j) {
@@ -517,11 +541,15 @@ struct SmemPlan {
   // per warp: the cells of the arguments of one derivative pass side by side (Jacobian
   // staging; with several passes the region is reused pass after pass) ...
   static constexpr int kJacobianDoubles = MaxStageDoubles<kRes, Ns...>();
-  // ... and one padded row per lane for the staged gradient reductions (plus, per lane,
-  // the destination offset and the live-column mask: 2 x 32 ints).  Within a derivative
-  // pass every gradient is out before the first cell is staged, so the gradient staging
-  // reuses the Jacobian staging buffer.
+  // ... and one padded row per lane for the staged gradient reductions plus, per staged
+  // element, its destination in the gradient (an int; -1 = nothing to add).  Within a
+  // derivative pass every gradient is out before the first cell is staged, so the gradient
+  // staging reuses the Jacobian staging buffer.
+#if CB200_KERNEL_GRADIENT_DESTINATIONS
+  static constexpr int kGradientStage = 48 * StagePitch(Dims::MaxSize());
+#else
   static constexpr int kGradientStage = 32 * StagePitch(Dims::MaxSize()) + 32;
+#endif
   // (several passes: each pass waits for the previous pass's stores to leave the staging
   // region before its own gradient uses it, so the alias holds pass by pass)
   static constexpr bool kGradientAliasesJacobian = kGradientStage <= kJacobianDoubles;
@@ -802,25 +830,23 @@ __global__ void __launch_bounds__(
 #pragma unroll
     for (int j = 0; j < kNB; ++j) soff_issue[j] = soff_next[j];
     const unsigned parity_issue = parity_of(soff_issue);
-    if constexpr (kStages == 1) load_offsets(kChunked ? walk_rb(walk) : rb + 2 * stride, soff_next);
     bool issued = false;
     auto issue_next = [&]() {
       if (!issued) {
         // (cooperative gathers overwrite rows other lanes read: the warp must be past them)
         if constexpr (kPrefetch && kStages == 1 && CB200_KERNEL_GATHER != 1) __syncwarp();
         prefetch(stage ^ 1, rb_next, soff_issue);
+        // The offsets of block k+2 are fetched right after the copies of block k+1 are
+        // issued: the load then writes the registers the copies just released and is not
+        // needed for a whole iteration.  Fetched before, ptxas keeps the loaded value in a
+        // temporary and moves it into the loop-carried register at once, i.e. it waits for
+        // a load it issued ~40 instructions earlier (one fifth of the kernel's stall
+        // samples, profiles/r2_L_ncu_summary.txt).
+        load_offsets(kChunked ? walk_rb(walk) : rb + 2 * stride, soff_next);
       }
       issued = true;
     };
-    if constexpr (kStages > 1) {
-      // The copies are issued first: the load below then writes the registers the copies
-      // just released.  In the other order ptxas keeps the loaded value in a temporary and
-      // moves it into the loop-carried register right here, i.e. it waits for a load it
-      // issued ~40 instructions earlier (one fifth of the kernel's stall samples,
-      // profiles/r2_L_ncu_summary.txt).
-      issue_next();
-      load_offsets(kChunked ? walk_rb(walk) : rb + 2 * stride, soff_next);
-    }
+    if constexpr (kStages > 1) issue_next();
 
     if constexpr (kPrefetch) {
       // this thread's copies for block k have landed ...
@@ -872,8 +898,12 @@ __global__ void __launch_bounds__(
       }
     }
     int respos = 0;
-    if (out_residuals)
-      respos = kAffine ? a.residual_base + tt * kRes : table(Smem::kSlotResidual, a.residual_pos, tt);
+    if (out_residuals) {
+      // (the Jet-free variant has no affine instantiation and reads its tables straight from
+      // global memory: take the computed position when the engine found the table affine)
+      const bool computed = kAffine || (!kJets && (a.affine & CB200_AFFINE_RESIDUAL));
+      respos = computed ? a.residual_base + tt * kRes : table(Smem::kSlotResidual, a.residual_pos, tt);
+    }
     int row_stride_crs = 0;
     if constexpr (kJets) {
       if (crs && out_jacobian)
@@ -884,7 +914,26 @@ __global__ void __launch_bounds__(
     int loss_at = 0;
     if (a.loss_index)
       loss_at = table(Smem::kSlotLoss, a.loss_index, tt);  // (direct load when not staged)
-    const Loss& loss = losses[loss_at];
+    // One loss object for the whole type (the usual case): its bytes ride in the kernel
+    // arguments, i.e. the constant bank, and become instruction operands; otherwise they
+    // are loaded from the table (a global load per block whose latency is exposed: 4-8 % of
+    // the Jet-free kernel's stall samples, profiles/r2_costonly_ncu_summary.txt).
+    // (the loss table already holds byte copies of the host objects - with their unused
+    // host vtable pointer - so a byte copy is all a loss needs to support)
+    constexpr bool kInlineLoss = sizeof(Loss) % 8 == 0 && sizeof(Loss) <= CB200_INLINE_LOSS_BYTES;
+    constexpr int kLossWords = kInlineLoss ? static_cast<int>(sizeof(Loss) / 8) : 1;
+    struct alignas(8) LossBytes { unsigned long long w[kLossWords]; } loss_bytes;
+    if constexpr (kInlineLoss) {
+      if (a.loss_inline_size == sizeof(Loss)) {
+#pragma unroll
+        for (int w = 0; w < kLossWords; ++w) loss_bytes.w[w] = a.loss_inline[w];
+      } else {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(losses + loss_at);
+#pragma unroll
+        for (int w = 0; w < kLossWords; ++w) loss_bytes.w[w] = __ldg(src + w);
+      }
+    }
+    const Loss& loss = kInlineLoss ? *reinterpret_cast<const Loss*>(&loss_bytes) : losses[loss_at];
 
     const double* sp = stage_params(stage);
     auto param = [&](int j, int i) -> double {
@@ -938,7 +987,7 @@ __global__ void __launch_bounds__(
         cost = 0.5 * rho[0];
         if (out_residuals) {
           // corrector.h:82-147 then :159-166
-          const double sqrt_rho1 = ::sqrt(rho[1]);
+          const double sqrt_rho1 = DeviceSqrt(rho[1]);
           double scaling = sqrt_rho1;
           if (!(s == 0.0 || rho[2] <= 0.0)) {
             const double D = 1.0 + 2.0 * s * rho[2] / rho[1];
@@ -1054,7 +1103,7 @@ __global__ void __launch_bounds__(
             double rho[3];
             loss.Evaluate(s, rho);
             cost = 0.5 * rho[0];
-            sqrt_rho1 = ::sqrt(rho[1]);
+            sqrt_rho1 = DeviceSqrt(rho[1]);
             residual_scaling = sqrt_rho1;
             if (!LossCurvature<Loss>::kNonPositive && !(s == 0.0 || rho[2] <= 0.0)) {
               const double D = 1.0 + 2.0 * s * rho[2] / rho[1];
@@ -1193,6 +1242,29 @@ __global__ void __launch_bounds__(
               // per-lane sums and let consecutive lanes add to consecutive addresses, so
               // one red instruction touches a few sectors instead of 32.
               constexpr int kPitch = StagePitch(kSize);
+#if CB200_KERNEL_GRADIENT_DESTINATIONS
+#pragma unroll
+              for (int c = 0; c < kSize; ++c) {
+                gbuf[lane * kPitch + c] = g[c];
+                const bool goes = emit && (!kGeneric || ((lv >> c) & 1u));
+                obuf[lane * kPitch + c] =
+                    goes ? doff + (kGeneric ? __popc(lv & ((1u << c) - 1u)) : c) : -1;
+              }
+              if constexpr (kPitch > kSize) obuf[lane * kPitch + kSize] = -1;  // the pad slot
+              __syncwarp();
+              // rounds walk the staged rows as they lie (pad slots included: no division)
+              if (!kGeneric && kPitch == kSize && emit_mask == 0xffffffffu) {
+#pragma unroll
+                for (int it = 0; it < kPitch; ++it)
+                  RedAdd(a.gradient + obuf[it * 32 + lane], gbuf[it * 32 + lane]);
+              } else {
+#pragma unroll
+                for (int it = 0; it < kPitch; ++it) {
+                  const int d = obuf[it * 32 + lane];
+                  RedAddIf(d >= 0, a.gradient + d, gbuf[it * 32 + lane]);
+                }
+              }
+#else
 #pragma unroll
               for (int c = 0; c < kSize; ++c) gbuf[lane * kPitch + c] = g[c];
               // destination of every lane's sums (or -1) and, with manifolds, its live
@@ -1227,6 +1299,7 @@ __global__ void __launch_bounds__(
                   RedAddIf(d >= 0, a.gradient + (d + c), sum);
                 }
               }
+#endif
               __syncwarp();
             } else if (emit) {
               double* __restrict__ dst = a.gradient + doff;

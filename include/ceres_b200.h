@@ -76,6 +76,8 @@ typedef struct cb200_parameter_block {
 /* Arguments of one kernel launch for one residual-block type.  All pointers are
  * device pointers owned by the engine.  Structure-of-arrays, argument-major:
  * entry (arg j, residual block t) of a per-argument table is at [j * n + t]. */
+#define CB200_INLINE_LOSS_BYTES 64
+
 typedef struct cb200_launch_args {
   int32_t n;                      /* residual blocks of this type on this rank */
   uint32_t output_residuals;
@@ -131,6 +133,13 @@ typedef struct cb200_launch_args {
   int32_t num_chunks;
   int32_t num_peers;
   double* peer_gradient[CB200_MAX_PEERS];
+  /* A copy of the loss object when the type has exactly one (loss_index == NULL) and it fits:
+   * kernel arguments live in the constant bank, so the kernel reads the loss parameters as
+   * instruction operands instead of loading them from loss_table for every residual block.
+   * loss_inline_size == 0: not provided, read loss_table. */
+  uint32_t loss_inline_size;
+  uint32_t reserved0;
+  uint64_t loss_inline[CB200_INLINE_LOSS_BYTES / 8];
 } cb200_launch_args;
 
 #define CB200_AFFINE_RESIDUAL 1u

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <random>
 #include <vector>
 
@@ -85,6 +86,7 @@ int main(int argc, char** argv) {
   a.functors = Upload(functors);
   std::vector<char> lb((char*)&loss, (char*)&loss + sizeof(loss));
   a.loss_table = Upload(lb); a.loss_index = nullptr;
+  if (!std::getenv("KBENCH_NO_INLINE_LOSS")) { a.loss_inline_size = sizeof(loss); std::memcpy(a.loss_inline, &loss, sizeof(loss)); }
   a.state_offset = Upload(soff); a.delta_offset = Upload(doff); a.jacobian_pos = Upload(jpos);
   a.residual_pos = Upload(respos); a.parameter_block = nullptr; a.parameter_block_table = nullptr;
   a.jacobian_row_stride = nullptr; a.state = Upload(state); a.plus_jacobians = nullptr;
@@ -117,6 +119,12 @@ int main(int argc, char** argv) {
     for (double v : gh) { gs += v; ga += std::fabs(v); }
     for (double v : jh) js += std::fabs(v);
     std::printf("checksums: gradient sum %.12e abs %.12e  jacobian abs %.12e\n", gs, ga, js);
+  }
+  {
+    using Plan = ceres::internal::SmemPlan<Functor, false, 2, 9, 3>;
+    std::printf("smem plan: %d bytes per CTA, %d CTAs per SM, Jacobian staged %d, stages %d, gather %d, passes %d\n",
+                Plan::kJetBytes, Plan::kCtas, (int)Plan::kStageJacobian, Plan::kStages, CB200_KERNEL_GATHER,
+                ceres::internal::PassPlan<2, 9, 3>::kNumPasses);
   }
   std::printf("KBENCH %s ctas=%d affine=%d fma_check=%d stage_g=%d stage_j=%d g=%d j=%d : mean %.3f ms best %.3f ms  (%.2f G blocks/s)  status=%d cost=%.6e\n",
               argc > 6 ? argv[6] : "", CB200_RESIDENT_CTAS_SMALL, affine, CB200_KERNEL_FMA_CHECK,

@@ -58,8 +58,9 @@ if len(body) != len(instrs):
 by_region = collections.defaultdict(lambda: [0, 0, collections.Counter()])
 by_inner = collections.defaultdict(lambda: [0, 0])
 total_n = total_s = 0
-mismatch = sum(1 for r, (text, _) in zip(body, instrs)
-               if r[idx['Source']].split()[-1 if False else 0].lstrip('@!UP0123456789T ') [:3] != text.lstrip('@!UP0123456789T ')[:3])
+def stem(t):
+    return re.sub(r'^@!?U?P\w+\s+', '', t.strip()).split()[0].rstrip(';').split('.')[0]
+mismatch = sum(1 for r, (text, _) in zip(body, instrs) if stem(r[idx['Source']]) != stem(text))
 if mismatch:
     print(f"warning: {mismatch} opcode mismatches between profile and disassembly", file=sys.stderr)
 for r, (text, (ifile, iline, ofile, oline)) in zip(body, instrs):
