@@ -26,6 +26,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges cost nothing unless a tool is attached
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -913,6 +914,14 @@ struct cb200_engine {
       return (e)->Fail(CB200_ERROR_CUDA, "%s: %s", #call, cudaGetErrorString(err__));  \
   } while (0)
 
+namespace {
+// NVTX range over one C-ABI call (Nsight Systems / Compute timelines: SURVEY.md section 5).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
+
 extern "C" {
 
 const char* cb200_version(void) { return "ceres_b200 0.1 (sm_100a)"; }
@@ -1059,6 +1068,7 @@ int cb200_engine_set_shard(cb200_engine* e, int32_t rank, int32_t world_size) {
 }
 
 int cb200_engine_finalize(cb200_engine* e) {
+  NvtxRange nvtx_range("cb200_engine_finalize");
   if (!e || e->finalized) return CB200_ERROR_INVALID_ARGUMENT;
   if (!e->planning) CB200_CUDA(e, cudaSetDevice(e->device));
   const int64_t nrb = e->num_rb;
@@ -1499,6 +1509,7 @@ int cb200_nccl_unique_id(void* out) {
 
 int cb200_engine_comm_init(cb200_engine* e, const void* unique_id, int32_t rank,
                            int32_t world_size) {
+  NvtxRange nvtx_range("cb200_engine_comm_init");
   if (!e || !unique_id) return CB200_ERROR_INVALID_ARGUMENT;
   if (e->planning) return e->Fail(CB200_ERROR_CUDA, "planning-only engine");
   NcclApi* n = GetNccl();
@@ -1678,6 +1689,7 @@ static int FinishTiming(cb200_engine* e) {
 int cb200_engine_evaluate(cb200_engine* e, const double* state, const double* plus_jacobians,
                           uint32_t flags, double* cost, double* residuals, double* gradient,
                           double* jacobian_values) {
+  NvtxRange nvtx_range("cb200_engine_evaluate");
   if (!e) return CB200_ERROR_INVALID_ARGUMENT;
   if (!e->finalized) return e->Fail(CB200_ERROR_NOT_FINALIZED, "evaluate before finalize");
   if (e->planning) return e->Fail(CB200_ERROR_CUDA, "planning-only engine: no device, no CPU fallback");
@@ -1724,6 +1736,7 @@ int cb200_engine_evaluate_device(cb200_engine* e, const double* state_device,
                                  const double* plus_jacobians_device, uint32_t flags,
                                  int want_residuals, int want_gradient, int want_jacobian,
                                  double* cost) {
+  NvtxRange nvtx_range("cb200_engine_evaluate_device");
   if (!e) return CB200_ERROR_INVALID_ARGUMENT;
   if (!e->finalized) return e->Fail(CB200_ERROR_NOT_FINALIZED, "evaluate before finalize");
   if (e->planning) return e->Fail(CB200_ERROR_CUDA, "planning-only engine: no device, no CPU fallback");
@@ -1869,6 +1882,7 @@ static int PrepareLinearAlgebra(cb200_engine* e, bool need_residuals) {
 }
 
 int cb200_engine_jacobian_multiply(cb200_engine* e, int transpose, const double* x, double* y) {
+  NvtxRange nvtx_range("cb200_engine_jacobian_multiply");
   int rc = PrepareLinearAlgebra(e, false);
   if (rc != CB200_OK) return rc;
   if (!x || !y) return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "x and y are required");
@@ -1894,6 +1908,7 @@ int cb200_engine_jacobian_multiply(cb200_engine* e, int transpose, const double*
 }
 
 int cb200_engine_jacobian_squared_column_norm(cb200_engine* e, double* out) {
+  NvtxRange nvtx_range("cb200_engine_jacobian_squared_column_norm");
   int rc = PrepareLinearAlgebra(e, false);
   if (rc != CB200_OK) return rc;
   if (!out) return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "out is required");
@@ -1909,6 +1924,7 @@ int cb200_engine_jacobian_squared_column_norm(cb200_engine* e, double* out) {
 }
 
 int cb200_engine_jacobian_scale_columns(cb200_engine* e, const double* scale) {
+  NvtxRange nvtx_range("cb200_engine_jacobian_scale_columns");
   int rc = PrepareLinearAlgebra(e, false);
   if (rc != CB200_OK) return rc;
   if (!scale) return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "scale is required");
@@ -2041,6 +2057,7 @@ static int CgnrSolve(cb200_engine* e, const double* d_squared, bool d_squared_on
 int cb200_engine_cgnr_solve(cb200_engine* e, const double* d_squared,
                             const cb200_cgnr_options* options, double* solution,
                             cb200_cgnr_summary* summary) {
+  NvtxRange nvtx_range("cb200_engine_cgnr_solve");
   if (e && !solution) return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "solution is required");
   return CgnrSolve(e, d_squared, false, options, solution, summary);
 }
@@ -2060,6 +2077,7 @@ static int PrepareTrustRegion(cb200_engine* e) {
 }
 
 int cb200_engine_state_upload(cb200_engine* e, const double* state) {
+  NvtxRange nvtx_range("cb200_engine_state_upload");
   int rc = PrepareTrustRegion(e);
   if (rc != CB200_OK) return rc;
   if (!state) return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "state is required");
@@ -2071,6 +2089,7 @@ int cb200_engine_state_upload(cb200_engine* e, const double* state) {
 }
 
 int cb200_engine_state_download(cb200_engine* e, int which, double* state) {
+  NvtxRange nvtx_range("cb200_engine_state_download");
   int rc = PrepareTrustRegion(e);
   if (rc != CB200_OK) return rc;
   if (!state || which < 0 || which > 1 || !e->tr_state_valid)
@@ -2083,6 +2102,7 @@ int cb200_engine_state_download(cb200_engine* e, int which, double* state) {
 
 int cb200_engine_evaluate_state(cb200_engine* e, int which, uint32_t flags, int want_residuals,
                                 int want_gradient, int want_jacobian, double* cost) {
+  NvtxRange nvtx_range("cb200_engine_evaluate_state");
   int rc = PrepareTrustRegion(e);
   if (rc != CB200_OK) return rc;
   if (which < 0 || which > 1 || !e->tr_state_valid)
@@ -2124,6 +2144,7 @@ int cb200_engine_jacobi_scale(cb200_engine* e, int compute) {
 
 int cb200_engine_trust_region_step(cb200_engine* e, const cb200_step_options* options,
                                    cb200_step_summary* summary) {
+  NvtxRange nvtx_range("cb200_engine_trust_region_step");
   int rc = PrepareLinearAlgebra(e, true);
   if (rc == CB200_OK) rc = PrepareTrustRegion(e);
   if (rc != CB200_OK) return rc;

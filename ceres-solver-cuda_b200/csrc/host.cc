@@ -19,6 +19,7 @@
 #include "ceres/internal/program.h"
 #include "ceres/internal/sparse_matrix.h"
 #include "ceres/problem.h"
+#include <nvtx3/nvToolsExt.h>
 
 namespace ceres {
 namespace internal {
@@ -947,6 +948,7 @@ class ProgramEvaluatorCUDA final : public Evaluator {
 
   bool Evaluate(const EvaluateOptions& evaluate_options, const double* state, double* cost,
                 double* residuals, double* gradient, SparseMatrix* jacobian) override {
+    struct Range { Range() { nvtxRangePushA("ProgramEvaluatorCUDA::Evaluate"); } ~Range() { nvtxRangePop(); } } nvtx_range;
     const auto start = std::chrono::steady_clock::now();
     if (options_.device < 0) {
       std::fprintf(stderr, "Evaluate on a planning-only evaluator: no device, no CPU fallback\n");

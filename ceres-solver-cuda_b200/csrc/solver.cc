@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <nvtx3/nvToolsExt.h>
 
 namespace ceres {
 namespace {
@@ -632,8 +633,10 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
 }
 
 void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* summary) {
+  nvtxRangePushA("ceres::Solve");
   Solver solver;
   solver.Solve(options, problem, summary);
+  nvtxRangePop();
 }
 
 }  // namespace ceres

@@ -308,6 +308,9 @@ __device__ __forceinline__ void CpAsyncWait() {
 // 2 = warp-cooperative, 16-byte pieces of the aligned windows.
 #define CB200_KERNEL_GATHER 2
 #endif
+#ifndef CB200_KERNEL_PARAM_READ128
+#define CB200_KERNEL_PARAM_READ128 1  // gather 2: the owner reads its windows with 16-byte loads
+#endif
 #ifndef CB200_KERNEL_EARLY_PREFETCH
 // 1: parameters and functor are double-buffered and the copies for block k+1 are issued
 // before block k is computed; 0: single-buffered, issued after block k's last functor call.
@@ -957,10 +960,35 @@ __global__ void __launch_bounds__(
     const Functor& functor = *functor_ptr;
 
     double xval[kNP];
+    if constexpr (kPrefetch && CB200_KERNEL_GATHER == 2 && CB200_KERNEL_PARAM_READ128) {
+      // The owner reads its windows in 16-byte pieces (lane pitch odd in pieces: conflict
+      // free, 4 wavefronts per instruction) and picks the doubles by the block's parity; the
+      // 8-byte reads at an even lane pitch are two-way bank conflicted (72 wavefronts per tile
+      // for 48 ideal, against 28 this way) and the shared-memory pipe is the busiest unit.
 #pragma unroll
-    for (int j = 0; j < kNB; ++j)
+      for (int j = 0; j < kNB; ++j) {
+        constexpr int kMaxW = Dims::MaxSize() / 2 + 1;
+        double2 w[kMaxW];
+        const double2* src = reinterpret_cast<const double2*>(sp) +
+                             (32 * Dims::PitchChunksBefore(j) + lane * Dims::WindowPitch(j));
 #pragma unroll
-      for (int i = 0; i < Dims::Size(j); ++i) xval[Dims::Offset(j) + i] = param(j, i);
+        for (int c = 0; c < kMaxW; ++c)
+          if (c < Dims::WindowChunks(j)) w[c] = src[c];
+        const bool odd = (parity_cur >> j) & 1u;
+#pragma unroll
+        for (int i = 0; i < Dims::Size(j); ++i) {
+          // element i of the block is double (parity + i) of the window
+          const double even_pick = (i & 1) ? w[i / 2].y : w[i / 2].x;
+          const double odd_pick = ((i + 1) & 1) ? w[(i + 1) / 2].y : w[(i + 1) / 2].x;
+          xval[Dims::Offset(j) + i] = odd ? odd_pick : even_pick;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kNB; ++j)
+#pragma unroll
+        for (int i = 0; i < Dims::Size(j); ++i) xval[Dims::Offset(j) + i] = param(j, i);
+    }
 
     double res[kRes];
     bool ok = true;

@@ -78,8 +78,9 @@ struct NormalPlan {
   static constexpr int kNP = Dims::kNumParameters;
   static constexpr int kXDoubles = 32 * 2 * Dims::PitchChunksBefore(kNB);  // one x stage of a warp
   static constexpr int kJDoubles = 32 * kRes * kNP;                    // one cell stage of a warp
-  // the staged reductions reuse the cell stage just consumed: [lane][pitch] sums + 32 offsets
-  static constexpr int kGradientDoubles = 32 * StagePitch(Dims::MaxSize()) + 16;
+  // the staged reductions reuse the cell stage just consumed: [lane][pitch] sums and,
+  // per element, its destination (an int)
+  static constexpr int kGradientDoubles = 48 * StagePitch(Dims::MaxSize());
   static constexpr int kStageDoubles = kJDoubles > kGradientDoubles ? kJDoubles : kGradientDoubles;
   static constexpr int kWarpDoubles = 2 * kXDoubles + 2 * kStageDoubles + 2;  // + two mbarriers
   static constexpr int kBytes = (kNormalThreads / 32) * kWarpDoubles * 8;
@@ -187,25 +188,41 @@ __global__ void __launch_bounds__(kNormalThreads, NormalPlan<kRes, Ns...>::kCtas
     const bool valid = rb < n;
     const double* xs = xstage(s);
     const double* js = jstage(s);
-    // this lane's cells and x entries -> registers
+    // this lane's cells and x entries -> registers (block sizes reach the loops below as
+    // compile-time constants: with a loop variable in their place the arrays are indexed
+    // dynamically and live in local memory - 288 bytes of stack and a third of the stall
+    // samples in profiles/r2_normal_product_ncu_summary.txt)
     double J[kRes][kNP], x[kNP];
+    ForEachBlock(
+        [&](auto jc) {
+          constexpr int j = decltype(jc)::value;
+          constexpr int kS = Dims::Size(j);
+          constexpr int kO = Dims::Offset(j);
+          // (16-byte reads: the lane stride kRes * kS * 8 is a multiple of 16, conflict free)
+          const double2* cell =
+              reinterpret_cast<const double2*>(js + 32 * kRes * kO + lane * kRes * kS);
 #pragma unroll
-    for (int j = 0; j < kNB; ++j) {
-      const int kS = Dims::Size(j);
-      // (16-byte reads: the lane stride kRes * kS * 8 is a multiple of 16, conflict free)
-      const double2* cell =
-          reinterpret_cast<const double2*>(js + 32 * kRes * Dims::Offset(j) + lane * kRes * kS);
+          for (int e = 0; e < kRes * kS; e += 2) {
+            const double2 v = cell[e / 2];
+            J[e / kS][kO + e % kS] = valid ? v.x : 0.0;
+            J[(e + 1) / kS][kO + (e + 1) % kS] = valid ? v.y : 0.0;
+          }
+          // the x window in 16-byte pieces (odd lane pitch: conflict free), picked by parity
+          constexpr int kW = Dims::WindowChunks(j);
+          const double2* xw = reinterpret_cast<const double2*>(xs) +
+                              (32 * Dims::PitchChunksBefore(j) + lane * Dims::WindowPitch(j));
+          double2 w[kW];
 #pragma unroll
-      for (int e = 0; e < kRes * kS; e += 2) {
-        const double2 v = cell[e / 2];
-        J[e / kS][Dims::Offset(j) + e % kS] = valid ? v.x : 0.0;
-        J[(e + 1) / kS][Dims::Offset(j) + (e + 1) % kS] = valid ? v.y : 0.0;
-      }
-      const double* xw = xs + 2 * (32 * Dims::PitchChunksBefore(j) + lane * Dims::WindowPitch(j)) +
-                         (soff_cur[j] & 1);
+          for (int c = 0; c < kW; ++c) w[c] = xw[c];
+          const bool odd = soff_cur[j] & 1;
 #pragma unroll
-      for (int c = 0; c < kS; ++c) x[Dims::Offset(j) + c] = valid ? xw[c] : 0.0;
-    }
+          for (int c = 0; c < kS; ++c) {
+            const double even_pick = (c & 1) ? w[c / 2].y : w[c / 2].x;
+            const double odd_pick = ((c + 1) & 1) ? w[(c + 1) / 2].y : w[(c + 1) / 2].x;
+            x[kO + c] = valid ? (odd ? odd_pick : even_pick) : 0.0;
+          }
+        },
+        std::make_index_sequence<kNB>{});
     double t[kRes];
 #pragma unroll
     for (int r = 0; r < kRes; ++r) {
@@ -217,29 +234,32 @@ __global__ void __launch_bounds__(kNormalThreads, NormalPlan<kRes, Ns...>::kCtas
     __syncwarp();  // every lane has its cells: the stage can take the sums
     double* gbuf = jstage(s);
     int* obuf = reinterpret_cast<int*>(gbuf + 32 * StagePitch(Dims::MaxSize()));
+    ForEachBlock(
+        [&](auto jc) {
+          constexpr int j = decltype(jc)::value;
+          constexpr int kS = Dims::Size(j);
+          constexpr int kO = Dims::Offset(j);
+          constexpr int kPitch = StagePitch(kS);
+          // sums and, per element, its destination (-1: nothing to add; pad slots too), so
+          // a round is two shared loads, one address and the red - no division
 #pragma unroll
-    for (int j = 0; j < kNB; ++j) {
-      const int kS = Dims::Size(j);
-      const int kPitch = StagePitch(kS);
+          for (int c = 0; c < kS; ++c) {
+            double acc = 0.0;
 #pragma unroll
-      for (int c = 0; c < kS; ++c) {
-        double acc = 0.0;
+            for (int r = 0; r < kRes; ++r) acc += J[r][kO + c] * t[r];
+            gbuf[lane * kPitch + c] = acc;
+            obuf[lane * kPitch + c] = valid ? soff_cur[j] + c : -1;
+          }
+          if constexpr (kPitch > kS) obuf[lane * kPitch + kS] = -1;
+          __syncwarp();
 #pragma unroll
-        for (int r = 0; r < kRes; ++r) acc += J[r][Dims::Offset(j) + c] * t[r];
-        gbuf[lane * kPitch + c] = acc;
-      }
-      obuf[lane] = valid ? soff_cur[j] : -1;
-      __syncwarp();
-#pragma unroll
-      for (int it = 0; it < kS; ++it) {
-        const int e = it * 32 + lane;
-        const int row = e / kS;
-        const int c = e - row * kS;
-        const int d = obuf[row];
-        RedAddIf(d >= 0, a.y + (d + c), gbuf[row * kPitch + c]);
-      }
-      __syncwarp();
-    }
+          for (int it = 0; it < kPitch; ++it) {
+            const int d = obuf[it * 32 + lane];
+            RedAddIf(d >= 0, a.y + d, gbuf[it * 32 + lane]);
+          }
+          __syncwarp();
+        },
+        std::make_index_sequence<kNB>{});
     // the stage was read and rewritten through the generic proxy; the copy engine (async
     // proxy) overwrites it two tiles from now
     if (bulk) FenceProxyAsyncShared();

@@ -108,6 +108,30 @@ int main(int argc, char** argv) {
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     if (it >= 3) { best = ms < best ? ms : best; sum += ms; }
   }
+  if (std::getenv("KBENCH_NORMAL")) {
+    // y += J'(J x) on the Jacobian just written (the conjugate-gradient product)
+    cb200_normal_args na{};
+    na.n = n; na.offset = a.state_offset; na.x = a.state; na.values = jac;
+    na.base[0] = 6 * n; na.base[1] = 0;
+    double* y; CK(cudaMalloc(&y, 8 * state.size() + 16));
+    na.y = y;
+    float nbest = 1e9f, nsum = 0;
+    for (int it = 0; it < reps + 3; ++it) {
+      CK(cudaMemsetAsync(y, 0, 8 * state.size(), s));
+      cudaEventRecord(e0, s);
+      int rc = ceres::internal::LaunchNormalProduct<2, 9, 3>(&na, s);
+      cudaEventRecord(e1, s);
+      CK(cudaStreamSynchronize(s));
+      if (rc) { std::printf("normal product launch failed %d\n", rc); return 1; }
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      if (it >= 3) { nbest = ms < nbest ? ms : nbest; nsum += ms; }
+    }
+    std::vector<double> yh(state.size());
+    CK(cudaMemcpy(yh.data(), y, 8 * yh.size(), cudaMemcpyDeviceToHost));
+    double ys = 0, ya = 0; for (double v : yh) { ys += v; ya += std::fabs(v); }
+    std::printf("KNORMAL %s : mean %.3f ms best %.3f ms (%.0f GB/s of Jacobian values)  y sum %.12e abs %.12e\n",
+                argc > 6 ? argv[6] : "", nsum / reps, nbest, 192.0 * n / (nsum / reps) / 1e6, ys, ya);
+  }
   int st; CK(cudaMemcpy(&st, status, 4, cudaMemcpyDeviceToHost));
   std::vector<double> part(grid_max); CK(cudaMemcpy(part.data(), cp, 8 * (size_t)grid_max, cudaMemcpyDeviceToHost));
   double cost = 0; for (double v : part) cost += v;
