@@ -1039,6 +1039,11 @@ __global__ void __launch_bounds__(
       int bulk_all_base = 0;
 #pragma unroll
       for (int j = 0; j < kNB; ++j) { bulk_arg[j] = false; coop_arg[j] = false; bulk_base[j] = 0; }
+      // (made after the first functor call: the generic variants read tangent sizes and
+      // gradient offsets from the parameter-block table, a dependent global load issued at
+      // the top of the iteration; consumed here, before the functor, it stalled the warp for
+      // the whole L2 round trip - 12 % of the pose-graph kernel's stall samples)
+      auto make_store_plan = [&]() {
       if constexpr (kStage) {
         if (out_jacobian && CB200_KERNEL_BULK_STORE) {
           if (!crs) {
@@ -1080,6 +1085,7 @@ __global__ void __launch_bounds__(
           }
         }
       }
+      };
       double sqrt_rho1 = 1.0, residual_scaling = 1.0, alpha_sq_norm = 0.0;
       bool correct = false;
       double res_corrected[kRes];
@@ -1109,6 +1115,7 @@ __global__ void __launch_bounds__(
         // Parameters and functor of this block are consumed (the last pass re-reads
         // neither): their rows take the next block's copies.
         if constexpr (p == Plan::kNumPasses - 1) issue_next();
+        if constexpr (p == 0) make_store_plan();
 
         FiniteCheck check;
 #pragma unroll
@@ -1271,12 +1278,13 @@ __global__ void __launch_bounds__(
               // one red instruction touches a few sectors instead of 32.
               constexpr int kPitch = StagePitch(kSize);
 #if CB200_KERNEL_GRADIENT_DESTINATIONS
+              int next = doff;  // destination of the next live column
 #pragma unroll
               for (int c = 0; c < kSize; ++c) {
                 gbuf[lane * kPitch + c] = g[c];
-                const bool goes = emit && (!kGeneric || ((lv >> c) & 1u));
-                obuf[lane * kPitch + c] =
-                    goes ? doff + (kGeneric ? __popc(lv & ((1u << c) - 1u)) : c) : -1;
+                const bool live_c = !kGeneric || ((lv >> c) & 1u);
+                obuf[lane * kPitch + c] = (emit && live_c) ? next : -1;
+                next += kGeneric ? static_cast<int>(live_c) : 1;
               }
               if constexpr (kPitch > kSize) obuf[lane * kPitch + kSize] = -1;  // the pad slot
               __syncwarp();
@@ -1347,7 +1355,19 @@ __global__ void __launch_bounds__(
             constexpr unsigned kAllLive = kSize >= 32 ? 0xffffffffu : ((1u << kSize) - 1u);
             const bool active = kGeneric ? delta_off[j] >= 0 : true;
             const unsigned lv = kGeneric ? live[j] : kAllLive;
-            auto dcol = [&](int c) -> int { return kGeneric ? __popc(lv & ((1u << c) - 1u)) : c; };
+            // tangent column of every ambient column: a running count of the live columns
+            // before it (once per argument; a population count per element and row measured
+            // 145 instructions per tile in the generic bundle-adjustment kernel)
+            int tangent_column[kSize];
+            {
+              int col = 0;
+#pragma unroll
+              for (int c = 0; c < kSize; ++c) {
+                tangent_column[c] = kGeneric ? col : c;
+                if constexpr (kGeneric) col += static_cast<int>((lv >> c) & 1u);
+              }
+            }
+            auto dcol = [&](int c) -> int { return tangent_column[c]; };
             auto is_live = [&](int c) -> bool { return kGeneric ? ((lv >> c) & 1u) : true; };
             const int tan = kGeneric ? tangent[j] : kSize;
             const int row_stride = crs ? row_stride_crs : tan;

@@ -81,15 +81,48 @@ int main(int argc, char** argv) {
     a.jacobian_base[0] = 6 * n; a.jacobian_step[0] = 18;
     a.jacobian_base[1] = 0; a.jacobian_step[1] = 6;
   }
+  // KBENCH_GENERIC=1: BASELINE config 4 - every camera has SubsetManifold(9, {0}) (8 tangent
+  // columns), compressed-row values (per block 2 rows of 3 point + 8 camera entries), the
+  // generic all-outputs variant with the parameter-block table.
+  const bool generic = std::getenv("KBENCH_GENERIC") != nullptr;
+  std::vector<int> pbid, pbtab;
+  if (generic) {
+    a.plain = 0; a.crs = 1;
+    a.affine = CB200_AFFINE_RESIDUAL | CB200_AFFINE_JACOBIAN;
+    a.residual_base = 0; a.row_stride = 11;
+    a.jacobian_base[0] = 3; a.jacobian_step[0] = 22;   // camera cell: after the point's 3 columns
+    a.jacobian_base[1] = 0; a.jacobian_step[1] = 22;
+    pbid.resize(2 * (size_t)n);
+    pbtab.assign(8 * ((size_t)np + nc), 0);
+    for (int p = 0; p < np; ++p) {
+      int* r = &pbtab[8 * (size_t)p];
+      r[0] = 3 * p; r[1] = 3 * p; r[2] = 3; r[3] = CB200_MANIFOLD_NONE; r[4] = 0; r[5] = -1;
+    }
+    for (int c = 0; c < nc; ++c) {
+      int* r = &pbtab[8 * ((size_t)np + c)];
+      r[0] = 3 * np + 9 * c; r[1] = 3 * np + 8 * c; r[2] = 8; r[3] = CB200_MANIFOLD_SUBSET; r[4] = 1; r[5] = -1;
+    }
+    for (size_t i = 0; i < (size_t)n; ++i) {
+      pbid[i] = np + (soff[i] - 3 * np) / 9;
+      pbid[n + i] = soff[n + i] / 3;
+      jpos[i] = 22 * (int)i + 3; jpos[n + i] = 22 * (int)i;
+    }
+  }
   const int grid_max = std::min((n + CB200_EVALUATE_THREADS - 1) / CB200_EVALUATE_THREADS, 4096);
   a.cost_partial_count = grid_max;
   a.functors = Upload(functors);
   std::vector<char> lb((char*)&loss, (char*)&loss + sizeof(loss));
   a.loss_table = Upload(lb); a.loss_index = nullptr;
+#ifdef CB200_INLINE_LOSS_BYTES
   if (!std::getenv("KBENCH_NO_INLINE_LOSS")) { a.loss_inline_size = sizeof(loss); std::memcpy(a.loss_inline, &loss, sizeof(loss)); }
+#endif
   a.state_offset = Upload(soff); a.delta_offset = Upload(doff); a.jacobian_pos = Upload(jpos);
   a.residual_pos = Upload(respos); a.parameter_block = nullptr; a.parameter_block_table = nullptr;
-  a.jacobian_row_stride = nullptr; a.state = Upload(state); a.plus_jacobians = nullptr;
+  a.jacobian_row_stride = nullptr;
+  if (generic) {
+    a.parameter_block = Upload(pbid); a.parameter_block_table = Upload(pbtab);
+    std::vector<int> rs(n, 11); a.jacobian_row_stride = Upload(rs);
+  } a.state = Upload(state); a.plus_jacobians = nullptr;
   double *res, *jac, *grad, *cp; int* status;
   CK(cudaMalloc(&res, 16 * (size_t)n)); CK(cudaMalloc(&jac, 192 * (size_t)n));
   CK(cudaMalloc(&grad, 8 * state.size())); CK(cudaMalloc(&cp, 8 * (size_t)grid_max)); CK(cudaMalloc(&status, 4));
