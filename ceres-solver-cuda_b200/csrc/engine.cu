@@ -1809,6 +1809,16 @@ static int RunJacobianWalk(cb200_engine* e, int op, const double* x, double* y) 
                           !getenv("CB200_GENERIC_NORMAL_PRODUCT");
         for (int j = 0; j < w.nb && contiguous; ++j)
           contiguous = t->jacobian_step[j] == w.kres * w.sizes[j];
+        if (!contiguous && getenv("CB200_VERBOSE")) {
+          static bool told = false;
+          if (!told)
+            std::fprintf(stderr,
+                         "cb200: table-walk normal product (thunk %d plain %d crs %d affine %u steps",
+                         t->desc.normal_product != nullptr, int(t->plain), int(w.crs), t->affine);
+          for (int j = 0; j < w.nb && !told; ++j) std::fprintf(stderr, " %d", t->jacobian_step[j]);
+          if (!told) std::fprintf(stderr, ")\n");
+          told = true;
+        }
         if (contiguous) {
           cb200_normal_args na{};
           na.n = t->n_local;
@@ -1819,6 +1829,8 @@ static int RunJacobianWalk(cb200_engine* e, int op, const double* x, double* y) 
           std::memcpy(na.base, t->jacobian_base, sizeof(na.base));
           const int rc = t->desc.normal_product(&na, s);
           if (rc == 0) break;
+          if (getenv("CB200_VERBOSE"))
+            std::fprintf(stderr, "cb200: per-type normal product declined (%d)\n", rc);
           if (rc > 0)
             return e->Fail(CB200_ERROR_CUDA, "normal product launch: %s",
                            cudaGetErrorString(static_cast<cudaError_t>(rc)));
