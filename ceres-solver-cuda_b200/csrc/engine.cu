@@ -283,7 +283,9 @@ __device__ __forceinline__ void RedAddF64(double* address, double value) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(address), "d"(value) : "memory");
 }
 
-enum { kOpRight = 0, kOpLeft = 1, kOpColumnNorm = 2, kOpScale = 3, kOpNormal = 4 };
+enum { kOpRight = 0, kOpLeft = 1, kOpColumnNorm = 2, kOpScale = 3, kOpNormal = 4,
+       kOpScaleNorm = 5 };  // kOpScaleNorm: kOpScale with x, then kOpColumnNorm into y (one pass
+                            // in the per-type kernel, two table walks otherwise)
 
 // One thread per residual block.  x / y meaning per operation:
 //   kOpRight:      y[rows] = sum_c J(r, c) x[c]        (y indexed by local residual)
@@ -891,6 +893,10 @@ struct cb200_engine {
   // diagonal, step
   DeviceBuffer<double> tr_state[2], tr_scale, tr_diagonal, tr_delta;
   bool tr_state_valid = false, tr_scale_valid = false, tr_diagonal_valid = false;
+  // la_col[7] holds the squared column norms of the Jacobian as it stands (after the Jacobi
+  // scaling): computed once per evaluation - by the scaling pass itself where the per-type
+  // kernel runs - and shared by the LM diagonal and the conjugate-gradient preconditioner.
+  bool colnorm_valid = false;
   bool plus_on_device = true;       // every manifold of the program is one PlusKernel knows
 
   void* comm = nullptr;
@@ -1529,6 +1535,7 @@ static int EvaluateOnDevice(cb200_engine* e, uint32_t flags, bool want_r, bool w
                             bool want_j) {
   cudaStream_t s = e->stream;
   if (want_j) e->jacobian_resident = true;   // values of an older evaluation are overwritten
+  if (want_j) e->colnorm_valid = false;
   if (want_r) e->residuals_resident = true;
   CB200_CUDA(e, cudaMemsetAsync(e->d_status.ptr, 0, sizeof(int32_t), s));
   const size_t ne = static_cast<size_t>(e->num_effective);
@@ -1795,46 +1802,61 @@ static int RunJacobianWalk(cb200_engine* e, int op, const double* x, double* y) 
     w.pb_table = e->d_pb_table.ptr;
     w.values = e->d_jacobian.ptr;
     const int grid = std::min((t->n_local + 255) / 256, 148 * 16);
+    // The per-type kernel (compile-time sizes, coalesced cell runs: ceres/internal/
+    // normal_kernel.cuh) where the structure allows it; the table-walk kernels otherwise.
+    {
+      constexpr uint32_t kAffinePlain =
+          CB200_AFFINE_RESIDUAL | CB200_AFFINE_JACOBIAN | CB200_AFFINE_DELTA_IS_STATE;
+      bool contiguous = t->desc.normal_product != nullptr && t->plain && !w.crs &&
+                        (t->affine & kAffinePlain) == kAffinePlain &&
+                        !getenv("CB200_GENERIC_NORMAL_PRODUCT");
+      for (int j = 0; j < w.nb && contiguous; ++j)
+        contiguous = t->jacobian_step[j] == w.kres * w.sizes[j];
+      if (!contiguous && getenv("CB200_VERBOSE")) {
+        static bool told = false;
+        if (!told)
+          std::fprintf(stderr,
+                       "cb200: table-walk linear algebra (thunk %d plain %d crs %d affine %u steps",
+                       t->desc.normal_product != nullptr, int(t->plain), int(w.crs), t->affine);
+        for (int j = 0; j < w.nb && !told; ++j) std::fprintf(stderr, " %d", t->jacobian_step[j]);
+        if (!told) std::fprintf(stderr, ")\n");
+        told = true;
+      }
+      if (contiguous) {
+        cb200_normal_args na{};
+        na.n = t->n_local;
+        na.offset = t->d_soff.ptr;
+        na.values = e->d_jacobian.ptr;
+        na.residual_base = t->residual_base;
+        std::memcpy(na.base, t->jacobian_base, sizeof(na.base));
+        switch (op) {
+          case kOpNormal: na.op = CB200_NORMAL_OP_NORMAL; na.x = x; na.y = y; break;
+          case kOpLeft: na.op = CB200_NORMAL_OP_LEFT; na.w = const_cast<double*>(x); na.y = y; break;
+          case kOpRight: na.op = CB200_NORMAL_OP_RIGHT; na.x = x; na.w = y; break;
+          case kOpColumnNorm: na.op = CB200_NORMAL_OP_COLUMN_NORM; na.y = y; break;
+          case kOpScaleNorm: na.op = CB200_NORMAL_OP_SCALE_NORM; na.x = x; na.y = y; break;
+          default: na.op = -1; break;
+        }
+        if (na.op >= 0) {
+          const int rc = t->desc.normal_product(&na, s);
+          if (rc == 0) continue;
+          if (rc > 0)
+            return e->Fail(CB200_ERROR_CUDA, "per-type linear algebra launch: %s",
+                           cudaGetErrorString(static_cast<cudaError_t>(rc)));
+          if (getenv("CB200_VERBOSE"))
+            std::fprintf(stderr, "cb200: per-type linear algebra kernel declined (%d)\n", rc);
+        }
+      }
+    }
     switch (op) {
       case kOpRight: JacobianWalkKernel<kOpRight><<<grid, 256, 0, s>>>(w, x, y); break;
       case kOpLeft: JacobianWalkKernel<kOpLeft><<<grid, 256, 0, s>>>(w, x, y); break;
       case kOpColumnNorm: JacobianWalkKernel<kOpColumnNorm><<<grid, 256, 0, s>>>(w, x, y); break;
+      case kOpScaleNorm:
+        JacobianWalkKernel<kOpScale><<<grid, 256, 0, s>>>(w, x, nullptr);
+        JacobianWalkKernel<kOpColumnNorm><<<grid, 256, 0, s>>>(w, nullptr, y);
+        break;
       case kOpNormal: {
-        // The per-type kernel (compile-time sizes, coalesced cell runs) where the structure
-        // allows it; the table-walk kernels below otherwise.
-        constexpr uint32_t kAffinePlain =
-            CB200_AFFINE_RESIDUAL | CB200_AFFINE_JACOBIAN | CB200_AFFINE_DELTA_IS_STATE;
-        bool contiguous = t->desc.normal_product != nullptr && t->plain && !w.crs &&
-                          (t->affine & kAffinePlain) == kAffinePlain &&
-                          !getenv("CB200_GENERIC_NORMAL_PRODUCT");
-        for (int j = 0; j < w.nb && contiguous; ++j)
-          contiguous = t->jacobian_step[j] == w.kres * w.sizes[j];
-        if (!contiguous && getenv("CB200_VERBOSE")) {
-          static bool told = false;
-          if (!told)
-            std::fprintf(stderr,
-                         "cb200: table-walk normal product (thunk %d plain %d crs %d affine %u steps",
-                         t->desc.normal_product != nullptr, int(t->plain), int(w.crs), t->affine);
-          for (int j = 0; j < w.nb && !told; ++j) std::fprintf(stderr, " %d", t->jacobian_step[j]);
-          if (!told) std::fprintf(stderr, ")\n");
-          told = true;
-        }
-        if (contiguous) {
-          cb200_normal_args na{};
-          na.n = t->n_local;
-          na.offset = t->d_soff.ptr;
-          na.x = x;
-          na.y = y;
-          na.values = e->d_jacobian.ptr;
-          std::memcpy(na.base, t->jacobian_base, sizeof(na.base));
-          const int rc = t->desc.normal_product(&na, s);
-          if (rc == 0) break;
-          if (getenv("CB200_VERBOSE"))
-            std::fprintf(stderr, "cb200: per-type normal product declined (%d)\n", rc);
-          if (rc > 0)
-            return e->Fail(CB200_ERROR_CUDA, "normal product launch: %s",
-                           cudaGetErrorString(static_cast<cudaError_t>(rc)));
-        }
         int cell_doubles = 0;
         for (int j = 0; j < w.nb; ++j) cell_doubles += w.kres * w.sizes[j];
         const size_t smem =
@@ -1936,6 +1958,7 @@ int cb200_engine_jacobian_squared_column_norm(cb200_engine* e, double* out) {
 }
 
 int cb200_engine_jacobian_scale_columns(cb200_engine* e, const double* scale) {
+  if (e) e->colnorm_valid = false;
   NvtxRange nvtx_range("cb200_engine_jacobian_scale_columns");
   int rc = PrepareLinearAlgebra(e, false);
   if (rc != CB200_OK) return rc;
@@ -1982,11 +2005,14 @@ static int CgnrSolve(cb200_engine* e, const double* d_squared, bool d_squared_on
     CB200_CUDA(e, cudaMemcpyAsync(d2, d_squared, col_bytes, cudaMemcpyHostToDevice, s));
   // b = J' residuals, preconditioner from the column norms
   CB200_CUDA(e, cudaMemsetAsync(b, 0, col_bytes, s));
-  CB200_CUDA(e, cudaMemsetAsync(colnorm, 0, col_bytes, s));
   if ((rc = RunJacobianWalk(e, kOpLeft, residuals, b)) != CB200_OK) return rc;
-  if ((rc = RunJacobianWalk(e, kOpColumnNorm, nullptr, colnorm)) != CB200_OK) return rc;
   if ((rc = SumOverRanks(e, b, ne)) != CB200_OK) return rc;
-  if ((rc = SumOverRanks(e, colnorm, ne)) != CB200_OK) return rc;
+  if (!e->colnorm_valid) {
+    CB200_CUDA(e, cudaMemsetAsync(colnorm, 0, col_bytes, s));
+    if ((rc = RunJacobianWalk(e, kOpColumnNorm, nullptr, colnorm)) != CB200_OK) return rc;
+    if ((rc = SumOverRanks(e, colnorm, ne)) != CB200_OK) return rc;
+    e->colnorm_valid = true;
+  }
   CB200_CUDA(e, cudaMemsetAsync(S, 0, 3 * kSCount * sizeof(double), s));
   CgInitKernel<<<vgrid, 256, 0, s>>>(ne, colnorm, d2, b, minv, r, p, x, S, red);
   CB200_CUDA(e, cudaMemcpyAsync(e->h_la_scalars, S, kSCount * sizeof(double),
@@ -2149,7 +2175,15 @@ int cb200_engine_jacobi_scale(cb200_engine* e, int compute) {
   }
   if (!e->tr_scale_valid)
     return e->Fail(CB200_ERROR_INVALID_ARGUMENT, "jacobi_scale: no scale computed yet");
-  if ((rc = RunJacobianWalk(e, kOpScale, e->tr_scale.ptr, nullptr)) != CB200_OK) return rc;
+  {
+    // J <- J diag(scale), and the squared column norms of the result in the same pass: the
+    // LM diagonal and the preconditioner of this iteration need them (la_col[7])
+    double* col = e->la_col[7].ptr;
+    CB200_CUDA(e, cudaMemsetAsync(col, 0, static_cast<size_t>(ne) * sizeof(double), s));
+    if ((rc = RunJacobianWalk(e, kOpScaleNorm, e->tr_scale.ptr, col)) != CB200_OK) return rc;
+    if ((rc = SumOverRanks(e, col, ne)) != CB200_OK) return rc;
+    e->colnorm_valid = true;
+  }
   CB200_CUDA(e, cudaStreamSynchronize(s));
   return CB200_OK;
 }
@@ -2173,9 +2207,12 @@ int cb200_engine_trust_region_step(cb200_engine* e, const cb200_step_options* op
   // LM diagonal (levenberg_marquardt_strategy.cc:83-96): clamp(diag(J'J)) / radius
   if (!options->reuse_diagonal || !e->tr_diagonal_valid) {
     double* col = e->la_col[7].ptr;
-    CB200_CUDA(e, cudaMemsetAsync(col, 0, static_cast<size_t>(ne) * sizeof(double), s));
-    if ((rc = RunJacobianWalk(e, kOpColumnNorm, nullptr, col)) != CB200_OK) return rc;
-    if ((rc = SumOverRanks(e, col, ne)) != CB200_OK) return rc;
+    if (!e->colnorm_valid) {
+      CB200_CUDA(e, cudaMemsetAsync(col, 0, static_cast<size_t>(ne) * sizeof(double), s));
+      if ((rc = RunJacobianWalk(e, kOpColumnNorm, nullptr, col)) != CB200_OK) return rc;
+      if ((rc = SumOverRanks(e, col, ne)) != CB200_OK) return rc;
+      e->colnorm_valid = true;
+    }
     ClampKernel<<<grid, 256, 0, s>>>(ne, col, options->min_lm_diagonal, options->max_lm_diagonal,
                                      e->tr_diagonal.ptr);
     e->tr_diagonal_valid = true;

@@ -78,20 +78,32 @@ struct NormalPlan {
   static constexpr int kNP = Dims::kNumParameters;
   static constexpr int kXDoubles = 32 * 2 * Dims::PitchChunksBefore(kNB);  // one x stage of a warp
   static constexpr int kJDoubles = 32 * kRes * kNP;                    // one cell stage of a warp
-  // the staged reductions reuse the cell stage just consumed: [lane][pitch] sums and,
-  // per element, its destination (an int)
+  // staged reductions: [lane][pitch] sums and, per element, its destination (an int)
   static constexpr int kGradientDoubles = 48 * StagePitch(Dims::MaxSize());
-  static constexpr int kStageDoubles = kJDoubles > kGradientDoubles ? kJDoubles : kGradientDoubles;
-  static constexpr int kWarpDoubles = 2 * kXDoubles + 2 * kStageDoubles + 2;  // + two mbarriers
+  static constexpr int kStageDoubles = kJDoubles;
+  // [x stage 0 | x stage 1 | cell stage 0 | cell stage 1 | reduction stage | two mbarriers]
+  // (the reductions have their own stage: the scaling operation writes its cells back from
+  // the cell stage with a bulk store that is still reading it while the sums are staged)
+  static constexpr int kWarpDoubles = 2 * kXDoubles + 2 * kStageDoubles + kGradientDoubles + 2;
   static constexpr int kBytes = (kNormalThreads / 32) * kWarpDoubles * 8;
   static constexpr int kCtas = (228 * 1024) / (kBytes + 1024) >= 3 ? 3
                                : ((228 * 1024) / (kBytes + 1024) >= 2 ? 2 : 1);
   static constexpr bool kFits = kBytes <= 227 * 1024 && (kRes * kNP) % 2 == 0;
 };
 
-template <int kRes, int... Ns>
+// Operations of the kernel (cb200_normal_args::op).  All of them walk the cells once.
+constexpr int kNormalOpNormal = CB200_NORMAL_OP_NORMAL;          // y += J'(J x)
+constexpr int kNormalOpLeft = CB200_NORMAL_OP_LEFT;              // y += J' w
+constexpr int kNormalOpRight = CB200_NORMAL_OP_RIGHT;            // w  = J x
+constexpr int kNormalOpColumnNorm = CB200_NORMAL_OP_COLUMN_NORM; // y += squared column norms
+constexpr int kNormalOpScaleNorm = CB200_NORMAL_OP_SCALE_NORM;   // J <- J diag(x) in place, then
+                                                                 // y += its squared column norms
+
+template <int kOp, int kRes, int... Ns>
 __global__ void __launch_bounds__(kNormalThreads, NormalPlan<kRes, Ns...>::kCtas)
     NormalProductKernel(const cb200_normal_args a) {
+  constexpr bool kGatherX = kOp == kNormalOpNormal || kOp == kNormalOpRight || kOp == kNormalOpScaleNorm;
+  constexpr bool kReduce = kOp != kNormalOpRight;
   using Dims = BlockDims<Ns...>;
   using Plan = NormalPlan<kRes, Ns...>;
   constexpr int kNB = Plan::kNB;
@@ -102,8 +114,9 @@ __global__ void __launch_bounds__(kNormalThreads, NormalPlan<kRes, Ns...>::kCtas
   double* const wbuf = reinterpret_cast<double*>(smem) + warp * Plan::kWarpDoubles;
   auto xstage = [&](int s) { return wbuf + s * Plan::kXDoubles; };
   auto jstage = [&](int s) { return wbuf + 2 * Plan::kXDoubles + s * Plan::kStageDoubles; };
-  unsigned long long* const bars =
-      reinterpret_cast<unsigned long long*>(wbuf + 2 * Plan::kXDoubles + 2 * Plan::kStageDoubles);
+  double* const gbuf = wbuf + 2 * Plan::kXDoubles + 2 * Plan::kStageDoubles;
+  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(
+      wbuf + 2 * Plan::kXDoubles + 2 * Plan::kStageDoubles + Plan::kGradientDoubles);
   // bulk loads need 16-byte aligned sources: the cell size is even, so only the bases matter
   bool bulk = true;
 #pragma unroll
@@ -131,7 +144,7 @@ __global__ void __launch_bounds__(kNormalThreads, NormalPlan<kRes, Ns...>::kCtas
     if (tile < num_tiles) {
       double* xs = xstage(s);
 #pragma unroll
-      for (int j = 0; j < kNB; ++j) {
+      for (int j = 0; j < (kGatherX ? kNB : 0); ++j) {
         const int kW = Dims::WindowChunks(j);
 #pragma unroll
         for (int it = 0; it < kW; ++it) {
@@ -142,6 +155,13 @@ __global__ void __launch_bounds__(kNormalThreads, NormalPlan<kRes, Ns...>::kCtas
           CpAsync16(xs + 2 * (32 * Dims::PitchChunksBefore(j) + owner * Dims::WindowPitch(j) + c),
                     a.x + ((so & ~1) + 2 * c));
         }
+      }
+      if constexpr (kOp == kNormalOpLeft) {
+        // the rows of the residual-space vector ride the same pipeline (the x stage is free)
+        const int rbw = min(tile * 32 + lane, n - 1);
+#pragma unroll
+        for (int r = 0; r < kRes; ++r)
+          CpAsync8(xs + lane * kRes + r, a.w + (a.residual_base + static_cast<int64_t>(rbw) * kRes + r));
       }
       double* js = jstage(s);
       const int rb0 = tile * 32;
@@ -178,6 +198,11 @@ __global__ void __launch_bounds__(kNormalThreads, NormalPlan<kRes, Ns...>::kCtas
     int soff_issue[kNB];
 #pragma unroll
     for (int j = 0; j < kNB; ++j) soff_issue[j] = soff_next[j];
+    if constexpr (kOp == kNormalOpScaleNorm) {
+      // last tile's write-back still reads stage s ^ 1
+      if (bulk && lane == 0) BulkWaitRead();
+      __syncwarp();
+    }
     prefetch(s ^ 1, tile + warps, soff_issue);
     load_offsets(tile + 2 * warps, soff_next);
     CpAsyncWait<1>();
@@ -207,59 +232,127 @@ __global__ void __launch_bounds__(kNormalThreads, NormalPlan<kRes, Ns...>::kCtas
             J[e / kS][kO + e % kS] = valid ? v.x : 0.0;
             J[(e + 1) / kS][kO + (e + 1) % kS] = valid ? v.y : 0.0;
           }
-          // the x window in 16-byte pieces (odd lane pitch: conflict free), picked by parity
-          constexpr int kW = Dims::WindowChunks(j);
-          const double2* xw = reinterpret_cast<const double2*>(xs) +
-                              (32 * Dims::PitchChunksBefore(j) + lane * Dims::WindowPitch(j));
-          double2 w[kW];
+          if constexpr (kGatherX) {
+            // the x window in 16-byte pieces (odd lane pitch: conflict free), picked by parity
+            constexpr int kW = Dims::WindowChunks(j);
+            const double2* xw = reinterpret_cast<const double2*>(xs) +
+                                (32 * Dims::PitchChunksBefore(j) + lane * Dims::WindowPitch(j));
+            double2 w[kW];
 #pragma unroll
-          for (int c = 0; c < kW; ++c) w[c] = xw[c];
-          const bool odd = soff_cur[j] & 1;
+            for (int c = 0; c < kW; ++c) w[c] = xw[c];
+            const bool odd = soff_cur[j] & 1;
 #pragma unroll
-          for (int c = 0; c < kS; ++c) {
-            const double even_pick = (c & 1) ? w[c / 2].y : w[c / 2].x;
-            const double odd_pick = ((c + 1) & 1) ? w[(c + 1) / 2].y : w[(c + 1) / 2].x;
-            x[kO + c] = valid ? (odd ? odd_pick : even_pick) : 0.0;
+            for (int c = 0; c < kS; ++c) {
+              const double even_pick = (c & 1) ? w[c / 2].y : w[c / 2].x;
+              const double odd_pick = ((c + 1) & 1) ? w[(c + 1) / 2].y : w[(c + 1) / 2].x;
+              x[kO + c] = valid ? (odd ? odd_pick : even_pick) : 0.0;
+            }
           }
         },
         std::make_index_sequence<kNB>{});
+    // rows of this block in the residual-space vector (residual positions are affine)
+    double* const wrow = a.w + (a.residual_base + static_cast<int64_t>(rb) * kRes);
     double t[kRes];
 #pragma unroll
-    for (int r = 0; r < kRes; ++r) {
-      double acc = 0.0;
+    for (int r = 0; r < kRes; ++r) t[r] = 0.0;
+    if constexpr (kOp == kNormalOpNormal || kOp == kNormalOpRight) {
 #pragma unroll
-      for (int c = 0; c < kNP; ++c) acc += J[r][c] * x[c];
-      t[r] = acc;
+      for (int r = 0; r < kRes; ++r) {
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < kNP; ++c) acc += J[r][c] * x[c];
+        t[r] = acc;
+      }
+    } else if constexpr (kOp == kNormalOpLeft) {
+      if (valid) {
+#pragma unroll
+        for (int r = 0; r < kRes; ++r) t[r] = xs[lane * kRes + r];
+      }
     }
-    __syncwarp();  // every lane has its cells: the stage can take the sums
-    double* gbuf = jstage(s);
-    int* obuf = reinterpret_cast<int*>(gbuf + 32 * StagePitch(Dims::MaxSize()));
-    ForEachBlock(
-        [&](auto jc) {
-          constexpr int j = decltype(jc)::value;
-          constexpr int kS = Dims::Size(j);
-          constexpr int kO = Dims::Offset(j);
-          constexpr int kPitch = StagePitch(kS);
-          // sums and, per element, its destination (-1: nothing to add; pad slots too), so
-          // a round is two shared loads, one address and the red - no division
+    if constexpr (kOp == kNormalOpRight) {
+      if (valid) {
 #pragma unroll
-          for (int c = 0; c < kS; ++c) {
-            double acc = 0.0;
+        for (int r = 0; r < kRes; ++r) wrow[r] = t[r];
+      }
+    }
+    if constexpr (kOp == kNormalOpScaleNorm) {
+      // scale the columns, put the cells back where they were staged and send the runs home
+      ForEachBlock(
+          [&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            constexpr int kS = Dims::Size(j);
+            constexpr int kO = Dims::Offset(j);
+            double2* cell = reinterpret_cast<double2*>(jstage(s) + 32 * kRes * kO + lane * kRes * kS);
 #pragma unroll
-            for (int r = 0; r < kRes; ++r) acc += J[r][kO + c] * t[r];
-            gbuf[lane * kPitch + c] = acc;
-            obuf[lane * kPitch + c] = valid ? soff_cur[j] + c : -1;
+            for (int r = 0; r < kRes; ++r)
+#pragma unroll
+              for (int c = 0; c < kS; ++c) J[r][kO + c] *= x[kO + c];
+            if (valid) {
+#pragma unroll
+              for (int e = 0; e < kRes * kS; e += 2)
+                cell[e / 2] = make_double2(J[e / kS][kO + e % kS], J[(e + 1) / kS][kO + (e + 1) % kS]);
+            }
+          },
+          std::make_index_sequence<kNB>{});
+      if (bulk) {
+        FenceProxyAsyncShared();
+        __syncwarp();
+        if (lane == 0) {
+          const int rb0 = tile * 32;
+          const int blocks = min(32, n - rb0);
+#pragma unroll
+          for (int j = 0; j < kNB; ++j) {
+            const int kCell = kRes * Dims::Size(j);
+            BulkStore(a.values + (a.base[j] + static_cast<int64_t>(rb0) * kCell),
+                      jstage(s) + 32 * kRes * Dims::Offset(j), blocks * kCell * 8);
           }
-          if constexpr (kPitch > kS) obuf[lane * kPitch + kS] = -1;
-          __syncwarp();
+          BulkCommit();
+        }
+      } else {
+        __syncwarp();
+        const int rb0 = tile * 32;
+        const int blocks = min(32, n - rb0);
 #pragma unroll
-          for (int it = 0; it < kPitch; ++it) {
-            const int d = obuf[it * 32 + lane];
-            RedAddIf(d >= 0, a.y + d, gbuf[it * 32 + lane]);
-          }
-          __syncwarp();
-        },
-        std::make_index_sequence<kNB>{});
+        for (int j = 0; j < kNB; ++j) {
+          const int kCell = kRes * Dims::Size(j);
+          double* dst = a.values + (a.base[j] + static_cast<int64_t>(rb0) * kCell);
+          const double* src = jstage(s) + 32 * kRes * Dims::Offset(j);
+          for (int e = lane; e < blocks * kCell; e += 32) dst[e] = src[e];
+        }
+      }
+    }
+    if constexpr (kReduce) {
+      int* obuf = reinterpret_cast<int*>(gbuf + 32 * StagePitch(Dims::MaxSize()));
+      ForEachBlock(
+          [&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            constexpr int kS = Dims::Size(j);
+            constexpr int kO = Dims::Offset(j);
+            constexpr int kPitch = StagePitch(kS);
+            // sums and, per element, its destination (-1: nothing to add; pad slots too), so
+            // a round is two shared loads, one address and the red - no division
+#pragma unroll
+            for (int c = 0; c < kS; ++c) {
+              double acc = 0.0;
+#pragma unroll
+              for (int r = 0; r < kRes; ++r)
+                acc += J[r][kO + c] * ((kOp == kNormalOpColumnNorm || kOp == kNormalOpScaleNorm)
+                                           ? J[r][kO + c]
+                                           : t[r]);
+              gbuf[lane * kPitch + c] = acc;
+              obuf[lane * kPitch + c] = valid ? soff_cur[j] + c : -1;
+            }
+            if constexpr (kPitch > kS) obuf[lane * kPitch + kS] = -1;
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < kPitch; ++it) {
+              const int d = obuf[it * 32 + lane];
+              RedAddIf(d >= 0, a.y + d, gbuf[it * 32 + lane]);
+            }
+            __syncwarp();
+          },
+          std::make_index_sequence<kNB>{});
+    }
     // the stage was read and rewritten through the generic proxy; the copy engine (async
     // proxy) overwrites it two tiles from now
     if (bulk) FenceProxyAsyncShared();
@@ -267,6 +360,9 @@ __global__ void __launch_bounds__(kNormalThreads, NormalPlan<kRes, Ns...>::kCtas
     for (int j = 0; j < kNB; ++j) soff_cur[j] = soff_issue[j];
   }
   CpAsyncWait<0>();
+  if constexpr (kOp == kNormalOpScaleNorm) {
+    if (bulk && lane == 0) BulkWaitAll();
+  }
 }
 
 template <int kRes, int... Ns>
@@ -279,15 +375,24 @@ int LaunchNormalProduct(const cb200_normal_args* args, void* stream) {
     int device = 0, sms = 0;
     cudaError_t e = cudaGetDevice(&device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    using Kernel = void (*)(const cb200_normal_args);
+    Kernel kernel = nullptr;
+    switch (args->op) {
+      case kNormalOpNormal: kernel = NormalProductKernel<kNormalOpNormal, kRes, Ns...>; break;
+      case kNormalOpLeft: kernel = NormalProductKernel<kNormalOpLeft, kRes, Ns...>; break;
+      case kNormalOpRight: kernel = NormalProductKernel<kNormalOpRight, kRes, Ns...>; break;
+      case kNormalOpColumnNorm: kernel = NormalProductKernel<kNormalOpColumnNorm, kRes, Ns...>; break;
+      case kNormalOpScaleNorm: kernel = NormalProductKernel<kNormalOpScaleNorm, kRes, Ns...>; break;
+      default: return -1;
+    }
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(NormalProductKernel<kRes, Ns...>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kBytes);
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
     const int tiles = (args->n + 31) / 32;
     const int needed = (tiles + kNormalThreads / 32 - 1) / (kNormalThreads / 32);
     const int wanted = (sms > 0 ? sms : 148) * Plan::kCtas;
-    NormalProductKernel<kRes, Ns...><<<needed < wanted ? needed : wanted, kNormalThreads,
-                                       Plan::kBytes, static_cast<cudaStream_t>(stream)>>>(*args);
+    kernel<<<needed < wanted ? needed : wanted, kNormalThreads, Plan::kBytes,
+             static_cast<cudaStream_t>(stream)>>>(*args);
     return static_cast<int>(cudaGetLastError());
   }
 }

@@ -153,19 +153,30 @@ typedef struct cb200_launch_args {
  * `stream` is a cudaStream_t.  Returns a cudaError_t value. */
 typedef int (*cb200_launch_fn)(const cb200_launch_args* args, void* stream);
 
-/* y += J'(J x) for one residual-block type on the Jacobian values left in HBM (conjugate
+/* y += J'(J x) and the other one-pass operations (CB200_NORMAL_OP_*) for one residual-block
+ * type on the Jacobian values left in HBM (conjugate
  * gradients on the normal equations; reference: CgnrSolver's two SpMVs per iteration,
  * internal/ceres/cgnr_solver.cc:190-330).  Compiled per <kNumResiduals, Ns...> next to the
  * launch thunk (ceres/internal/normal_kernel.cuh).  Only for block-sparse values of a type
  * without manifolds or constant blocks whose cells are an arithmetic progression with step
  * num_residuals * size[j]; the engine's generic kernels serve everything else. */
+#define CB200_NORMAL_OP_NORMAL 0       /* y += J'(J x) */
+#define CB200_NORMAL_OP_LEFT 1         /* y += J' w                (LeftMultiplyAndAccumulate) */
+#define CB200_NORMAL_OP_RIGHT 2        /* w  = J x                 (RightMultiplyAndAccumulate into zero) */
+#define CB200_NORMAL_OP_COLUMN_NORM 3  /* y += squared column norms (SquaredColumnNorm) */
+#define CB200_NORMAL_OP_SCALE_NORM 4   /* J <- J diag(x) in place (ScaleColumns), then y += its
+                                          squared column norms: one pass instead of two */
+
 typedef struct cb200_normal_args {
   int32_t n;               /* residual blocks of this type on this rank */
   const int32_t* offset;   /* [num_blocks][n] gradient (== state) offset of every argument */
   const double* x;         /* 16-byte aligned, followed by >= 2 doubles of slack */
   double* y;
-  const double* values;    /* this rank's Jacobian values */
+  double* values;          /* this rank's Jacobian values (written by CB200_NORMAL_OP_SCALE_NORM) */
   int32_t base[CB200_MAX_PARAMETER_BLOCKS]; /* cell (t, j) starts at base[j] + t * kRes * size[j] */
+  int32_t op;              /* CB200_NORMAL_OP_* */
+  int32_t residual_base;   /* rows of block t are w[residual_base + t * kRes ...] (affine) */
+  double* w;               /* residual-space vector of LEFT (read) and RIGHT (written) */
 } cb200_normal_args;
 typedef int (*cb200_normal_fn)(const cb200_normal_args* args, void* stream);
 

@@ -144,7 +144,7 @@ int main(int argc, char** argv) {
   if (std::getenv("KBENCH_NORMAL")) {
     // y += J'(J x) on the Jacobian just written (the conjugate-gradient product)
     cb200_normal_args na{};
-    na.n = n; na.offset = a.state_offset; na.x = a.state; na.values = jac;
+    na.n = n; na.offset = a.state_offset; na.x = a.state; na.values = jac; na.op = std::getenv("KBENCH_NORMAL_OP") ? std::atoi(std::getenv("KBENCH_NORMAL_OP")) : 0; na.w = res; na.residual_base = 0;
     na.base[0] = 6 * n; na.base[1] = 0;
     double* y; CK(cudaMalloc(&y, 8 * state.size() + 16));
     na.y = y;
