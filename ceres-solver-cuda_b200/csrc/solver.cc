@@ -482,23 +482,26 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
   const int m = program->NumResiduals();
   const int nt = std::max(1, options.num_threads);
   Buckets buckets;
-  PinnedVector x(n), x_plus(n), gradient(ne), scale(ne, 1.0), diagonal(ne), D2(ne), y(ne);
-  std::vector<double> delta(ne);
-  // only the host linear solver reads the residuals and the model on the host
-  std::vector<double> residuals, model;
+  PinnedVector x(n);
   program->ParameterBlocksToStateVector(x.data());
   auto* resident = dynamic_cast<internal::DeviceResidentJacobian*>(jacobian.get());
-  // with a device-resident Jacobian the residuals stay on the device as well
-  if (!resident) {
-    residuals.resize(m);
-    model.resize(m);
-  }
   if (resident && DeviceLoopPossible(options, *program, *impl)) {
+    // (the loop on the device needs the state on the host twice - up, and down at the end -
+    // and none of the host loop's work vectors: page-locking those cost 0.5 s on BAL L)
     MinimizeOnDevice(options, resident->engine(), fixed_cost, start, x.data(), summary);
     program->StateVectorToParameterBlocks(x.data());  // results back into the user's arrays
     summary->minimizer_time_in_seconds = Seconds() - minimizer_start;
     summary->total_time_in_seconds = Seconds() - start;
     return;
+  }
+  PinnedVector x_plus(n), gradient(ne), scale(ne, 1.0), diagonal(ne), D2(ne), y(ne);
+  std::vector<double> delta(ne);
+  // only the host linear solver reads the residuals and the model on the host
+  std::vector<double> residuals, model;
+  // with a device-resident Jacobian the residuals stay on the device as well
+  if (!resident) {
+    residuals.resize(m);
+    model.resize(m);
   }
   double* const residuals_out = resident ? nullptr : residuals.data();
   double cost = 0.0;
