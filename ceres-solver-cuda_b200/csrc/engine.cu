@@ -1176,11 +1176,16 @@ int cb200_engine_finalize(cb200_engine* e) {
       // blocks i, i + 1 of the exclusive range is valid at residual block position
       // min(first[i + 1 ...]) iff every block up to i was last touched before it.
       // A chunk is a warp's unit of work (tiles of 32 blocks, one fence and one copy at its
-      // end): about 8 chunks per warp of a full persistent grid (148 SMs x 12 warps) keeps
-      // the warps balanced, 128..2048 blocks bounds the overhead of partial tiles and fences.
+      // end), drawn from a counter by the warps of the persistent grid (148 SMs x 12 warps).
+      // About 12 chunks per warp bounds the idle tail when the warps run out of chunks; chunk
+      // lengths that are multiples of 32 leave no partial tile (at 8 GPUs half a tile in
+      // seven was idle lanes).  A cut is taken at the first valid position that makes the
+      // length a multiple of 32 once half the target is reached (with ~6.5 blocks per point
+      // such a position comes every ~200 blocks); without one by three times the target, at
+      // the last valid position within the target.
       const int64_t local_blocks = nrb * (e->rank + 1) / e->world - nrb * e->rank / e->world;
-      const int kChunkBlocks = static_cast<int>(
-          std::min<int64_t>(2048, std::max<int64_t>(128, local_blocks / (148 * 12 * 8) / 32 * 32)));
+      const int kChunkBlocks = static_cast<int>(std::min<int64_t>(
+          4096, std::max<int64_t>(128, 2 * (local_blocks / (148 * 12 * 12) - 104) / 32 * 32)));
       int i0 = -1, i1 = -1;  // active blocks [i0, i1) of this rank's exclusive interval
       for (const GradientInterval& iv : e->exchange) {
         if (iv.owner != e->rank) continue;
@@ -1223,14 +1228,19 @@ int cb200_engine_finalize(cb200_engine* e) {
           if (cut == INT32_MAX || !(prefmax < cut) || e->blocks[i + 1].tangent_size == 0) continue;
           const int64_t cut_delta = e->blocks[i + 1].delta_offset;
           if (cut <= start_rb) continue;
-          while (cut - start_rb > kChunkBlocks && best_rb > start_rb) {
+          // past three times the target without a tile-aligned cut: the best plain one
+          while (cut - start_rb > 3 * kChunkBlocks && best_rb > start_rb) {
             close_chunk(best_rb, best_delta);
             best_rb = -1;
           }
-          if (cut - start_rb > kChunkBlocks) {  // no cut inside the target size: a long chunk
+          const int32_t length = cut - start_rb;
+          if (length > 3 * kChunkBlocks) {  // no cut inside the window: a long chunk
             close_chunk(cut, cut_delta);
             best_rb = -1;
-          } else {
+          } else if (length % 32 == 0 && 2 * length >= kChunkBlocks) {
+            close_chunk(cut, cut_delta);    // whole tiles only
+            best_rb = -1;
+          } else if (length <= kChunkBlocks || best_rb <= start_rb) {
             best_rb = cut;
             best_delta = cut_delta;
           }
@@ -1429,7 +1439,7 @@ int cb200_engine_finalize(cb200_engine* e) {
   if (e->peer_plan && !e->chunk_table.empty())
     CB200_CUDA(e, e->d_chunks.Upload(e->chunk_table, e->stream));
   CB200_CUDA(e, e->d_cost_partials.Resize(static_cast<size_t>(e->total_cost_partials) + 1));
-  CB200_CUDA(e, e->d_status.Resize(1));
+  CB200_CUDA(e, e->d_status.Resize(2));  // [failure flag, chunk counter of the chunked kernel]
   CB200_CUDA(e, cudaStreamSynchronize(e->stream));
   // Layout arrays were consumed.
   std::vector<int32_t>().swap(e->jpro);
@@ -1537,7 +1547,7 @@ static int EvaluateOnDevice(cb200_engine* e, uint32_t flags, bool want_r, bool w
   if (want_j) e->jacobian_resident = true;   // values of an older evaluation are overwritten
   if (want_j) e->colnorm_valid = false;
   if (want_r) e->residuals_resident = true;
-  CB200_CUDA(e, cudaMemsetAsync(e->d_status.ptr, 0, sizeof(int32_t), s));
+  CB200_CUDA(e, cudaMemsetAsync(e->d_status.ptr, 0, 2 * sizeof(int32_t), s));
   const size_t ne = static_cast<size_t>(e->num_effective);
   // Several ranks with the peer exchange: this evaluation's [gradient | cost | failed] is
   // one of the two peer-mapped buffers.  Only what this rank's blocks add to is zeroed: the
@@ -1615,7 +1625,10 @@ static int EvaluateOnDevice(cb200_engine* e, uint32_t flags, bool want_r, bool w
         CB200_AFFINE_RESIDUAL | CB200_AFFINE_JACOBIAN | CB200_AFFINE_DELTA_IS_STATE;
     if (peer && t->desc.supports_chunks && e->d_chunks.ptr && t->plain && !a.crs && want_r &&
         want_j && a.apply_loss_function && (t->affine & kAffinePlain) == kAffinePlain &&
-        !getenv("CB200_NO_CHUNKED_KERNEL")) {
+        // (measured on B200: with two ranks the copies issued from inside the kernel slow it
+        // by more than the separate push costs - 1.15 against 1.05 ms of device time on BAL
+        // L - while from four ranks on the fused form wins: 0.37 against 0.55 ms on eight)
+        (e->world >= 4 || getenv("CB200_CHUNKED_KERNEL")) && !getenv("CB200_NO_CHUNKED_KERNEL")) {
       a.chunks = e->d_chunks.ptr;
       a.num_chunks = static_cast<int32_t>(e->chunk_table.size() / 4);
       a.num_peers = num_peers;

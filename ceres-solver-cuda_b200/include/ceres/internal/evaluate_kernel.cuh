@@ -788,11 +788,20 @@ __global__ void __launch_bounds__(
   };
   // (chunks belong to WARPS: a warp that finishes a chunk fences and copies on its own while
   // the other warps of the thread block keep evaluating)
+  // Chunks are drawn from a counter (a.status[1], zero at launch), one ahead: a static
+  // round-robin leaves the warps with 8 or 9 chunks each (10 % of the kernel at 8 GPUs).
+  auto draw_chunk = [&]() {
+    int c = 0;
+    if (lane == 0) c = atomicAdd(a.status + 1, 1);
+    return __shfl_sync(0xffffffffu, c, 0);
+  };
+  int chunk_ahead = 0;
   auto walk_rb = [&](const Walk& w) { return w.lo + w.t * 32 + lane; };
   auto walk_advance = [&](Walk& w) {
     ++w.t;
     if (w.lo + w.t * 32 >= w.hi) {
-      w.c += gridDim.x * (kEvaluateThreads / 32);
+      w.c = chunk_ahead;
+      chunk_ahead = draw_chunk();
       w.t = 0;
       load_chunk(w);
     }
@@ -800,7 +809,8 @@ __global__ void __launch_bounds__(
   Walk walk{0, 0, 0, 0};
   int rb0 = first, hi0 = n, c0 = 0, rb1 = first + stride, hi1 = n, c1 = 0;
   if constexpr (kChunked) {
-    walk.c = blockIdx.x * (kEvaluateThreads / 32) + (tid >> 5);
+    walk.c = draw_chunk();
+    chunk_ahead = draw_chunk();
     load_chunk(walk);
     rb0 = walk_rb(walk); hi0 = walk.hi; c0 = walk.c;
     walk_advance(walk);
@@ -1513,13 +1523,26 @@ __global__ void __launch_bounds__(
       // into every other rank's gradient buffer; meanwhile the other warps of this SM keep
       // evaluating.
       if (warp_rb + 32 >= limit) {
-        __threadfence();
+        // The range was added to by this warp's lanes only: ordering among them is all the
+        // reads below need (a device-wide fence here waited for every red of the chunk to be
+        // acknowledged, once per chunk and warp).  The peers read the copies after the
+        // system-scope flag exchange of ExchangeSharedKernel.
+        __threadfence_block();
         __syncwarp();
         const int4 rec = __ldg(chunk_table + c0);
-        for (int i = rec.z + lane; i < rec.w; i += 32) {
-          const double v = __ldcg(a.gradient + i);
+        // four independent loads in flight per lane: the loop is latency bound otherwise
+        for (int i0 = rec.z + lane; i0 < rec.w; i0 += 128) {
+          double v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            v[u] = i0 + 32 * u < rec.w ? __ldcg(a.gradient + i0 + 32 * u) : 0.0;
 #pragma unroll 1
-          for (int q = 0; q < a.num_peers; ++q) __stcg(a.peer_gradient[q] + i, v);
+          for (int q = 0; q < a.num_peers; ++q) {
+            double* __restrict__ dst = a.peer_gradient[q];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (i0 + 32 * u < rec.w) __stcg(dst + i0 + 32 * u, v[u]);
+          }
         }
       }
       rb0 = rb1; hi0 = hi1; c0 = c1;

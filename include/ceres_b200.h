@@ -111,7 +111,9 @@ typedef struct cb200_launch_args {
   double* jacobian_values;
   double* gradient;
   double* cost_partials;          /* one per thread block of this launch */
-  int32_t* status;                /* set non-zero when a functor fails / yields a non-finite value */
+  int32_t* status;                /* set non-zero when a functor fails / yields a non-finite value;
+                                     status[1] (zero at launch) is the work counter the
+                                     chunked variant draws its chunks from */
   /* Tables that are arithmetic progressions need not be read (found by cb200_engine_finalize;
    * typical of a single residual-block type laid out in program order, e.g. bundle adjustment):
    *   CB200_AFFINE_RESIDUAL        residual_pos[t] == residual_base + t * num_residuals

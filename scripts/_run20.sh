@@ -1,0 +1,3 @@
+cd /root/repo
+./build/kbench/kb_cur 13682 4456117 28987644 1 1 plain | grep KBENCH
+for c in 224 992; do KBENCH_CHUNK=$c ./build/kbench/kb_cur 13682 4456117 28987644 1 1 chunk$c | grep "KBENCH"; for pe in 1 7; do KBENCH_PEERS=$pe KBENCH_CHUNK=$c ./build/kbench/kb_cur 13682 4456117 28987644 1 1 chunk${c}_peers$pe | grep "KBENCH"; done; done

@@ -123,16 +123,36 @@ int main(int argc, char** argv) {
     a.parameter_block = Upload(pbid); a.parameter_block_table = Upload(pbtab);
     std::vector<int> rs(n, 11); a.jacobian_row_stride = Upload(rs);
   } a.state = Upload(state); a.plus_jacobians = nullptr;
+  // KBENCH_CHUNK=<blocks>: the chunked (multi-GPU) variant on one GPU, no peers: what the chunk
+  // walk itself costs against the grid-stride walk
+  if (const char* cb = std::getenv("KBENCH_CHUNK")) {
+    const int chunk = std::atoi(cb);
+    std::vector<int> table;
+    for (int lo = 0; lo < n; lo += chunk) {
+      const int hi = std::min(n, lo + chunk);
+      table.push_back(lo); table.push_back(hi);
+      // KBENCH_PEERS=k: the chunk's point gradient range is copied to k local stand-in buffers
+      const bool copy = std::getenv("KBENCH_PEERS") != nullptr;
+      table.push_back(copy ? soff[(size_t)n + lo] : 0);
+      table.push_back(copy ? (hi < n ? soff[(size_t)n + hi] : 3 * np) : 0);
+    }
+    a.chunks = Upload(table); a.num_chunks = (int)(table.size() / 4); a.num_peers = 0;
+    if (const char* pe = std::getenv("KBENCH_PEERS")) {
+      a.num_peers = std::atoi(pe);
+      for (int q = 0; q < a.num_peers; ++q) CK(cudaMalloc(&a.peer_gradient[q], 8 * state.size()));
+    }
+  }
   double *res, *jac, *grad, *cp; int* status;
   CK(cudaMalloc(&res, 16 * (size_t)n)); CK(cudaMalloc(&jac, 192 * (size_t)n));
-  CK(cudaMalloc(&grad, 8 * state.size())); CK(cudaMalloc(&cp, 8 * (size_t)grid_max)); CK(cudaMalloc(&status, 4));
-  CK(cudaMemset(status, 0, 4));
+  CK(cudaMalloc(&grad, 8 * state.size())); CK(cudaMalloc(&cp, 8 * (size_t)grid_max)); CK(cudaMalloc(&status, 8));
+  CK(cudaMemset(status, 0, 8));
   a.residuals = res; a.jacobian_values = jac; a.gradient = grad; a.cost_partials = cp; a.status = status;
   cudaStream_t s; CK(cudaStreamCreate(&s));
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   float best = 1e9f, sum = 0; const int reps = 10;
   for (int it = 0; it < reps + 3; ++it) {
     CK(cudaMemsetAsync(grad, 0, 8 * state.size(), s));
+    CK(cudaMemsetAsync(status, 0, 8, s));
     cudaEventRecord(e0, s);
     int rc = ceres::internal::LaunchEvaluate<Functor, Loss, 2, 9, 3>(&a, s);
     cudaEventRecord(e1, s);

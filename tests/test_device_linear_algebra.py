@@ -142,6 +142,35 @@ def test_trust_region_loop_on_the_device_matches_the_host_loop(kind, monkeypatch
     assert dev["final_cost"] < 0.9 * dev["initial_cost"]
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_ordering", [False, True])
+def test_resident_solve_runs_on_the_per_type_kernels(with_ordering, monkeypatch, capfd):
+    """CGNR + CUDA_SPARSE keeps the Jacobian in HBM in a two-region layout (the ordering's
+    first group, or - without an ordering - the parameter blocks that only appear in one
+    argument slot), so that the evaluation kernel's bulk stores and the per-type linear
+    algebra kernel apply.  The engine reports every fall-back to its table-walk kernels under
+    CB200_VERBOSE; a bundle adjustment problem must not produce one."""
+    spec = P.bal_problem(9, 400, 1800, seed=21)
+    ordering = None
+    if with_ordering:
+        ordering = np.array([0 if s == 3 else 1 for s in spec.pb_size], dtype=np.int32)
+    monkeypatch.setenv("CB200_VERBOSE", "1")
+    out = B.solve(spec, B.CGNR, max_num_iterations=5, cuda_sparse=True, ordering=ordering)
+    captured = capfd.readouterr()
+    assert out["usable"], out["message"]
+    assert out["final_cost"] < 0.5 * out["initial_cost"]
+    assert "table-walk" not in captured.err, captured.err
+    assert "declined" not in captured.err, captured.err
+    # the same solve on the table-walk kernels takes the same steps
+    monkeypatch.setenv("CB200_GENERIC_NORMAL_PRODUCT", "1")
+    monkeypatch.setenv("CB200_DRIVER_ETA", "1e-9")
+    generic = B.solve(spec, B.CGNR, max_num_iterations=5, cuda_sparse=True, ordering=ordering)
+    monkeypatch.delenv("CB200_GENERIC_NORMAL_PRODUCT")
+    typed = B.solve(spec, B.CGNR, max_num_iterations=5, cuda_sparse=True, ordering=ordering)
+    assert generic["iterations"] == typed["iterations"]
+    assert abs(generic["final_cost"] - typed["final_cost"]) <= 1e-6 * typed["final_cost"]
+
+
 def test_abi_exports_the_linear_algebra_entry_points():
     lib = B.abi()
     for name in ("cb200_engine_jacobian_multiply", "cb200_engine_jacobian_squared_column_norm",
