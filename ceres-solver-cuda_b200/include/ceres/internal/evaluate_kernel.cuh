@@ -319,6 +319,9 @@ __device__ __forceinline__ void CpAsyncWait() {
 #ifndef CB200_KERNEL_CHUNKED_EXCHANGE
 #define CB200_KERNEL_CHUNKED_EXCHANGE 1  // instantiate the chunked (multi-rank) kernel variant
 #endif
+#ifndef CB200_KERNEL_PEER_BULK_STORE
+#define CB200_KERNEL_PEER_BULK_STORE 1  // chunked kernel: exclusive ranges leave through TMA bulk stores
+#endif
 #ifndef CB200_KERNEL_SEGMENTED_GRADIENT
 #define CB200_KERNEL_SEGMENTED_GRADIENT 1  // warp-shuffle pre-reduction of long same-block runs
 #endif
@@ -1530,6 +1533,49 @@ __global__ void __launch_bounds__(
         __threadfence_block();
         __syncwarp();
         const int4 rec = __ldg(chunk_table + c0);
+#if CB200_KERNEL_PEER_BULK_STORE
+        // The range goes to the peers through the copy engine (one bulk store per peer and
+        // piece, shared -> peer memory over NVLink): stores issued by the lanes themselves sit
+        // in the SM's load/store queue until NVLink takes them and hold up every other warp's
+        // memory instructions behind them.  Staged in this tile's parameter rows, which are
+        // free until the next iteration's prefetch; 16-byte granularity, odd ends by lane 0/1.
+        if constexpr (kPrefetch && CB200_KERNEL_GATHER != 1) {
+          const int d0 = rec.z, d1 = rec.w;
+          const int a0 = (d0 + 1) & ~1, a1 = d1 & ~1;
+          if (lane == 0 && d0 < a0 && d0 < d1) {
+            const double v = __ldcg(a.gradient + d0);
+            for (int q = 0; q < a.num_peers; ++q) __stcg(a.peer_gradient[q] + d0, v);
+          }
+          if (lane == 1 && a1 < d1 && a1 >= a0 && a1 >= d0) {
+            const double v = __ldcg(a.gradient + a1);
+            for (int q = 0; q < a.num_peers; ++q) __stcg(a.peer_gradient[q] + a1, v);
+          }
+          double* const piece = const_cast<double*>(stage_params(stage));
+          constexpr int kCapacity = (32 * (Smem::kParamBytes / 8)) & ~1;
+          for (int base = a0; base < a1; base += kCapacity) {
+            const int count = min(kCapacity, a1 - base);
+            for (int i0 = lane; i0 < count; i0 += 128) {
+              double v[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                v[u] = i0 + 32 * u < count ? __ldcg(a.gradient + base + i0 + 32 * u) : 0.0;
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (i0 + 32 * u < count) piece[i0 + 32 * u] = v[u];
+            }
+            FenceProxyAsyncShared();
+            __syncwarp();
+            if (lane == 0) {
+              for (int q = 0; q < a.num_peers; ++q)
+                BulkStore(a.peer_gradient[q] + base, piece, static_cast<unsigned>(count) * 8u);
+              BulkCommit();
+              BulkWaitRead();  // (also covers this tile's Jacobian stores: their stage is free)
+            }
+            __syncwarp();
+            bulk_pending = false;
+          }
+        } else
+#endif
         // four independent loads in flight per lane: the loop is latency bound otherwise
         for (int i0 = rec.z + lane; i0 < rec.w; i0 += 128) {
           double v[4];
@@ -1551,7 +1597,8 @@ __global__ void __launch_bounds__(
     }
   }
   if constexpr (kPrefetch) CpAsyncWait<0>();
-  if (bulk_pending && lane == 0) BulkWaitAll();
+  // (the chunked variant may have peer copies in flight whose staging was already released)
+  if ((bulk_pending || kChunked) && lane == 0) BulkWaitAll();
 
   if (!all_ok) *a.status = 1;
 
