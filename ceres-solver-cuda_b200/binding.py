@@ -107,6 +107,8 @@ def driver():
                                    C.c_void_p, C.c_int]
         L.drv_evaluate_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.drv_timing.argtypes = [C.c_void_p, C.c_void_p]
+        L.drv_evaluate_device_steps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.drv_shard_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.drv_callback_info.argtypes = [C.c_void_p, C.c_void_p]
         L.drv_exchange_mode.argtypes = [C.c_void_p]
@@ -311,6 +313,18 @@ class CudaProblem:
         if rc < 0:
             raise RuntimeError(f"evaluate_device failed ({rc})")
         return rc == 0, float(cost[0])
+
+    def evaluate_device_steps(self, steps, residuals=True, gradient=True, jacobian=True,
+                              apply_loss_function=True):
+        """`steps` evaluations at the resident state, back to back inside the driver (no
+        interpreter time between them).  Returns (ok, cost, kernel_ms[steps], device_ms[steps])."""
+        cost, kernel_ms, device_ms = np.zeros(1), np.zeros(steps), np.zeros(steps)
+        rc = driver().drv_evaluate_device_steps(
+            self.h, int(steps), int(apply_loss_function), int(residuals), int(gradient),
+            int(jacobian), _p(kernel_ms), _p(device_ms), _p(cost))
+        if rc < 0:
+            raise RuntimeError(f"evaluate_device_steps failed ({rc})")
+        return rc == 0, float(cost[0]), kernel_ms, device_ms
 
     # ---- Problem::Evaluate / Problem::EvaluateResidualBlock (the user-level entry points)
     def problem_evaluate(self, parameter_blocks=None, residual_blocks=None,

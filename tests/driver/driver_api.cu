@@ -274,6 +274,29 @@ int drv_evaluate_device(void* h, int apply_loss_function, int want_residuals, in
                                       want_residuals, want_gradient, want_jacobian, cost);
 }
 
+// `steps` back-to-back calls of cb200_engine_evaluate_device (each one a complete evaluation:
+// launches, cost read back, stream synchronised) with the per-call timings of
+// cb200_engine_last_timing collected on the way - bench.py's timed loop without an
+// interpreter round trip per step.  Returns the last call's status.
+int drv_evaluate_device_steps(void* h, int steps, int apply_loss_function, int want_residuals,
+                              int want_gradient, int want_jacobian, double* kernel_ms,
+                              double* device_ms, double* cost) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  if (!dp->evaluator) return -1;
+  int rc = 0;
+  for (int k = 0; k < steps; ++k) {
+    rc = cb200_engine_evaluate_device(dp->evaluator->engine(), nullptr, nullptr,
+                                      apply_loss_function ? CB200_APPLY_LOSS_FUNCTION : 0u,
+                                      want_residuals, want_gradient, want_jacobian, cost);
+    if (rc < 0) return rc;
+    double t[4] = {0, 0, 0, 0};
+    cb200_engine_last_timing(dp->evaluator->engine(), t);
+    if (kernel_ms) kernel_ms[k] = t[0];
+    if (device_ms) device_ms[k] = t[1];
+  }
+  return rc;
+}
+
 // Problem::Evaluate through ProblemCUDA's wrapped Problem.  parameter_blocks / residual_blocks
 // are ids in creation order (NULL = all).  dims: [num_residuals, num_gradient, num_rows,
 // num_cols, num_nonzeros]; the arrays are then fetched with drv_problem_evaluate_get.
