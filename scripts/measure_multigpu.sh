@@ -1,3 +1,7 @@
+#!/bin/bash
+# Multi-GPU check and bench on N GPUs of one box (gpurun --gpus N): sharded vs unsharded
+# evaluation at 5 % scale, then bench.py; `all` as second argument also times the separate-push
+# exchange.   usage: measure_multigpu.sh <N> [all]
 cd /root/repo
 export MASTER_ADDR=127.0.0.1
 N=${1:-2}
