@@ -129,6 +129,7 @@ def driver():
                                      C.c_double, C.c_void_p, C.c_void_p]
         L.drv_user_values.argtypes = [C.c_void_p, C.c_void_p]
         L.drv_options_is_valid.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+        L.drv_argument_slot_ordering.argtypes = [C.c_void_p, C.c_void_p]
         _DRV = L
     return _DRV
 
@@ -185,6 +186,24 @@ def solve(spec, linear_solver_type=ITERATIVE_SCHUR, max_num_iterations=20, order
                 jacobian_evaluations=int(out[5]), residual_evaluations=int(out[6]),
                 linear_solver_seconds=float(out[7]), message=msg,
                 x=x)
+
+
+def argument_slot_ordering(spec):
+    """internal::ArgumentSlotOrdering on the ProblemSpec (host code, no GPU): (found, group per
+    parameter block)."""
+    L = driver()
+    h = L.drv_create(
+        spec.num_pb, _p(spec.pb_size), _p(spec.pb_values), _p(spec.pb_constant),
+        _p(spec.pb_manifold_kind), _p(spec.pb_manifold_param), spec.num_rb,
+        _p(spec.rb_type), _p(spec.rb_pb), _p(spec.rb_loss_kind), _p(spec.rb_loss_a),
+        _p(spec.rb_loss_b), _p(spec.fdata), 0)
+    err = L.drv_error(h)
+    if err:
+        raise RuntimeError(err.decode())
+    groups = np.zeros(spec.num_pb, dtype=np.int32)
+    found = L.drv_argument_slot_ordering(h, _p(groups))
+    L.drv_destroy(h)
+    return bool(found), groups
 
 
 def options_is_valid(spec, minimizer_type):

@@ -361,6 +361,38 @@ void MinimizeOnDevice(const Solver::Options& options, cb200_engine* engine, doub
 }
 }  // namespace
 
+namespace internal {
+// The parameter blocks that only ever appear as argument j of their residual blocks form an
+// independent set: every residual block holds exactly one of them (the points of a bundle
+// adjustment problem for j = 1).  Puts them in group 0 and everything else in group 1 for the
+// argument slot with the most such blocks; false when no slot covers half of the variable
+// blocks (a small first group is not worth its own region of the Jacobian).
+bool ArgumentSlotOrdering(const ProblemImpl& problem, ParameterBlockOrdering* ordering) {
+  const auto& pbs = problem.parameter_blocks();
+  std::vector<uint32_t> slots(pbs.size(), 0u);
+  int common_slots = CB200_MAX_PARAMETER_BLOCKS;
+  for (const ResidualTypeStore& t : problem.types()) {
+    const int nb = t.desc.num_parameter_blocks;
+    if (t.size() == 0) continue;
+    common_slots = std::min(common_slots, nb);
+    for (size_t k = 0; k < t.parameter_blocks.size(); ++k)
+      slots[t.parameter_blocks[k]] |= 1u << (k % nb);
+  }
+  int best_slot = -1;
+  size_t best_count = 0, variable = 0;
+  for (size_t i = 0; i < pbs.size(); ++i) variable += !pbs[i]->IsConstant();
+  for (int j = 0; j < common_slots; ++j) {
+    size_t count = 0;
+    for (size_t i = 0; i < pbs.size(); ++i) count += slots[i] == (1u << j) && !pbs[i]->IsConstant();
+    if (count > best_count) { best_count = count; best_slot = j; }
+  }
+  if (best_slot < 0 || 2 * best_count < variable) return false;
+  for (size_t i = 0; i < pbs.size(); ++i)
+    ordering->AddElementToGroup(pbs[i]->user_state, slots[i] == (1u << best_slot) ? 0 : 1);
+  return true;
+}
+}  // namespace internal
+
 void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
   const double start = Seconds();
   *summary = Summary();
@@ -408,37 +440,11 @@ void Solver::Solve(const Options& options, Problem* problem, Summary* summary) {
   const bool resident_cgnr = options.linear_solver_type == CGNR &&
                              options.sparse_linear_algebra_library_type == CUDA_SPARSE;
   const ParameterBlockOrdering* ordering = options.linear_solver_ordering.get();
-  // No ordering given for the resident layout: the parameter blocks that only ever appear as
-  // argument j of their residual blocks (the points of a bundle adjustment problem for j = 1)
-  // form an independent set - every residual block holds exactly one of them - and become
-  // the first group; j is the argument slot with the most such blocks.
+  // No ordering given for the resident layout: the argument-slot independent set (above)
+  // becomes the first group.
   ParameterBlockOrdering slot_ordering;
-  if (resident_cgnr && !ordering) {
-    const auto& pbs = impl->parameter_blocks();
-    std::vector<uint32_t> slots(pbs.size(), 0u);
-    int common_slots = CB200_MAX_PARAMETER_BLOCKS;
-    for (const internal::ResidualTypeStore& t : impl->types()) {
-      const int nb = t.desc.num_parameter_blocks;
-      if (t.size() == 0) continue;
-      common_slots = std::min(common_slots, nb);
-      for (size_t k = 0; k < t.parameter_blocks.size(); ++k)
-        slots[t.parameter_blocks[k]] |= 1u << (k % nb);
-    }
-    int best_slot = -1;
-    size_t best_count = 0;
-    for (int j = 0; j < common_slots; ++j) {
-      size_t count = 0;
-      for (size_t i = 0; i < pbs.size(); ++i) count += slots[i] == (1u << j) && !pbs[i]->IsConstant();
-      if (count > best_count) { best_count = count; best_slot = j; }
-    }
-    size_t variable = 0;
-    for (size_t i = 0; i < pbs.size(); ++i) variable += !pbs[i]->IsConstant();
-    if (best_slot >= 0 && 2 * best_count >= variable) {  // (a small set is not worth a region)
-      for (size_t i = 0; i < pbs.size(); ++i)
-        slot_ordering.AddElementToGroup(pbs[i]->user_state, slots[i] == (1u << best_slot) ? 0 : 1);
-      ordering = &slot_ordering;
-    }
-  }
+  if (resident_cgnr && !ordering && internal::ArgumentSlotOrdering(*impl, &slot_ordering))
+    ordering = &slot_ordering;
   int num_eliminate_blocks = 0;
   if ((schur || resident_cgnr) && ordering) {
     // ApplyOrdering + size of the first elimination group (reorder_program.cc:469-560).

@@ -60,6 +60,13 @@ class ParameterBlockOrdering {
   std::unordered_map<const double*, int> groups_;
 };
 
+namespace internal {
+class ProblemImpl;
+// Two-group ordering from the argument slots of the residual blocks (csrc/solver.cc): used for
+// the device-resident Jacobian layout when the caller gives no linear_solver_ordering.
+bool ArgumentSlotOrdering(const ProblemImpl& problem, ParameterBlockOrdering* ordering);
+}  // namespace internal
+
 enum TerminationType { CONVERGENCE, NO_CONVERGENCE, FAILURE, USER_SUCCESS, USER_FAILURE };
 
 class Solver {

@@ -478,6 +478,19 @@ int drv_options_is_valid(void* h, int minimizer_type, char* msg, int msg_size) {
   return ok ? 1 : 0;
 }
 
+// internal::ArgumentSlotOrdering (the resident Jacobian's two-region layout when the caller gives
+// no ordering): group per parameter block in creation order, -1 when the block got none.
+// Returns 1 when an ordering was found.  Host code only.
+int drv_argument_slot_ordering(void* h, int* groups) {
+  auto* dp = static_cast<DriverProblem*>(h);
+  ceres::ParameterBlockOrdering ordering;
+  const bool found = ceres::internal::ArgumentSlotOrdering(
+      *dp->problem.mutable_problem()->mutable_impl(), &ordering);
+  for (size_t k = 0; k < dp->pb_offset.size(); ++k)
+    groups[k] = found ? ordering.GroupId(dp->pb(static_cast<int>(k))) : -1;
+  return found ? 1 : 0;
+}
+
 void drv_user_values(void* h, double* out) {
   auto* dp = static_cast<DriverProblem*>(h);
   std::memcpy(out, dp->values.data(), dp->values.size() * sizeof(double));

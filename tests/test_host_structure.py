@@ -208,3 +208,38 @@ def test_random_mixed_problems_values(seed):
             assert np.max(np.abs(g - g_o), initial=0.0) <= 1e-10 * scale(g_o)
             n = op.num_jacobian_values
             assert np.max(np.abs(j[:n] - j_o[:n]), initial=0.0) <= 1e-12 * scale(j_o[:n])
+
+
+def test_argument_slot_ordering_finds_the_points():
+    """ceres::Solve keeps the Jacobian of CGNR + CUDA_SPARSE in HBM in a two-region layout.
+    Without a linear_solver_ordering the first region is the set of parameter blocks that only
+    appear in one argument slot (internal::ArgumentSlotOrdering): the points of a bundle
+    adjustment problem, constant blocks aside; a pose graph, whose poses appear in both slots,
+    gets no ordering and keeps the row-by-row layout."""
+    spec = P.bal_problem(9, 300, 1400, seed=3, constant_cameras=1)
+    found, groups = B.argument_slot_ordering(spec)
+    assert found
+    sizes = np.asarray(spec.pb_size)
+    assert np.all(groups[sizes == 3] == 0) and np.all(groups[sizes == 9] == 1)
+
+    pose = P.pose_graph_problem(60, 200, seed=2)
+    found, groups = B.argument_slot_ordering(pose)
+    assert not found and np.all(groups == -1)
+
+    # several residual-block types: the same rule restated in numpy
+    mixed = P.evaluator_cuda_test_problem()
+    found, groups = B.argument_slot_ordering(mixed)
+    slots, at = {}, 0
+    common = min(len(P.COST_TYPES[int(t)][1]) for t in mixed.rb_type)
+    for t in mixed.rb_type:
+        nb = len(P.COST_TYPES[int(t)][1])
+        for j, i in enumerate(mixed.rb_pb[at:at + nb]):
+            slots[int(i)] = slots.get(int(i), 0) | (1 << j)
+        at += nb
+    variable = [i for i in range(mixed.num_pb) if not mixed.pb_constant[i]]
+    counts = [sum(1 for i in variable if slots.get(i, 0) == (1 << j)) for j in range(common)]
+    best = int(np.argmax(counts))
+    assert found == (2 * counts[best] >= len(variable))
+    if found:
+        expect = np.array([0 if slots.get(i, 0) == (1 << best) else 1 for i in range(mixed.num_pb)])
+        assert np.array_equal(groups, expect)
