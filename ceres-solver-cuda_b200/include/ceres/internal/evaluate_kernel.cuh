@@ -857,7 +857,7 @@ __global__ void __launch_bounds__(
         // needed for a whole iteration.  Fetched before, ptxas keeps the loaded value in a
         // temporary and moves it into the loop-carried register at once, i.e. it waits for
         // a load it issued ~40 instructions earlier (one fifth of the kernel's stall
-        // samples, profiles/r2_L_ncu_summary.txt).
+        // samples, profiles/r2_v10_offset_load_stall.txt).
         load_offsets(kChunked ? walk_rb(walk) : rb + 2 * stride, soff_next);
       }
       issued = true;
