@@ -782,9 +782,14 @@ __global__ void __launch_bounds__(
   const int4* const chunk_table = reinterpret_cast<const int4*>(a.chunks);
   auto load_chunk = [&](Walk& w) {
     if (w.c < a.num_chunks) {
-      const int4 rec = __ldg(chunk_table + w.c);
-      w.lo = rec.x;
-      w.hi = rec.y;
+      if (chunk_table) {
+        const int4 rec = __ldg(chunk_table + w.c);
+        w.lo = rec.x;
+        w.hi = rec.y;
+      } else {  // uniform chunks, nothing to copy (cb200_launch_args::chunk_blocks)
+        w.lo = w.c * a.chunk_blocks;
+        w.hi = min(n, w.lo + a.chunk_blocks);
+      }
     } else {
       w.lo = w.hi = n;
     }
@@ -1525,7 +1530,7 @@ __global__ void __launch_bounds__(
       // any rank, adds to it).  Make this warp's reductions visible, then copy the range
       // into every other rank's gradient buffer; meanwhile the other warps of this SM keep
       // evaluating.
-      if (warp_rb + 32 >= limit) {
+      if (warp_rb + 32 >= limit && a.num_peers > 0) {
         // The range was added to by this warp's lanes only: ordering among them is all the
         // reads below need (a device-wide fence here waited for every red of the chunk to be
         // acknowledged, once per chunk and warp).  The peers read the copies after the
@@ -1665,7 +1670,7 @@ int LaunchEvaluate(const cb200_launch_args* args, void* stream) {
 #if CB200_KERNEL_SPECIALISE_ALL_OUTPUTS
   if (all && args->plain && !args->crs) {
 #if CB200_KERNEL_CHUNKED_EXCHANGE
-    if (args->chunks && (args->affine & kAffinePlain) == kAffinePlain)
+    if ((args->chunks || args->num_chunks > 0) && (args->affine & kAffinePlain) == kAffinePlain)
       return LaunchVariant(
           EvaluateKernel<kVariantPlainAll, true, true, Functor, Loss, kRes, Ns...>, kAffineCtas,
           Computed::kJetBytes, args, s,

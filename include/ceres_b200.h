@@ -134,6 +134,11 @@ typedef struct cb200_launch_args {
   const int32_t* chunks;
   int32_t num_chunks;
   int32_t num_peers;
+  /* chunks == NULL and num_chunks > 0: the same warp-private walk over uniform chunks of
+   * chunk_blocks residual blocks (a multiple of 32), nothing copied - on large problems the
+   * walk itself is ~2 % faster than the grid stride (profiles/r2_kbench_variants.txt). */
+  int32_t chunk_blocks;
+  int32_t reserved1;
   double* peer_gradient[CB200_MAX_PEERS];
   /* A copy of the loss object when the type has exactly one (loss_index == NULL) and it fits:
    * kernel arguments live in the constant bank, so the kernel reads the loss parameters as

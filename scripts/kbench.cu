@@ -137,6 +137,7 @@ int main(int argc, char** argv) {
       table.push_back(copy ? (hi < n ? soff[(size_t)n + hi] : 3 * np) : 0);
     }
     a.chunks = Upload(table); a.num_chunks = (int)(table.size() / 4); a.num_peers = 0;
+    if (std::getenv("KBENCH_UNIFORM")) { a.chunks = nullptr; a.chunk_blocks = chunk; }  // table-free form
     if (const char* pe = std::getenv("KBENCH_PEERS")) {
       a.num_peers = std::atoi(pe);
       for (int q = 0; q < a.num_peers; ++q) CK(cudaMalloc(&a.peer_gradient[q], 8 * state.size()));
