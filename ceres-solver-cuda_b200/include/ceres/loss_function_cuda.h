@@ -78,7 +78,12 @@ class HuberLossCUDA : public LossFunctionCUDABase {
     }
     double root, inv_root;
     loss_internal::RootAndReciprocal(s, &root, &inv_root);
+#ifdef __CUDA_ARCH__
     const double slope = loss_internal::AtLeastTiny(a_ * inv_root);
+#else
+    // (host evaluation, e.g. Problem::EvaluateResidualBlock: the reference's expression)
+    const double slope = loss_internal::AtLeastTiny(a_ / root);
+#endif
     loss_internal::Set(rho, 2.0 * a_ * root - b_, slope, -slope / (2.0 * s));
   }
 
